@@ -1,0 +1,133 @@
+/* rtts_b200.h - C ABI of libreformer_b200.so: the sm_100a kernels behind Reformer-TTS's LSH-attention /
+ * reversible / chunked-FFN hot path.
+ *
+ * The reference has no native boundary for this path (pure Python); the functions
+ * below are what a binding for it would call - each one replaces the run of ATen library launches the
+ * cited reference lines issue.  `ref:` = kowaalczyk/reformer-tts, `rp:` = reformer-pytorch 0.19.1
+ * (rows R1-R11 of SURVEY.md 8(a)), `hf:` = transformers modeling_reformer.py (5.5.0 line numbers).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; the library never allocates,
+ *    frees or retains memory: outputs and workspaces are caller-owned.
+ *  - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it.
+ *  - return 0 on success, negative on error; rtts_last_error() gives a thread-local message.
+ *  - activations: bf16 row-major [B, T, H*dh] ("token-major", heads side by side, leading
+ *    dimension ld in elements); integer tensors int32; accumulators / statistics fp32.
+ *  - no global mutable state; re-entrant; one CUDA context per process.
+ */
+#ifndef RTTS_B200_H
+#define RTTS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTTS_KEYNORM_L2 0  /* rp R5: x / max(|x|_2, 1e-12)                     */
+#define RTTS_KEYNORM_RMS 1 /* hf:1042-1056: x * rsqrt(mean(x^2)+1e-6) / sqrt(dh) */
+#define RTTS_MASK_QUERY_AND_KEY 0 /* rp R8 */
+#define RTTS_MASK_KEY_ONLY 1      /* hf:914-922 */
+
+/* Constants that differ between the two LSH implementations the reference can select
+ * (ref:reformer_tts/model/reformer.py:198-213). */
+typedef struct rtts_lsh_spec {
+  float score_scale; /* rp R7: dh^-0.5 ; hf: 1 */
+  int32_t key_norm;  /* RTTS_KEYNORM_* */
+  float mask_value;  /* rp R8: -FLT_MAX ; hf:431: -1e9 */
+  float self_value;  /* rp R8: -5e4     ; hf:430: -1e5 */
+  int32_t mask_mode; /* RTTS_MASK_* */
+  int32_t causal;    /* ref:reformer_tts/model/reformer.py:68,117 */
+} rtts_lsh_spec;
+
+const char* rtts_last_error(void);
+int rtts_abi_version(void);
+
+/* ---- LSH bucketing --------------------------------------------------------------------------- */
+
+/* Random-rotation hash + argmax + round offsets (rp R2; hf:717-758; replaces randn-einsum-cat-argmax).
+ * qk bf16 [B,T,H*dh] (ld elements per token), rot fp32 [rot_heads, dh, R, n_buckets/2] with rot_heads
+ * = 1 (rp: shared) or H (hf: per head).  pad_mask uint8 [B,T] (1 = real token) or NULL; when
+ * use_pad_bucket != 0 padded tokens get bucket n_buckets and the round stride is n_buckets+1 (hf:740-747).
+ * buckets int32 [B,H,R*T] (value = round*stride + id).  Arithmetic: fp32 FMA on the bf16 inputs. */
+int rtts_lsh_hash(const void* qk, int64_t ld, const float* rot, int rot_heads, const uint8_t* pad_mask,
+                  int use_pad_bucket, int32_t* buckets, int B, int T, int H, int dh, int R, int n_buckets,
+                  void* stream);
+
+/* Stable sort by (bucket, position) per (batch*head) row, and its inverse (rp R3; hf:150-156,762-779).
+ * sticker[i] = round*T + pos sitting at sorted slot i; undo[sticker[i]] = i.  ids_per_round = round
+ * stride used by rtts_lsh_hash (n_buckets or n_buckets+1).  Bit-exact with torch.sort of T*bucket+pos. */
+int rtts_lsh_sort(const int32_t* buckets, int32_t* sticker, int32_t* undo, int rows, int T, int R,
+                  int ids_per_round, void* stream);
+
+/* ---- chunked shared-QK attention ------------------------------------------------------------- */
+
+/* Gather by sticker, key normalisation, look-one-back, QK^T, masks, softmax, PV and un-sort in one
+ * kernel (rp R4-R10; hf:563-599,801-906,1067-1096).  bucket in {64,128}, dh = 64, T % 128 == 0.
+ * mask uint8 [B,T] (1 = real token) or NULL.  Outputs, already UNSORTED:
+ *   o_rounds bf16 [B,H,R,T,dh], lse_rounds fp32 [B,H,R,T]. */
+int rtts_lsh_attn_fwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
+                      const rtts_lsh_spec* spec_host, void* o_rounds, float* lse_rounds, int B, int T, int H,
+                      int dh, int R, int bucket, void* stream);
+
+/* Combine hash rounds (rp R11; hf:626-645): out bf16 [B,T,H*dh] (ld_out), lse fp32 [B,H,T] = logsumexp_r. */
+int rtts_lsh_merge_fwd(const void* o_rounds, const float* lse_rounds, void* out, int64_t ld_out, float* lse,
+                       int B, int T, int H, int dh, int R, void* stream);
+
+/* delta[b,h,t] = <dout[b,t,h,:], out[b,t,h,:]> (fp32), the per-query term of the attention backward. */
+int rtts_lsh_delta(const void* dout, const void* out, int64_t ld, float* delta, int B, int T, int H, int dh,
+                   void* stream);
+
+/* Backward of rtts_lsh_attn_fwd + rtts_lsh_merge_fwd with in-kernel recompute of the scores
+ * (autograd of rp R4-R11).  Inputs: qk, v, sticker, mask as in forward; dout bf16 [B,T,H*dh];
+ * lse [B,H,T] and delta [B,H,T] from the two calls above.  Outputs per sorted slot, scattered to
+ * UNSORTED [B,H,R,T,dh] fp32 layout: dq_rounds (query role), dk_rounds (key role, before the
+ * normalisation Jacobian), dv_rounds.  dk/dv hold the sum over both appearances of a key (own chunk
+ * and look-back of the next chunk) when `spill` buffers of the same shape are reduced with them by
+ * rtts_lsh_grad_reduce. */
+int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
+                      const rtts_lsh_spec* spec_host, const void* dout, const float* lse, const float* delta,
+                      float* dq_rounds, float* dk_rounds, float* dv_rounds, int B, int T, int H, int dh, int R,
+                      int bucket, void* stream);
+
+/* Sum the per-round gradients over rounds, apply the key-normalisation Jacobian and emit
+ * dqk bf16 [B,T,H*dh], dv bf16 [B,T,H*dh]. */
+int rtts_lsh_grad_reduce(const void* qk, int64_t ld, const float* dq_rounds, const float* dk_rounds,
+                         const float* dv_rounds, const rtts_lsh_spec* spec_host, void* dqk, void* dv, int B, int T,
+                         int H, int dh, int R, void* stream);
+
+/* ---- LayerNorm (ref:reformer_tts/model/reformer.py:25-33, eps 1e-5, affine) -------------------- */
+
+/* x fp32 [rows, dim] -> y bf16 [rows, dim]; saves mean / rstd fp32 [rows] when non-NULL. */
+int rtts_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                       int rows, int dim, float eps, void* stream);
+/* dy fp32 [rows, dim] (gradient w.r.t. the normalised, affine output) -> dx fp32; dgamma/dbeta fp32 [dim]
+ * are ACCUMULATED (+=) so they can point at parameter .grad buffers. */
+int rtts_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       float* dx, float* dgamma, float* dbeta, int rows, int dim, void* stream);
+
+/* ---- GEMM with fused epilogue (projections rp R1, FeedForward ref:reformer_tts/model/modules.py:195-207) */
+
+#define RTTS_EPI_BIAS 1      /* + bias[n] (fp32)                         */
+#define RTTS_EPI_RELU 2      /* max(., 0)                                */
+#define RTTS_EPI_GATE 4      /* * (gate[m,n] > 0), gate bf16 (ReLU bwd)  */
+#define RTTS_EPI_OUT_BF16 8  /* C is bf16 (else fp32)                    */
+#define RTTS_EPI_ATOMIC 16   /* C (fp32) += result, split-K allowed      */
+#define RTTS_EPI_COLSUM 32   /* also accumulate column sums into colsum  */
+
+/* C[M,N] = epilogue(A . B^T).  Operands bf16, fp32 accumulate in TMEM (tcgen05).
+ * a_mn_major = 0: A is [M,K] row-major (lda = K stride); 1: A is stored [K,M] row-major.
+ * b_mn_major = 0: B is [N,K] row-major (an nn.Linear weight); 1: B is stored [K,N] row-major.
+ * M % 128 == 0, N % 128 == 0, K % 64 == 0.  split_k >= 1 requires RTTS_EPI_ATOMIC when > 1. */
+int rtts_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
+                   int64_t ldc, const float* bias, const void* gate, int64_t ldgate, float* colsum, int M, int N,
+                   int K, int epilogue, int split_k, void* stream);
+
+/* ---- small fused element-wise helpers used by the host mirror -------------------------------- */
+
+/* fp32 -> bf16 cast with optional column-sum accumulation (bias gradients): colsum fp32 [cols] += sum_rows. */
+int rtts_cast_bf16_colsum(const float* x, void* y, float* colsum, int rows, int cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTTS_B200_H */

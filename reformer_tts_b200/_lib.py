@@ -1,0 +1,65 @@
+"""ctypes binding of libreformer_b200.so (the C ABI declared in include/rtts_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+Build it with ``python reformer_tts_b200/csrc/build.py`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libreformer_b200.so"
+
+
+class LSHSpecStruct(ctypes.Structure):
+    """Mirror of ``rtts_lsh_spec``."""
+    _fields_ = [("score_scale", c_float), ("key_norm", c_int32), ("mask_value", c_float), ("self_value", c_float),
+                ("mask_mode", c_int32), ("causal", c_int32)]
+
+
+_P, _I, _L, _F = c_void_p, c_int, c_int64, c_float
+_SPEC = POINTER(LSHSpecStruct)
+
+# name -> argtypes, in header order
+SIGNATURES = {
+    "rtts_lsh_hash": [_P, _L, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "rtts_lsh_sort": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "rtts_lsh_attn_fwd": [_P, _P, _L, _P, _P, _SPEC, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "rtts_lsh_merge_fwd": [_P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P],
+    "rtts_lsh_delta": [_P, _P, _L, _P, _I, _I, _I, _I, _P],
+    "rtts_lsh_attn_bwd": [_P, _P, _L, _P, _P, _SPEC, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "rtts_lsh_grad_reduce": [_P, _L, _P, _P, _P, _P, _SPEC, _P, _P, _I, _I, _I, _I, _I, _P],
+    "rtts_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "rtts_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "rtts_gemm_bf16": [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P],
+    "rtts_cast_bf16_colsum": [_P, _P, _P, _I, _I, _P],
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: the CUDA extension is not built and there is no fallback path. "
+                               "Run `python reformer_tts_b200/csrc/build.py`.")
+        lib = ctypes.CDLL(str(LIB_PATH))
+        lib.rtts_last_error.restype = c_char_p
+        lib.rtts_last_error.argtypes = []
+        lib.rtts_abi_version.restype = c_int
+        lib.rtts_abi_version.argtypes = []
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here = header / library mismatch: fail loudly
+            fn.restype = c_int
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.rtts_last_error().decode()}")

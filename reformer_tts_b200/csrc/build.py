@@ -1,0 +1,52 @@
+"""Build libreformer_b200.so in-tree with nvcc for sm_100a (no torch headers: the library is a plain C ABI)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+LIB = HERE.parent / "libreformer_b200.so"
+SOURCES = ["api.cu", "lsh_bucket.cu", "lsh_attn_fwd.cu", "lsh_attn_bwd.cu", "gemm.cu", "rowwise.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",
+         "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"), "-I", str(HERE)]
+
+
+def _stale(obj: Path, src: Path) -> bool:
+    if not obj.exists():
+        return True
+    newest = max(p.stat().st_mtime for p in [src, *HERE.glob("*.cuh"), *HERE.glob("*.h"), ROOT / "include" / "rtts_b200.h"])
+    return obj.stat().st_mtime < newest
+
+
+def build(verbose: bool = False, force: bool = False) -> Path:
+    objs = []
+    procs = []
+    for name in SOURCES:
+        src = HERE / name
+        if not src.exists():
+            continue
+        obj = HERE / "build" / (name + ".o")
+        obj.parent.mkdir(exist_ok=True)
+        objs.append(obj)
+        if force or _stale(obj, src):
+            cmd = [NVCC, *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", str(src), "-o", str(obj)]
+            procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for name, proc in procs:
+        out, _ = proc.communicate()
+        if verbose or proc.returncode:
+            print(f"--- {name}\n{out}", file=sys.stderr)
+        failed |= proc.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    if procs or not LIB.exists():
+        subprocess.check_call([NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

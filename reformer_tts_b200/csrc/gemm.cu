@@ -1,0 +1,277 @@
+// bf16 GEMM with fused epilogue on tcgen05 (rtts_gemm_bf16): projections (rp R1), FeedForward
+// (ref:reformer_tts/model/modules.py:195-207) and their backward (dgrad / wgrad, split-K atomic).
+//
+// C[M,N] = epilogue(A . B^T), 128x128 output tile per CTA, K consumed in 64-wide blocks through a
+// 3-stage TMA -> shared-memory ring (SWIZZLE_128B), accumulator in TMEM (128 fp32 columns), so two
+// CTAs fit per SM and one CTA's epilogue overlaps the other's main loop.
+//   warp 0    : TMA producer (one elected lane)
+//   warp 1    : tcgen05.mma issuer (one elected lane)
+//   warps 2-5 : epilogue, one TMEM lane quarter each: tcgen05.ld -> bias / ReLU / gate / cast -> global
+// Operands may be K-major (row-major [rows, K]) or MN-major (stored [K, rows]); the latter is what the
+// weight-gradient GEMM dW = dY^T X needs, and is loaded as two 64-wide boxes per 128-row tile.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "host_util.h"
+#include "rtts_b200.h"
+
+namespace rtts {
+
+constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3;
+constexpr int kTileBytes = 128 * kBK * 2;                     // 16 KB per operand per stage
+constexpr int kGemmThreads = 192;
+constexpr int kGemmSmem = kStages * 2 * kTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  void* C;
+  int64_t ldc;
+  const float* bias;
+  const __nv_bfloat16* gate;
+  int64_t ldgate;
+  float* colsum;
+  int M, N, K;       // K = per-split extent
+  int epilogue;
+};
+
+// Sum r[0..32) over the 32 lanes of a warp; lane i ends up owning column i's total.
+__device__ __forceinline__ float warp_column_sums(float* r, int lane) {
+#pragma unroll
+  for (int width = 16; width >= 1; width >>= 1) {
+    const bool upper = (lane & width) != 0;
+#pragma unroll
+    for (int i = 0; i < width; ++i) {
+      const float send = upper ? r[i] : r[i + width];
+      const float keep = upper ? r[i + width] : r[i];
+      r[i] = keep + __shfl_xor_sync(0xffffffffu, send, width);
+    }
+  }
+  return r[0];
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                 const __grid_constant__ CUtensorMap tmap_b,
+                                                                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t s_base = smem_u32(smem);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * 2 * kTileBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* accum_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;
+  const int k_begin = blockIdx.z * p.K;
+  const int num_kb = p.K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kBN);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(empty_bar + s, ((kb / kStages) & 1) ^ 1);
+        const uint32_t sa = s_base + s * 2 * kTileBytes, sb = sa + kTileBytes;
+        const int k0 = k_begin + kb * kBK;
+        mbar_arrive_expect_tx(full_bar + s, 2 * kTileBytes);
+        if (A_MN) {
+          tma_load_2d(sa, &tmap_a, full_bar + s, m0, k0);
+          tma_load_2d(sa + kTileBytes / 2, &tmap_a, full_bar + s, m0 + 64, k0);
+        } else {
+          tma_load_2d(sa, &tmap_a, full_bar + s, k0, m0);
+        }
+        if (B_MN) {
+          tma_load_2d(sb, &tmap_b, full_bar + s, n0, k0);
+          tma_load_2d(sb + kTileBytes / 2, &tmap_b, full_bar + s, n0 + 64, k0);
+        } else {
+          tma_load_2d(sb, &tmap_b, full_bar + s, k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, A_MN, B_MN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(full_bar + s, (kb / kStages) & 1);
+        tc_fence_after_sync();
+        const uint32_t sa = s_base + s * 2 * kTileBytes, sb = sa + kTileBytes;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t da = A_MN ? umma_desc_sw128(sa + k * 2048, kTileBytes / 2, 1024) : umma_desc_sw128(sa + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, kTileBytes / 2, 1024) : umma_desc_sw128(sb + k * 32, 16, 1024);
+          umma_ss(tmem, da, db, idesc, (kb | k) != 0);
+        }
+        umma_commit(empty_bar + s);          // smem slot reusable once these MMAs retire
+      }
+      umma_commit(accum_bar);                // accumulator complete
+    }
+  } else {
+    // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = output rows m0 + that range ----
+    const int quarter = warp & 3;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after_sync();
+    const int row = m0 + quarter * 32 + lane;
+    const int epi = p.epilogue;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kBN; c0 += 32) {
+      uint32_t raw[32];
+      tmem_ld32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + c0, raw);
+      tmem_ld_wait();
+      float r[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(raw[i]);
+      const int col = n0 + c0;
+      if (epi & RTTS_EPI_BIAS) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+          r[i] += bv.x; r[i + 1] += bv.y; r[i + 2] += bv.z; r[i + 3] += bv.w;
+        }
+      }
+      if (epi & RTTS_EPI_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = fmaxf(r[i], 0.f);
+      }
+      if (epi & RTTS_EPI_GATE) {
+        const uint4* g = reinterpret_cast<const uint4*>(p.gate + static_cast<int64_t>(row) * p.ldgate + col);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 u = __ldg(g + q);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (!(bf16_lo(w[e]) > 0.f)) r[q * 8 + 2 * e] = 0.f;
+            if (!(bf16_hi(w[e]) > 0.f)) r[q * 8 + 2 * e + 1] = 0.f;
+          }
+        }
+      }
+      if (epi & RTTS_EPI_OUT_BF16) {
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + col);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16(r[q * 8 + 0], r[q * 8 + 1]); u.y = pack_bf16(r[q * 8 + 2], r[q * 8 + 3]);
+          u.z = pack_bf16(r[q * 8 + 4], r[q * 8 + 5]); u.w = pack_bf16(r[q * 8 + 6], r[q * 8 + 7]);
+          dst[q] = u;
+        }
+      } else if (epi & RTTS_EPI_ATOMIC) {
+        float* dst = static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(dst + i, r[i]);
+      } else {
+        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+      }
+      if (epi & RTTS_EPI_COLSUM) {
+        const float tot = warp_column_sums(r, lane);
+        atomicAdd(p.colsum + col + lane, tot);
+      }
+    }
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, kBN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows of `ld` elements; box = box_inner x box_outer.
+static int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, int64_t ld, uint32_t box_inner,
+                     uint32_t box_outer) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return fail(kErrCuda, "rtts_gemm_bf16: cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t gdim[2] = {inner, outer};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(kErrCuda, "rtts_gemm_bf16: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return kOk;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    if (e != cudaSuccess) return fail(kErrCuda, "rtts_gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  gemm_bf16_kernel<A_MN, B_MN><<<grid, kGemmThreads, kGemmSmem, stream>>>(ta, tb, p);
+  return check_launch("rtts_gemm_bf16");
+}
+
+}  // namespace rtts
+
+using namespace rtts;
+
+extern "C" int rtts_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
+                              int64_t ldc, const float* bias, const void* gate, int64_t ldgate, float* colsum, int M, int N,
+                              int K, int epilogue, int split_k, void* stream) {
+  RTTS_REQUIRE(A && B && C, "rtts_gemm_bf16: null pointer");
+  RTTS_REQUIRE(M > 0 && N > 0 && K > 0 && M % kBM == 0 && N % kBN == 0, "rtts_gemm_bf16: M=%d, N=%d must be multiples of 128", M, N);
+  RTTS_REQUIRE(split_k >= 1 && K % (kBK * split_k) == 0, "rtts_gemm_bf16: K=%d must be a multiple of 64*split_k", K);
+  RTTS_REQUIRE(split_k == 1 || (epilogue & RTTS_EPI_ATOMIC), "rtts_gemm_bf16: split_k > 1 needs RTTS_EPI_ATOMIC");
+  RTTS_REQUIRE(!((epilogue & RTTS_EPI_ATOMIC) && (epilogue & (RTTS_EPI_OUT_BF16 | RTTS_EPI_BIAS | RTTS_EPI_RELU | RTTS_EPI_GATE | RTTS_EPI_COLSUM))),
+               "rtts_gemm_bf16: RTTS_EPI_ATOMIC cannot be combined with other epilogue flags");
+  RTTS_REQUIRE(!(epilogue & RTTS_EPI_BIAS) || bias, "rtts_gemm_bf16: bias flag without bias pointer");
+  RTTS_REQUIRE(!(epilogue & RTTS_EPI_GATE) || gate, "rtts_gemm_bf16: gate flag without gate pointer");
+  RTTS_REQUIRE(!(epilogue & RTTS_EPI_COLSUM) || colsum, "rtts_gemm_bf16: colsum flag without colsum pointer");
+  RTTS_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && (ldgate % 8 == 0), "rtts_gemm_bf16: leading dimensions must be multiples of 8");
+  RTTS_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) == 0,
+               "rtts_gemm_bf16: operands must be 16-byte aligned");
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn_major) rc = make_tmap(&ta, A, M, K, lda, 64, kBK);
+  else rc = make_tmap(&ta, A, K, M, lda, kBK, kBM);
+  if (rc) return rc;
+  if (b_mn_major) rc = make_tmap(&tb, B, N, K, ldb, 64, kBK);
+  else rc = make_tmap(&tb, B, K, N, ldb, kBK, kBN);
+  if (rc) return rc;
+  GemmParams p;
+  p.C = C; p.ldc = ldc; p.bias = bias; p.gate = static_cast<const __nv_bfloat16*>(gate); p.ldgate = ldgate; p.colsum = colsum;
+  p.M = M; p.N = N; p.K = K / split_k; p.epilogue = epilogue;
+  dim3 grid(N / kBN, M / kBM, split_k);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a_mn_major && b_mn_major) return launch_gemm<true, true>(ta, tb, p, grid, s);
+  if (a_mn_major) return launch_gemm<true, false>(ta, tb, p, grid, s);
+  if (b_mn_major) return launch_gemm<false, true>(ta, tb, p, grid, s);
+  return launch_gemm<false, false>(ta, tb, p, grid, s);
+}

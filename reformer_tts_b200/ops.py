@@ -1,0 +1,243 @@
+"""Torch-tensor front end of the C ABI: checks, output allocation, stream plumbing.  No arithmetic here.
+
+Every function launches on ``torch.cuda.current_stream()`` and raises ``RuntimeError`` on a non-zero
+return from the library.  PyTorch is only the allocator / stream provider.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+KEYNORM_L2, KEYNORM_RMS = 0, 1
+MASK_QUERY_AND_KEY, MASK_KEY_ONLY = 0, 1
+EPI_BIAS, EPI_RELU, EPI_GATE, EPI_OUT_BF16, EPI_ATOMIC, EPI_COLSUM = 1, 2, 4, 8, 16, 32
+
+
+@dataclass(frozen=True)
+class LSHSpec:
+    """Constants separating the two implementations ref:reformer_tts/model/reformer.py:198-213 can select."""
+    score_scale: float
+    key_norm: int
+    mask_value: float
+    self_value: float
+    mask_mode: int
+    causal: bool
+
+    @staticmethod
+    def reformer_pytorch(dh: int, causal: bool) -> "LSHSpec":      # rp R5, R7, R8
+        return LSHSpec(dh ** -0.5, KEYNORM_L2, -torch.finfo(torch.float32).max, -5e4, MASK_QUERY_AND_KEY, causal)
+
+    @staticmethod
+    def huggingface(dh: int, causal: bool) -> "LSHSpec":           # hf:430-431,914-922,1042-1056
+        return LSHSpec(1.0, KEYNORM_RMS, -1e9, -1e5, MASK_KEY_ONLY, causal)
+
+    def struct(self) -> _lib.LSHSpecStruct:
+        return _lib.LSHSpecStruct(self.score_scale, self.key_norm, self.mask_value, self.self_value, self.mask_mode,
+                                  int(self.causal))
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(t: torch.Tensor, dtype, name: str, inner_contig: bool = True):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if inner_contig and t.stride(-1) != 1:
+        raise RuntimeError(f"{name}: innermost dimension must be contiguous")
+
+
+def _token_major(t: torch.Tensor, name: str) -> int:
+    """[B, T, C] bf16 view with contiguous channels and B-stride == T * ld; returns ld."""
+    _check(t, torch.bfloat16, name)
+    b, tt, _ = t.shape
+    ld = t.stride(1)
+    if b > 1 and t.stride(0) != tt * ld:
+        raise RuntimeError(f"{name}: batch stride must equal T * token stride")
+    return ld
+
+
+def lsh_hash(qk: torch.Tensor, rot: torch.Tensor, n_heads: int, n_rounds: int, n_buckets: int,
+             pad_mask: Optional[torch.Tensor] = None, use_pad_bucket: bool = False) -> torch.Tensor:
+    """qk bf16 [B,T,H*64]; rot fp32 [1|H, 64, R, nb/2]  ->  buckets int32 [B,H,R*T]."""
+    ld = _token_major(qk, "qk")
+    b, t, c = qk.shape
+    dh = c // n_heads
+    _check(rot, torch.float32, "rot")
+    rot = rot.contiguous()
+    assert rot.shape[1:] == (dh, n_rounds, n_buckets // 2), f"rot shape {tuple(rot.shape)}"
+    if pad_mask is not None:
+        _check(pad_mask, torch.uint8, "pad_mask")
+        pad_mask = pad_mask.contiguous()
+    out = torch.empty((b, n_heads, n_rounds * t), dtype=torch.int32, device=qk.device)
+    _lib.call("rtts_lsh_hash", _ptr(qk), ld, _ptr(rot), rot.shape[0], _ptr(pad_mask), int(use_pad_bucket), _ptr(out),
+              b, t, n_heads, dh, n_rounds, n_buckets, _stream())
+    return out
+
+
+def lsh_sort(buckets: torch.Tensor, seq_len: int, n_rounds: int, ids_per_round: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """buckets int32 [..., R*T] -> (sticker, undo) int32, same shape."""
+    _check(buckets, torch.int32, "buckets")
+    buckets = buckets.contiguous()
+    rows = buckets.numel() // (n_rounds * seq_len)
+    sticker, undo = torch.empty_like(buckets), torch.empty_like(buckets)
+    _lib.call("rtts_lsh_sort", _ptr(buckets), _ptr(sticker), _ptr(undo), rows, seq_len, n_rounds, ids_per_round, _stream())
+    return sticker, undo
+
+
+def lsh_attn_fwd(qk: torch.Tensor, v: torch.Tensor, sticker: torch.Tensor, mask: Optional[torch.Tensor], spec: LSHSpec,
+                 n_heads: int, n_rounds: int, bucket: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> o_rounds bf16 [B,H,R,T,64], lse_rounds fp32 [B,H,R,T] (both already unsorted)."""
+    ld = _token_major(qk, "qk")
+    if _token_major(v, "v") != ld:
+        raise RuntimeError("qk and v must share the token stride")
+    b, t, c = qk.shape
+    dh = c // n_heads
+    _check(sticker, torch.int32, "sticker")
+    assert sticker.is_contiguous() and sticker.numel() == b * n_heads * n_rounds * t
+    if mask is not None:
+        _check(mask, torch.uint8, "mask")
+        mask = mask.contiguous()
+    o = torch.empty((b, n_heads, n_rounds, t, dh), dtype=torch.bfloat16, device=qk.device)
+    lse = torch.empty((b, n_heads, n_rounds, t), dtype=torch.float32, device=qk.device)
+    st = spec.struct()
+    _lib.call("rtts_lsh_attn_fwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(mask), ctypes.byref(st), _ptr(o), _ptr(lse),
+              b, t, n_heads, dh, n_rounds, bucket, _stream())
+    return o, lse
+
+
+def lsh_merge_fwd(o_rounds: torch.Tensor, lse_rounds: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> out bf16 [B,T,H*64], lse fp32 [B,H,T]."""
+    _check(o_rounds, torch.bfloat16, "o_rounds")
+    _check(lse_rounds, torch.float32, "lse_rounds")
+    b, h, r, t, dh = o_rounds.shape
+    assert o_rounds.is_contiguous() and lse_rounds.is_contiguous()
+    out = torch.empty((b, t, h * dh), dtype=torch.bfloat16, device=o_rounds.device)
+    lse = torch.empty((b, h, t), dtype=torch.float32, device=o_rounds.device)
+    _lib.call("rtts_lsh_merge_fwd", _ptr(o_rounds), _ptr(lse_rounds), _ptr(out), h * dh, _ptr(lse), b, t, h, dh, r, _stream())
+    return out, lse
+
+
+def lsh_delta(dout: torch.Tensor, out: torch.Tensor, n_heads: int) -> torch.Tensor:
+    ld = _token_major(dout, "dout")
+    if _token_major(out, "out") != ld:
+        raise RuntimeError("dout and out must share the token stride")
+    b, t, c = dout.shape
+    delta = torch.empty((b, n_heads, t), dtype=torch.float32, device=dout.device)
+    _lib.call("rtts_lsh_delta", _ptr(dout), _ptr(out), ld, _ptr(delta), b, t, n_heads, c // n_heads, _stream())
+    return delta
+
+
+def lsh_attn_bwd(qk, v, sticker, mask, spec: LSHSpec, dout, lse, delta, n_heads: int, n_rounds: int, bucket: int):
+    """-> (dq_rounds, dk_rounds, dv_rounds) fp32 [B,H,R,T,64] (unsorted layout)."""
+    ld = _token_major(qk, "qk")
+    if _token_major(v, "v") != ld or _token_major(dout, "dout") != ld:
+        raise RuntimeError("qk, v and dout must share the token stride")
+    b, t, c = qk.shape
+    dh = c // n_heads
+    _check(lse, torch.float32, "lse")
+    _check(delta, torch.float32, "delta")
+    shape = (b, n_heads, n_rounds, t, dh)
+    dq = torch.empty(shape, dtype=torch.float32, device=qk.device)
+    dk = torch.empty(shape, dtype=torch.float32, device=qk.device)
+    dv = torch.empty(shape, dtype=torch.float32, device=qk.device)
+    st = spec.struct()
+    _lib.call("rtts_lsh_attn_bwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(mask), ctypes.byref(st), _ptr(dout),
+              _ptr(lse.contiguous()), _ptr(delta.contiguous()), _ptr(dq), _ptr(dk), _ptr(dv), b, t, n_heads, dh, n_rounds,
+              bucket, _stream())
+    return dq, dk, dv
+
+
+def lsh_grad_reduce(qk, dq_rounds, dk_rounds, dv_rounds, spec: LSHSpec, n_heads: int):
+    """-> dqk, dv bf16 [B,T,H*64]."""
+    ld = _token_major(qk, "qk")
+    b, t, c = qk.shape
+    r = dq_rounds.shape[2]
+    dqk = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device)
+    dv = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device)
+    st = spec.struct()
+    _lib.call("rtts_lsh_grad_reduce", _ptr(qk), ld, _ptr(dq_rounds), _ptr(dk_rounds), _ptr(dv_rounds), ctypes.byref(st),
+              _ptr(dqk), _ptr(dv), b, t, n_heads, c // n_heads, r, _stream())
+    return dqk, dv
+
+
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, save_stats: bool = True):
+    """x fp32 [..., dim] -> (y bf16, mean, rstd)."""
+    _check(x, torch.float32, "x")
+    x = x.contiguous()
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    _lib.call("rtts_layernorm_fwd", _ptr(x), _ptr(gamma.contiguous()), _ptr(beta.contiguous()), _ptr(y), _ptr(mean), _ptr(rstd),
+              rows, dim, eps, _stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta):
+    """dy, x fp32 [..., dim] -> dx fp32; dgamma / dbeta (fp32 [dim]) are accumulated in place."""
+    _check(dy, torch.float32, "dy")
+    dy, x = dy.contiguous(), x.contiguous()
+    dim = x.shape[-1]
+    dx = torch.empty_like(x)
+    _lib.call("rtts_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(gamma.contiguous()), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma),
+              _ptr(dbeta), x.numel() // dim, dim, _stream())
+    return dx
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_major: bool = False, bias=None, relu=False,
+         gate=None, out_dtype=torch.float32, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+         colsum: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
+    """C = epilogue(A . B^T) with bf16 operands.  A: [M,K] (or stored [K,M] when a_mn_major); B: [N,K] (or [K,N])."""
+    _check(a, torch.bfloat16, "a")
+    _check(b, torch.bfloat16, "b")
+    assert a.dim() == 2 and b.dim() == 2
+    m, k = (a.shape[1], a.shape[0]) if a_mn_major else a.shape
+    n, kb = (b.shape[1], b.shape[0]) if b_mn_major else b.shape
+    assert k == kb, f"K mismatch {k} vs {kb}"
+    flags = 0
+    if bias is not None:
+        _check(bias, torch.float32, "bias")
+        flags |= EPI_BIAS
+    if relu:
+        flags |= EPI_RELU
+    if gate is not None:
+        _check(gate, torch.bfloat16, "gate")
+        flags |= EPI_GATE
+    if colsum is not None:
+        _check(colsum, torch.float32, "colsum")
+        flags |= EPI_COLSUM
+    if accumulate:
+        assert out is not None and out.dtype == torch.float32
+        flags |= EPI_ATOMIC
+    elif out_dtype == torch.bfloat16:
+        flags |= EPI_OUT_BF16
+    if out is None:
+        out = torch.empty((m, n), dtype=out_dtype, device=a.device)
+    assert out.shape == (m, n) and out.stride(1) == 1
+    _lib.call("rtts_gemm_bf16", _ptr(a), a.stride(0), int(a_mn_major), _ptr(b), b.stride(0), int(b_mn_major), _ptr(out),
+              out.stride(0), _ptr(bias), _ptr(gate), 0 if gate is None else gate.stride(0), _ptr(colsum), m, n, k, flags, split_k,
+              _stream())
+    return out
+
+
+def cast_bf16_colsum(x: torch.Tensor, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 copy; colsum (fp32 [cols]) += column sums."""
+    _check(x, torch.float32, "x")
+    x = x.contiguous()
+    cols = x.shape[-1]
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.call("rtts_cast_bf16_colsum", _ptr(x), _ptr(y), _ptr(colsum), x.numel() // cols, cols, _stream())
+    return y
