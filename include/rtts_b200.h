@@ -78,22 +78,26 @@ int rtts_lsh_delta(const void* dout, const void* out, int64_t ld, float* delta, 
                    void* stream);
 
 /* Backward of rtts_lsh_attn_fwd + rtts_lsh_merge_fwd with in-kernel recompute of the scores
- * (autograd of rp R4-R11).  Inputs: qk, v, sticker, mask as in forward; dout bf16 [B,T,H*dh];
- * lse [B,H,T] and delta [B,H,T] from the two calls above.  Outputs per sorted slot, scattered to
- * UNSORTED [B,H,R,T,dh] fp32 layout: dq_rounds (query role), dk_rounds (key role, before the
- * normalisation Jacobian), dv_rounds.  dk/dv hold the sum over both appearances of a key (own chunk
- * and look-back of the next chunk) when `spill` buffers of the same shape are reduced with them by
- * rtts_lsh_grad_reduce. */
+ * (autograd of rp R4-R11; the per-round o / lse of the forward are not needed).  Inputs: qk, v, sticker,
+ * mask as in forward; dout bf16 [B,T,H*dh] = gradient of the merged output; lse [B,H,T] from
+ * rtts_lsh_merge_fwd; delta [B,H,T] from rtts_lsh_delta.  Outputs, fp32 [B,H,R,T,dh], scattered to the
+ * UNSORTED slot like the forward:
+ *   dq_a  query-role gradient from the keys of the CTA that owns the slot as a key,
+ *   dq_b  query-role gradient from the previous CTA (slot seen as look-ahead chunk); written for every
+ *         slot when bucket == 128 and only for slots in even sorted chunks when bucket == 64,
+ *   dxk   key-role gradient with the key-normalisation Jacobian already applied,
+ *   dv    value gradient. */
 int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
                       const rtts_lsh_spec* spec_host, const void* dout, const float* lse, const float* delta,
-                      float* dq_rounds, float* dk_rounds, float* dv_rounds, int B, int T, int H, int dh, int R,
+                      float* dq_a, float* dq_b, float* dxk, float* dv_rounds, int B, int T, int H, int dh, int R,
                       int bucket, void* stream);
 
-/* Sum the per-round gradients over rounds, apply the key-normalisation Jacobian and emit
- * dqk bf16 [B,T,H*dh], dv bf16 [B,T,H*dh]. */
-int rtts_lsh_grad_reduce(const void* qk, int64_t ld, const float* dq_rounds, const float* dk_rounds,
-                         const float* dv_rounds, const rtts_lsh_spec* spec_host, void* dqk, void* dv, int B, int T,
-                         int H, int dh, int R, void* stream);
+/* Sum the per-round gradients over the R rounds: dqk = sum_r (dq_a + dq_b + dxk), dv = sum_r dv_rounds,
+ * both bf16 [B,T,H*dh] (ld).  undo (from rtts_lsh_sort) tells which slots have a dq_b entry; may be NULL
+ * when bucket == 128. */
+int rtts_lsh_grad_reduce(const float* dq_a, const float* dq_b, const float* dxk, const float* dv_rounds,
+                         const int32_t* undo, void* dqk, void* dv, int64_t ld, int B, int T, int H, int dh, int R,
+                         int bucket, void* stream);
 
 /* ---- LayerNorm (ref:reformer_tts/model/reformer.py:25-33, eps 1e-5, affine) -------------------- */
 

@@ -1,12 +1,434 @@
-// placeholder: replaced by the real backward kernels
+// Fused chunked shared-QK attention, backward (rtts_lsh_attn_bwd) and the per-token gradient reduce
+// (rtts_lsh_grad_reduce).  Contract: include/rtts_b200.h; tiling: DESIGN.md "K15".
+//
+// Across hash rounds the LSH attention is ONE softmax over the multiset of (round, key) pairs with the
+// total normaliser L = logsumexp_r lse_r, so with Pt_ij = exp(s_ij - L_i) and delta_i = <dout_i, out_i>
+//     dV_j += Pt_ij dout_i,   dS_ij = Pt_ij (<dout_i, v_j> - delta_i)  (0 where a mask constant was written),
+//     dQ_i += dS_ij khat_j,   dKhat_j += dS_ij q_i
+// and nothing per-round from the forward has to be stored: the scores are recomputed here.
+//
+// One CTA (128 threads, thread = key row) owns 128 consecutive SORTED key slots and the 128+bucket query
+// slots that can see them (the key slots themselves, then the next chunk, which looks one chunk back).
+// Everything is formed TRANSPOSED, keys on the TMEM lane axis, because per-query quantities (L, delta,
+// position) are then per-column broadcasts and per-key ones (1/|k|, position) live in registers:
+//   per 64-query block qb:  St  = K  Q_qb^T      (M128 N64 K64)      dPt = V dO_qb^T   (M128 N64 K64)
+//                           Pt, dSt -> bf16 shared-memory tiles (K-major in q), then
+//                           dV += Pt_qb dO_qb    (M128 N64 K64)      G  += dSt_qb Q_qb (M128 N64 K64)
+//   per pair of blocks:     dQ  = dS K           (A = dSt tile read MN-major, M128 N64 K128)
+// G = (dKhat * 1/|k|) goes through the key-normalisation Jacobian in the epilogue: dx = G - x |k|^-2 <x, G>.
+// A key's dV / dx are complete inside one CTA; a query chunk's dQ is split between the CTA that owns it as
+// a key chunk (dq_a) and the previous one where it is the look-back chunk (dq_b).
+#include <cfloat>
+
+#include "common.cuh"
 #include "host_util.h"
 #include "rtts_b200.h"
-using namespace rtts;
-extern "C" int rtts_lsh_attn_bwd(const void*, const void*, int64_t, const int32_t*, const uint8_t*, const rtts_lsh_spec*,
-                                 const void*, const float*, const float*, float*, float*, float*, int, int, int, int, int, int, void*) {
-  return fail(kErrUnsupported, "rtts_lsh_attn_bwd: not built yet");
+
+namespace rtts {
+
+constexpr int kBDh = 64;
+constexpr int kKeyRows = 128;
+constexpr float kBLog2e = 1.4426950408889634f;
+constexpr int kBPadFlag = 0x40000000;
+constexpr int kBlk = 128 * 128;   // bytes of one 64-column block of a 128-row bf16 tile
+
+struct AttnBwdParams {
+  const __nv_bfloat16* qk;
+  const __nv_bfloat16* v;
+  const __nv_bfloat16* dout;
+  int64_t ld;
+  const int32_t* sticker;
+  const uint8_t* mask;
+  const float* lse;     // [B,H,T]
+  const float* delta;   // [B,H,T]
+  float* dq_a;
+  float* dq_b;
+  float* dxk;
+  float* dv;
+  int T, H, R, tiles_per_row;
+  float score_scale;
+  float mask_value_log2, self_value_log2;
+  int key_norm, mask_mode, causal;
+};
+
+template <int BUCKET>
+struct AttnBwdSmem {
+  static constexpr int kQRows = kKeyRows + BUCKET;      // 192 | 256
+  static constexpr int kQBlocks = kQRows / 64;          // 3 | 4
+  static constexpr int kOffX = 0;                        // qk rows of all query slots (first 128 = keys)
+  static constexpr int kOffV = kOffX + kQRows * 128;     // v rows of the key slots
+  static constexpr int kOffDO = kOffV + kKeyRows * 128;  // dout rows of the query slots
+  static constexpr int kOffPT = kOffDO + kQRows * 128;   // Pt  tile: kQBlocks blocks of [128 x 64] bf16
+  static constexpr int kOffDS = kOffPT + kQBlocks * kBlk;  // dSt tile: always 4 blocks (pair reads need block 3)
+  static constexpr int kOffQMeta = kOffDS + 4 * kBlk;      // int2[kQRows]  (enc, limit)
+  static constexpr int kOffQStat = kOffQMeta + kQRows * 8; // float2[kQRows] (L*log2e, delta)
+  static constexpr int kOffQSlot = kOffQStat + kQRows * 8; // int[kQRows] unsorted slot
+  static constexpr int kOffBar = kOffQSlot + kQRows * 4;
+  static constexpr int kOffTmem = kOffBar + 8;
+  static constexpr int kTotal = kOffTmem + 8;
+  static constexpr int kDynamic = kTotal + 1024;
+};
+
+template <int BUCKET>
+__global__ void __launch_bounds__(128) lsh_attn_bwd_kernel(const AttnBwdParams p) {
+  using L = AttnBwdSmem<BUCKET>;
+  constexpr int kQRows = L::kQRows, kQBlocks = L::kQBlocks;
+  constexpr uint32_t kTmemCols = 512;
+  // TMEM columns
+  constexpr uint32_t cS = 0, cDP = 64, cDV = 128, cG = 192, cDQ0 = 256, cDQ1 = 320;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sX = smem_u32(smem + L::kOffX), sV = smem_u32(smem + L::kOffV), sDO = smem_u32(smem + L::kOffDO);
+  const uint32_t sPT = smem_u32(smem + L::kOffPT), sDS = smem_u32(smem + L::kOffDS);
+  int2* q_meta = reinterpret_cast<int2*>(smem + L::kOffQMeta);
+  float2* q_stat = reinterpret_cast<float2*>(smem + L::kOffQStat);
+  int* q_slot = reinterpret_cast<int*>(smem + L::kOffQSlot);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row_bh = blockIdx.x / p.tiles_per_row;
+  const int tile = blockIdx.x - row_bh * p.tiles_per_row;
+  const int b = row_bh / p.H, h = row_bh - b * p.H;
+  const int RT = p.R * p.T;
+  const int32_t* stk = p.sticker + static_cast<int64_t>(row_bh) * RT;
+  const int first_slot = tile * kKeyRows;      // sorted slot of row 0; rows >= RT wrap to the start
+
+  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+
+  // ---- gather qk / dout rows of the query slots, v rows of the key slots ---------------------------------
+  {
+    const int g = tid >> 3, c = tid & 7;
+    constexpr int kPasses = kQRows / 16;
+    int pos[kPasses];
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i) {
+      const int j = i * 16 + g;
+      int slot = first_slot + j;
+      slot = slot >= RT ? slot - RT : slot;
+      const int st = __ldg(stk + slot);
+      pos[i] = st % p.T;
+      if (c == 0) {
+        int enc = pos[i];
+        if (p.mask != nullptr && __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos[i]) == 0) enc |= kBPadFlag;
+        int limit = p.causal ? pos[i] : (kBPadFlag - 1);
+        if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && (enc & kBPadFlag)) limit = -1;
+        q_meta[j] = make_int2(enc, limit);
+        const int64_t sidx = static_cast<int64_t>(row_bh) * p.T + pos[i];
+        q_stat[j] = make_float2(__ldg(p.lse + sidx) * kBLog2e, __ldg(p.delta + sidx));
+        q_slot[j] = st;
+      }
+    }
+    const int64_t head_off = static_cast<int64_t>(h) * kBDh + c * 8;
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i) {
+      const int j = i * 16 + g;
+      const int64_t off = (static_cast<int64_t>(b) * p.T + pos[i]) * p.ld + head_off;
+      const uint32_t so = sw128_offset(j, c);
+      cp_async16(sX + so, p.qk + off);
+      cp_async16(sDO + so, p.dout + off);
+      if (j < kKeyRows) cp_async16(sV + so, p.v + off);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
+  __syncthreads();
+
+  // ---- this thread's key row: 1/|k| and position ---------------------------------------------------------------
+  const int j = tid;
+  float inv;
+  {
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = *reinterpret_cast<const uint4*>(smem + L::kOffX + sw128_offset(j, c));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+        ss = fmaf(lo, lo, ss);
+        ss = fmaf(hi, hi, ss);
+      }
+    }
+    if (p.key_norm == RTTS_KEYNORM_L2) inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    else inv = rsqrtf(ss * (1.f / kBDh) + 1e-6f) * 0.125f;
+  }
+  const float cs = inv * p.score_scale * kBLog2e;   // score scale in log2 units
+  const float gs = inv * p.score_scale;             // folded into dSt so one tile serves dQ and G
+  const int k_enc = q_meta[j].x;
+  const int k_chunk = j / BUCKET;                   // 0|1 for bucket 64, 0 for bucket 128
+  const float mv = p.mask_value_log2, sv = p.self_value_log2;
+
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  uint32_t phase = 0;
+
+#pragma unroll 1
+  for (int qb = 0; qb < kQBlocks; ++qb) {
+    if (tid == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, false, false);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss(tmem + cS, umma_desc_sw128(sX + k * 32, 16, 1024), umma_desc_sw128(sX + qb * 8192 + k * 32, 16, 1024), idesc, k > 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss(tmem + cDP, umma_desc_sw128(sV + k * 32, 16, 1024), umma_desc_sw128(sDO + qb * 8192 + k * 32, 16, 1024), idesc, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after_sync();
+
+    // which query chunk is this block, and does it see this thread's key chunk?
+    const int q_chunk = (qb * 64) / BUCKET;
+    const bool pair_live = (q_chunk == k_chunk) || (q_chunk == k_chunk + 1);
+    uint8_t* pt_row = smem + L::kOffPT + qb * kBlk;
+    uint8_t* ds_row = smem + L::kOffDS + qb * kBlk;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t rs[32], rp[32];
+      tmem_ld32(t_row + cS + half * 32, rs);
+      tmem_ld32(t_row + cDP + half * 32, rp);
+      tmem_ld_wait();
+      float pe[32], de[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int qi = qb * 64 + half * 32 + i;
+        const int2 qm = q_meta[qi];
+        const float2 qs = q_stat[qi];
+        const bool masked = k_enc > qm.y;
+        const bool self = k_enc == qm.x;
+        float s = __uint_as_float(rs[i]) * cs;
+        s = masked ? mv : s;
+        s = self ? sv : s;
+        const float pr = pair_live ? exp2f(s - qs.x) : 0.f;
+        pe[i] = pr;
+        de[i] = (masked || self) ? 0.f : pr * (__uint_as_float(rp[i]) - qs.y) * gs;
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 u, w;
+        u.x = pack_bf16(pe[q4 * 8 + 0], pe[q4 * 8 + 1]); u.y = pack_bf16(pe[q4 * 8 + 2], pe[q4 * 8 + 3]);
+        u.z = pack_bf16(pe[q4 * 8 + 4], pe[q4 * 8 + 5]); u.w = pack_bf16(pe[q4 * 8 + 6], pe[q4 * 8 + 7]);
+        w.x = pack_bf16(de[q4 * 8 + 0], de[q4 * 8 + 1]); w.y = pack_bf16(de[q4 * 8 + 2], de[q4 * 8 + 3]);
+        w.z = pack_bf16(de[q4 * 8 + 4], de[q4 * 8 + 5]); w.w = pack_bf16(de[q4 * 8 + 6], de[q4 * 8 + 7]);
+        const uint32_t off = sw128_offset(j, half * 4 + q4);
+        *reinterpret_cast<uint4*>(pt_row + off) = u;
+        *reinterpret_cast<uint4*>(ds_row + off) = w;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+
+    if (tid == 0) {
+      constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, false, true);   // A K-major, B MN-major
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss(tmem + cDV, umma_desc_sw128(sPT + qb * kBlk + k * 32, 16, 1024),
+                umma_desc_sw128(sDO + qb * 8192 + k * 2048, 0, 1024), idesc_kn, (qb | k) != 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss(tmem + cG, umma_desc_sw128(sDS + qb * kBlk + k * 32, 16, 1024),
+                umma_desc_sw128(sX + qb * 8192 + k * 2048, 0, 1024), idesc_kn, (qb | k) != 0);
+      if ((qb & 1) || qb == kQBlocks - 1) {
+        // dQ for query rows [pair*128, +128): A = dSt blocks (pair*2, pair*2+1) read MN-major (M = queries)
+        constexpr uint32_t idesc_nn = umma_idesc_bf16(128, 64, true, true);
+        const int pair = qb >> 1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tmem + (pair ? cDQ1 : cDQ0), umma_desc_sw128(sDS + pair * 2 * kBlk + k * 2048, kBlk, 1024),
+                  umma_desc_sw128(sX + k * 2048, 0, 1024), idesc_nn, k > 0);
+      }
+    }
+  }
+  if (tid == 0) umma_commit(bar);
+  mbar_wait(bar, phase);
+  tc_fence_after_sync();
+
+  // ---- epilogue ---------------------------------------------------------------------------------------------------
+  const int64_t out_base = static_cast<int64_t>(row_bh) * RT;
+  {
+    // dV row j and dx row j (key-normalisation Jacobian applied to G)
+    float g[64];
+    float4* dv_dst = reinterpret_cast<float4*>(p.dv + (out_base + q_slot[j]) * kBDh);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      tmem_ld32(t_row + cDV + half * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        dv_dst[half * 8 + q] = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                                           __uint_as_float(r[q * 4 + 3]));
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      tmem_ld32(t_row + cG + half * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) g[half * 32 + i] = __uint_as_float(r[i]);
+    }
+    float x[64];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = *reinterpret_cast<const uint4*>(smem + L::kOffX + sw128_offset(j, c));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        x[c * 8 + 2 * e] = bf16_lo(w[e]);
+        x[c * 8 + 2 * e + 1] = bf16_hi(w[e]);
+        dot = fmaf(x[c * 8 + 2 * e], g[c * 8 + 2 * e], dot);
+        dot = fmaf(x[c * 8 + 2 * e + 1], g[c * 8 + 2 * e + 1], dot);
+      }
+    }
+    const float coef = inv * inv * dot;   // dh == 64: the L2 and the RMS/sqrt(dh) norms share |k|^-2 = inv^2
+    float4* dx_dst = reinterpret_cast<float4*>(p.dxk + (out_base + q_slot[j]) * kBDh);
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      dx_dst[q] = make_float4(g[q * 4] - x[q * 4] * coef, g[q * 4 + 1] - x[q * 4 + 1] * coef, g[q * 4 + 2] - x[q * 4 + 2] * coef,
+                              g[q * 4 + 3] - x[q * 4 + 3] * coef);
+  }
+  {
+    // dQ: accumulator 0 = query rows 0..127 (the key slots themselves) -> dq_a;
+    //     accumulator 1 = query rows 128.. (the look-ahead chunk, BUCKET rows) -> dq_b
+    float4* dst = reinterpret_cast<float4*>(p.dq_a + (out_base + q_slot[j]) * kBDh);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      tmem_ld32(t_row + cDQ0 + half * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        dst[half * 8 + q] = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                                        __uint_as_float(r[q * 4 + 3]));
+    }
+    // every warp must execute the (warp-collective) TMEM loads; only rows < BUCKET are stored
+    const bool live = j < BUCKET;
+    float4* dst_b = reinterpret_cast<float4*>(p.dq_b + (out_base + q_slot[live ? kKeyRows + j : 0]) * kBDh);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      tmem_ld32(t_row + cDQ1 + half * 32, r);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          dst_b[half * 8 + q] = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                                            __uint_as_float(r[q * 4 + 3]));
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
-extern "C" int rtts_lsh_grad_reduce(const void*, int64_t, const float*, const float*, const float*, const rtts_lsh_spec*, void*,
-                                    void*, int, int, int, int, int, void*) {
-  return fail(kErrUnsupported, "rtts_lsh_grad_reduce: not built yet");
+
+// ---------------------------------------------------------------------------------------------------------------------
+// dqk[b,t,h,:] = sum_r dq_a + dq_b(if written) + dxk ;  dv[b,t,h,:] = sum_r dv_r.  16 lanes x float4 per (b,h,t) row.
+// dq_b is written for every slot when bucket == 128, and only for slots in even chunks when bucket == 64
+// (the chunk index comes from `undo`).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lsh_grad_reduce_kernel(const float* __restrict__ dq_a, const float* __restrict__ dq_b,
+                                                              const float* __restrict__ dxk, const float* __restrict__ dvr,
+                                                              const int32_t* __restrict__ undo, __nv_bfloat16* __restrict__ dqk,
+                                                              __nv_bfloat16* __restrict__ dv, int64_t ld, int T, int H, int R,
+                                                              int bucket, int64_t rows) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) >> 4;   // (b*H + h)*T + t
+  const int c = threadIdx.x & 15;
+  if (row >= rows) return;
+  const int64_t bh = row / T;
+  const int t = static_cast<int>(row - bh * T);
+  float4 aq = make_float4(0, 0, 0, 0), av = make_float4(0, 0, 0, 0);
+  for (int r = 0; r < R; ++r) {
+    const int64_t idx = (bh * R + r) * T + t;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(dq_a + idx * kBDh) + c);
+    const float4 k = __ldg(reinterpret_cast<const float4*>(dxk + idx * kBDh) + c);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(dvr + idx * kBDh) + c);
+    aq.x += a.x + k.x; aq.y += a.y + k.y; aq.z += a.z + k.z; aq.w += a.w + k.w;
+    av.x += w.x; av.y += w.y; av.z += w.z; av.w += w.w;
+    bool has_b = true;
+    if (bucket == 64) has_b = ((__ldg(undo + idx) >> 6) & 1) == 0;
+    if (has_b) {
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(dq_b + idx * kBDh) + c);
+      aq.x += bq.x; aq.y += bq.y; aq.z += bq.z; aq.w += bq.w;
+    }
+  }
+  const int64_t b = bh / H;
+  const int h = static_cast<int>(bh - b * H);
+  const int64_t o = (b * T + t) * ld + h * kBDh + c * 4;
+  uint2 u;
+  u.x = pack_bf16(aq.x, aq.y); u.y = pack_bf16(aq.z, aq.w);
+  *reinterpret_cast<uint2*>(dqk + o) = u;
+  u.x = pack_bf16(av.x, av.y); u.y = pack_bf16(av.z, av.w);
+  *reinterpret_cast<uint2*>(dv + o) = u;
+}
+
+template <int BUCKET>
+int launch_attn_bwd(const AttnBwdParams& p, int ctas, cudaStream_t stream) {
+  using L = AttnBwdSmem<BUCKET>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(lsh_attn_bwd_kernel<BUCKET>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+    if (e != cudaSuccess) return fail(kErrCuda, "rtts_lsh_attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  lsh_attn_bwd_kernel<BUCKET><<<ctas, 128, L::kDynamic, stream>>>(p);
+  return check_launch("rtts_lsh_attn_bwd");
+}
+
+}  // namespace rtts
+
+using namespace rtts;
+
+extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
+                                 const rtts_lsh_spec* spec, const void* dout, const float* lse, const float* delta, float* dq_a,
+                                 float* dq_b, float* dxk, float* dv_rounds, int B, int T, int H, int dh, int R, int bucket,
+                                 void* stream) {
+  RTTS_REQUIRE(qk && v && sticker && spec && dout && lse && delta && dq_a && dq_b && dxk && dv_rounds, "rtts_lsh_attn_bwd: null pointer");
+  RTTS_REQUIRE(dh == kBDh, "rtts_lsh_attn_bwd: head size %d unsupported (64 only)", dh);
+  RTTS_REQUIRE(bucket == 64 || bucket == 128, "rtts_lsh_attn_bwd: bucket size %d unsupported (64 or 128)", bucket);
+  RTTS_REQUIRE(T % (2 * bucket) == 0, "rtts_lsh_attn_bwd: T=%d must be a multiple of 2*bucket", T);
+  RTTS_REQUIRE(ld % 8 == 0 && ((reinterpret_cast<uintptr_t>(qk) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0,
+               "rtts_lsh_attn_bwd: tensors must be 16-byte aligned");
+  AttnBwdParams p;
+  p.qk = static_cast<const __nv_bfloat16*>(qk);
+  p.v = static_cast<const __nv_bfloat16*>(v);
+  p.dout = static_cast<const __nv_bfloat16*>(dout);
+  p.ld = ld; p.sticker = sticker; p.mask = mask; p.lse = lse; p.delta = delta;
+  p.dq_a = dq_a; p.dq_b = dq_b; p.dxk = dxk; p.dv = dv_rounds;
+  p.T = T; p.H = H; p.R = R; p.tiles_per_row = R * T / kKeyRows;
+  p.score_scale = spec->score_scale;
+  p.mask_value_log2 = fmaxf(spec->mask_value * kBLog2e, -3.0e38f);
+  p.self_value_log2 = spec->self_value * kBLog2e;
+  p.key_norm = spec->key_norm; p.mask_mode = spec->mask_mode; p.causal = spec->causal;
+  const int64_t ctas = static_cast<int64_t>(B) * H * p.tiles_per_row;
+  RTTS_REQUIRE(ctas > 0 && ctas < (1ll << 31), "rtts_lsh_attn_bwd: bad grid");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return bucket == 64 ? launch_attn_bwd<64>(p, static_cast<int>(ctas), s) : launch_attn_bwd<128>(p, static_cast<int>(ctas), s);
+}
+
+extern "C" int rtts_lsh_grad_reduce(const float* dq_a, const float* dq_b, const float* dxk, const float* dv_rounds,
+                                    const int32_t* undo, void* dqk, void* dv, int64_t ld, int B, int T, int H, int dh, int R,
+                                    int bucket, void* stream) {
+  RTTS_REQUIRE(dq_a && dq_b && dxk && dv_rounds && dqk && dv, "rtts_lsh_grad_reduce: null pointer");
+  RTTS_REQUIRE(dh == kBDh && ld % 8 == 0, "rtts_lsh_grad_reduce: head size 64 and 16-byte rows required");
+  RTTS_REQUIRE(bucket == 128 || (bucket == 64 && undo), "rtts_lsh_grad_reduce: bucket 64 needs undo");
+  const int64_t rows = static_cast<int64_t>(B) * H * T;
+  const int64_t blocks = (rows * 16 + 255) / 256;
+  lsh_grad_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dq_a, dq_b, dxk, dv_rounds, undo, static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), ld, T, H, R, bucket, rows);
+  return check_launch("rtts_lsh_grad_reduce");
 }

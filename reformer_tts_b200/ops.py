@@ -139,8 +139,8 @@ def lsh_delta(dout: torch.Tensor, out: torch.Tensor, n_heads: int) -> torch.Tens
     return delta
 
 
-def lsh_attn_bwd(qk, v, sticker, mask, spec: LSHSpec, dout, lse, delta, n_heads: int, n_rounds: int, bucket: int):
-    """-> (dq_rounds, dk_rounds, dv_rounds) fp32 [B,H,R,T,64] (unsorted layout)."""
+def lsh_attn_bwd(qk, v, sticker, undo, mask, spec: LSHSpec, dout, lse, delta, n_heads: int, n_rounds: int, bucket: int):
+    """Backward of lsh_attn_fwd + lsh_merge_fwd (scores recomputed in-kernel) -> dqk, dv bf16 [B,T,H*64]."""
     ld = _token_major(qk, "qk")
     if _token_major(v, "v") != ld or _token_major(dout, "dout") != ld:
         raise RuntimeError("qk, v and dout must share the token stride")
@@ -148,27 +148,18 @@ def lsh_attn_bwd(qk, v, sticker, mask, spec: LSHSpec, dout, lse, delta, n_heads:
     dh = c // n_heads
     _check(lse, torch.float32, "lse")
     _check(delta, torch.float32, "delta")
-    shape = (b, n_heads, n_rounds, t, dh)
-    dq = torch.empty(shape, dtype=torch.float32, device=qk.device)
-    dk = torch.empty(shape, dtype=torch.float32, device=qk.device)
-    dv = torch.empty(shape, dtype=torch.float32, device=qk.device)
+    _check(undo, torch.int32, "undo")
+    assert lse.is_contiguous() and delta.is_contiguous() and sticker.is_contiguous() and undo.is_contiguous()
+    # fp32 per-round partials [4, B,H,R,T,dh]: dq_a, dq_b, dxk, dv
+    part = torch.empty((4, b, n_heads, n_rounds, t, dh), dtype=torch.float32, device=qk.device)
     st = spec.struct()
     _lib.call("rtts_lsh_attn_bwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(mask), ctypes.byref(st), _ptr(dout),
-              _ptr(lse.contiguous()), _ptr(delta.contiguous()), _ptr(dq), _ptr(dk), _ptr(dv), b, t, n_heads, dh, n_rounds,
+              _ptr(lse), _ptr(delta), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), _ptr(part[3]), b, t, n_heads, dh, n_rounds,
               bucket, _stream())
-    return dq, dk, dv
-
-
-def lsh_grad_reduce(qk, dq_rounds, dk_rounds, dv_rounds, spec: LSHSpec, n_heads: int):
-    """-> dqk, dv bf16 [B,T,H*64]."""
-    ld = _token_major(qk, "qk")
-    b, t, c = qk.shape
-    r = dq_rounds.shape[2]
     dqk = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device)
     dv = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device)
-    st = spec.struct()
-    _lib.call("rtts_lsh_grad_reduce", _ptr(qk), ld, _ptr(dq_rounds), _ptr(dk_rounds), _ptr(dv_rounds), ctypes.byref(st),
-              _ptr(dqk), _ptr(dv), b, t, n_heads, c // n_heads, r, _stream())
+    _lib.call("rtts_lsh_grad_reduce", _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), _ptr(part[3]), _ptr(undo), _ptr(dqk),
+              _ptr(dv), c, b, t, n_heads, dh, n_rounds, bucket, _stream())
     return dqk, dv
 
 

@@ -6,7 +6,7 @@ import sys
 import os
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-GROUPS = ["gemm_tn", "gemm_mn", "gemm_epi", "rowwise", "hash", "sort", "attn64", "attn128", "merge"]
+GROUPS = ["gemm_tn", "gemm_mn", "gemm_epi", "rowwise", "hash", "attn64", "attn128", "bwd64", "bwd128"]
 
 
 def rel(a, b):
@@ -120,6 +120,39 @@ def run(group):
                     out_bh = out.float().view(B, T, H, 64).transpose(1, 2).reshape(B * H, T, 64).cpu()
                     print(*tag, "merged out rel", rel(out_bh, out_ref), "lse_tot maxabs",
                           (lse_tot.cpu().view(B * H, T) - torch.logsumexp(lse_ref, 1)).abs().max().item(), flush=True)
+    elif group in ("bwd64", "bwd128"):
+        from oracle import lsh_core
+        bucket = 128 if group == "bwd128" else 64
+        B, T, H, R = 2, 512, 2, 4
+        for impl in ("rp", "hf"):
+            for causal in (False, True):
+                for pad in (False, True):
+                    qk = torch.randn(B, T, H * 64, device=dev).bfloat16()
+                    v = torch.randn(B, T, H * 64, device=dev).bfloat16()
+                    dout = torch.randn(B, T, H * 64, device=dev).bfloat16()
+                    nb = T // bucket
+                    buckets = torch.randint(0, nb, (B * H, R, T)) + nb * torch.arange(R).view(1, R, 1)
+                    buckets = buckets.view(B * H, R * T)
+                    mask = None
+                    if pad:
+                        mask = torch.ones(B, T, dtype=torch.bool); mask[0, -100:] = False; mask[1, -3:] = False
+                    ospec = (lsh_core.LSHSpec.reformer_pytorch if impl == "rp" else lsh_core.LSHSpec.huggingface)(64, causal)
+                    gspec = (ops.LSHSpec.reformer_pytorch if impl == "rp" else ops.LSHSpec.huggingface)(64, causal)
+                    to_bh = lambda x: x.float().view(B, T, H, 64).transpose(1, 2).reshape(B * H, T, 64).cpu()
+                    q32 = to_bh(qk).requires_grad_(True); v32 = to_bh(v).requires_grad_(True)
+                    m_bh = None if mask is None else mask[:, None, :].expand(B, H, T).reshape(B * H, T)
+                    res = lsh_core.lsh_attention(q32, v32, buckets, bucket, R, ospec, m_bh)
+                    (res["out"] * to_bh(dout)).sum().backward()
+                    bk = buckets.to(torch.int32).to(dev).view(B, H, R * T)
+                    sticker, undo = ops.lsh_sort(bk, T, R, nb)
+                    mk = None if mask is None else mask.to(torch.uint8).to(dev)
+                    o, lse_r = ops.lsh_attn_fwd(qk, v, sticker, mk, gspec, H, R, bucket)
+                    out, lse = ops.lsh_merge_fwd(o, lse_r)
+                    delta = ops.lsh_delta(dout, out, H)
+                    dqk, dv = ops.lsh_attn_bwd(qk, v, sticker, undo, mk, gspec, dout, lse, delta, H, R, bucket)
+                    torch.cuda.synchronize()
+                    tag = (group, impl, "causal" if causal else "full", "pad" if pad else "nopad")
+                    print(*tag, "dqk rel", rel(to_bh(dqk), q32.grad), "dv rel", rel(to_bh(dv), v32.grad), flush=True)
     import torch
     torch.cuda.synchronize()
 
