@@ -1,0 +1,66 @@
+"""Fused LayerNorm + FeedForward (ref:reformer_tts/model/modules.py:195-207 under ref:reformer_tts/model/reformer.py:25-45).
+
+The reference runs ``Chunk(100, WithNorm(LayerNorm, FeedForward))``: ~90 slices of 3-11 rows, each a LayerNorm, two
+skinny addmm and a ReLU.  LayerNorm and the FFN are row-wise, so chunking is the identity; here the
+whole [B*T, dim] slab goes through one LayerNorm kernel and two tcgen05 GEMMs with bias / ReLU fused in the epilogue,
+forward and backward hand-written (no autograd graph inside)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .lsh_attention import _split_k
+
+
+class _LNFeedForwardFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, w1_bf16, w2_bf16, eps):
+        shape = x.shape
+        d = shape[-1]
+        x2 = x.reshape(-1, d)
+        if ln_w is not None:
+            xn, mean, rstd = ops.layernorm_fwd(x2, ln_w, ln_b, eps)
+        else:
+            xn, mean, rstd = ops.cast_bf16_colsum(x2), None, None
+        hid = ops.gemm(xn, w1_bf16, bias=b1, relu=True, out_dtype=torch.bfloat16)
+        y = ops.gemm(hid, w2_bf16, bias=b2)
+        ctx.has_ln = ln_w is not None
+        ctx.save_for_backward(x2, ln_w, mean, rstd, xn, hid, w1_bf16, w2_bf16)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, ln_w, mean, rstd, xn, hid, w1_bf16, w2_bf16 = ctx.saved_tensors
+        rows, d = x2.shape
+        f = hid.shape[1]
+        dev = x2.device
+        sk = _split_k(rows)
+        g_b2 = torch.zeros(d, dtype=torch.float32, device=dev)
+        dyb = ops.cast_bf16_colsum(dy.reshape(rows, d), g_b2)
+        g_w2 = torch.zeros((d, f), dtype=torch.float32, device=dev)
+        ops.gemm(dyb, hid, a_mn_major=True, b_mn_major=True, out=g_w2, accumulate=True, split_k=sk)
+        g_b1 = torch.zeros(f, dtype=torch.float32, device=dev)
+        # dh = (dy W2) * 1[h > 0]; W2 is [d, f] = [K, N] row-major -> MN-major B, no transposed copy
+        dh = ops.gemm(dyb, w2_bf16, b_mn_major=True, gate=hid, colsum=g_b1, out_dtype=torch.bfloat16)
+        g_w1 = torch.zeros((f, d), dtype=torch.float32, device=dev)
+        ops.gemm(dh, xn, a_mn_major=True, b_mn_major=True, out=g_w1, accumulate=True, split_k=sk)
+        dxn = ops.gemm(dh, w1_bf16, b_mn_major=True)
+        g_lnw = g_lnb = None
+        if ctx.has_ln:
+            g_lnw = torch.zeros(d, dtype=torch.float32, device=dev)
+            g_lnb = torch.zeros(d, dtype=torch.float32, device=dev)
+            dx = ops.layernorm_bwd(dxn, x2, ln_w, mean, rstd, g_lnw, g_lnb)
+        else:
+            dx = dxn
+        return dx.view(dy.shape), g_lnw, g_lnb, g_w1, g_b1, g_w2, g_b2, None, None, None
+
+
+def ln_feed_forward(x, norm, lin1, lin2, cache1, cache2):
+    if not x.is_cuda:
+        raise RuntimeError("reformer_tts_b200 FeedForward runs on sm_100a CUDA only; there is no CPU path")
+    ln_w = ln_b = None
+    eps = 1e-5
+    if norm is not None:
+        ln_w, ln_b, eps = norm.weight, norm.bias, norm.eps
+    return _LNFeedForwardFn.apply(x.float(), ln_w, ln_b, lin1.weight, lin1.bias, lin2.weight, lin2.bias,
+                                  cache1.get(lin1.weight), cache2.get(lin2.weight), eps)

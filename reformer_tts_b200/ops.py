@@ -139,7 +139,8 @@ def lsh_delta(dout: torch.Tensor, out: torch.Tensor, n_heads: int) -> torch.Tens
     return delta
 
 
-def lsh_attn_bwd(qk, v, sticker, undo, mask, spec: LSHSpec, dout, lse, delta, n_heads: int, n_rounds: int, bucket: int):
+def lsh_attn_bwd(qk, v, sticker, undo, mask, spec: LSHSpec, dout, lse, delta, n_heads: int, n_rounds: int, bucket: int,
+                 out_dqk: Optional[torch.Tensor] = None, out_dv: Optional[torch.Tensor] = None):
     """Backward of lsh_attn_fwd + lsh_merge_fwd (scores recomputed in-kernel) -> dqk, dv bf16 [B,T,H*64]."""
     ld = _token_major(qk, "qk")
     if _token_major(v, "v") != ld or _token_major(dout, "dout") != ld:
@@ -156,10 +157,13 @@ def lsh_attn_bwd(qk, v, sticker, undo, mask, spec: LSHSpec, dout, lse, delta, n_
     _lib.call("rtts_lsh_attn_bwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(mask), ctypes.byref(st), _ptr(dout),
               _ptr(lse), _ptr(delta), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), _ptr(part[3]), b, t, n_heads, dh, n_rounds,
               bucket, _stream())
-    dqk = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device)
-    dv = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device)
+    dqk = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device) if out_dqk is None else out_dqk
+    dv = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device) if out_dv is None else out_dv
+    ld_out = _token_major(dqk, "out_dqk")
+    if _token_major(dv, "out_dv") != ld_out:
+        raise RuntimeError("out_dqk and out_dv must share the token stride")
     _lib.call("rtts_lsh_grad_reduce", _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), _ptr(part[3]), _ptr(undo), _ptr(dqk),
-              _ptr(dv), c, b, t, n_heads, dh, n_rounds, bucket, _stream())
+              _ptr(dv), ld_out, b, t, n_heads, dh, n_rounds, bucket, _stream())
     return dqk, dv
 
 

@@ -1,0 +1,210 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/rtts_b200.h declares, the host mirror keeps
+the reference's constructor / state-dict contract, the reversible algebra (pure PyTorch) matches the oracle and the
+reference's golden gradients, and the data-parallel gradient averaging works over gloo with world_size 2."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from reformer_tts_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "rtts_b200.h")).read()
+    declared = set(re.findall(r"\b(rtts_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 12
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared - {"rtts_last_error", "rtts_abi_version"} == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
+    assert lib.rtts_abi_version() == 1
+    # argument validation happens before any CUDA call: a bad head size is reported, not launched
+    rc = lib.rtts_lsh_hash(None, 0, None, 1, None, 0, None, 1, 128, 1, 64, 1, 2, None)
+    assert rc != 0 and b"null pointer" in lib.rtts_last_error()
+
+
+def test_product_modules_refuse_cpu_tensors():
+    from reformer_tts_b200.lsh_attention import LSHSelfAttention
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        LSHSelfAttention(128, heads=2)(torch.randn(1, 128, 128))
+
+
+def test_unsupported_kwargs_raise_at_construction():
+    from reformer_tts_b200.lsh_attention import LSHSelfAttention
+    from reformer_tts_b200.model import FeedForward, LSHSelfAttentionWrapper
+    for bad in (dict(use_full_attn=True), dict(num_mem_kv=4), dict(dropout=0.1), dict(random_rotations_per_head=True),
+                dict(attend_across_buckets=False), dict(allow_duplicate_attention=False), dict(one_value_head=True),
+                dict(return_attn=True), dict(attn_chunks=2), dict(bucket_size=32), dict(heads=4)):
+        with pytest.raises(NotImplementedError):
+            LSHSelfAttention(512, **bad)
+    with pytest.raises(NotImplementedError):
+        FeedForward(512, 2048, dropout=0.1)
+    with pytest.raises(ValueError):
+        LSHSelfAttentionWrapper(512, causal=False, implementation="other", heads=8)
+
+
+def test_state_dict_keys_match_reference_model():
+    """Checkpoint compatibility: parameter names / shapes equal those of the reference ReformerTTS (HF variant, instantiated
+    from /root/reference by tests/golden/make_golden.py)."""
+    from reformer_tts_b200.model import ReformerTTS, config as C
+    want = json.load(open(os.path.join(GOLDEN, "state_dict_keys_hf.json")))
+    ours = {k: list(v.shape) for k, v in ReformerTTS(**C.reference_model_kwargs("huggingface-lsh")).state_dict().items()}
+    # transformers 5.x registers its mask constants as non-persistent buffers, so they are not in the golden list either
+    assert ours == want
+    rp = ReformerTTS(**C.reference_model_kwargs("baseline")).state_dict()
+    base = "enc.reformer.layers.blocks.0.f.net.fn.layer."
+    assert {k[len(base):] for k in rp if k.startswith(base)} == {"toqk.weight", "tov.weight", "to_out.weight", "to_out.bias"}
+    assert "dec.reformer.layers.blocks.4.f.net.fn.fn.net.3.bias" in rp and "dec.reformer.layers.blocks.2.f.net.fn.layer.in_proj_weight" in rp
+
+
+def test_config_loader_applies_reference_defaults():
+    from reformer_tts_b200.model import config as C
+    kw = C.reference_model_kwargs("bucket-size-64-18-06")
+    assert kw["enc_reformer_kwargs"]["depth"] == 6 and kw["dec_reformer_kwargs"]["self_attn_kwargs"]["bucket_size"] == 64
+    assert kw["enc_reformer_kwargs"]["attn_kwargs"]["post_attn_dropout"] == 0.15 and kw["pad_base"] == 256
+    assert C.reference_model_kwargs("baseline")["dec_reformer_kwargs"]["self_attn_kwargs"]["bucket_size"] == 128
+    with pytest.raises(KeyError):
+        C.model_kwargs({"num_mel_coeffs": 80, "dict_size": 76, "no_such_key": 1})
+
+
+def _mlp(d, seed):
+    torch.manual_seed(seed)
+    return nn.Sequential(nn.LayerNorm(d), nn.Linear(d, 2 * d), nn.ReLU(), nn.Linear(2 * d, d))
+
+
+def test_reversible_mirror_matches_reference_golden_gradients():
+    """The product's reversible.py is pure PyTorch, so it is checked on CPU against the gradients the reference's own file
+    produced (tests/golden/reversible_ref.npz)."""
+    from reformer_tts_b200.model.reversible import ReversibleBlock, ReversibleHalfResidual, ReversibleSequence, ReversibleSwap
+    z = np.load(os.path.join(GOLDEN, "reversible_ref.npz"))
+    nets = [_mlp(16, 10 + i) for i in range(7)]
+    blocks = nn.ModuleList([ReversibleBlock(nets[0], nets[1]), ReversibleBlock(nets[2], nets[3]), ReversibleHalfResidual(nets[4]),
+                            ReversibleSwap(), ReversibleHalfResidual(nets[5]), ReversibleSwap()])
+    seq = ReversibleSequence(blocks).train()
+    x = torch.from_numpy(z["x"]).requires_grad_(True)
+    y = seq(x, kwargs_list=[{}] * 6)
+    (y * torch.from_numpy(z["w"])).sum().backward()
+    assert (y.detach() - torch.from_numpy(z["y"])).abs().max().item() <= 1e-6
+    assert (x.grad - torch.from_numpy(z["dx"])).abs().max().item() <= 1e-5
+    for i, n in enumerate(nets[:6]):
+        for k, p in n.named_parameters():
+            assert (p.grad - torch.from_numpy(z[f"g{i}_{k}"])).abs().max().item() <= 1e-5, (i, k)
+    # public concatenated-tensor interface (forward / backward_pass) of a single block
+    blk = blocks[0]
+    xx = torch.from_numpy(z["x"])
+    yy = blk(xx)
+    x_rec, dx = blk.backward_pass(yy, torch.ones_like(yy))
+    assert (x_rec - xx).abs().max().item() <= 1e-5 and dx.shape == xx.shape
+
+
+def test_reversible_context_tensor_gets_summed_gradient():
+    """A tensor the blocks close over (the encoder output in the decoder) receives the sum of every block's gradient once."""
+    from reformer_tts_b200.model.reversible import ReversibleHalfResidual, ReversibleSequence, ReversibleSwap
+
+    class AddCtx(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = nn.Linear(8, 8)
+
+        def forward(self, x, key=None):
+            return self.lin(x) * key.mean(dim=1, keepdim=True)
+    torch.manual_seed(0)
+    blocks = nn.ModuleList([ReversibleHalfResidual(AddCtx()), ReversibleSwap(), ReversibleHalfResidual(AddCtx()), ReversibleSwap()])
+    seq = ReversibleSequence(blocks)
+    x = torch.randn(2, 4, 16, requires_grad=True)
+    key = torch.randn(2, 3, 8, requires_grad=True)
+    kw = [{"key": key}, {}, {"key": key}, {}]
+    seq(x, kwargs_list=kw).sum().backward()
+    gx, gk = x.grad.clone(), key.grad.clone()
+    x.grad = key.grad = None
+    h1, h2 = x.chunk(2, dim=2)
+    h1 = h1 + blocks[0].f.net(h2, key=key)
+    h1, h2 = h2, h1
+    h1 = h1 + blocks[2].f.net(h2, key=key)
+    (h1.sum() + h2.sum()).backward()
+    assert (gx - x.grad).abs().max().item() <= 1e-5 and (gk - key.grad).abs().max().item() <= 1e-5
+
+
+def test_chunk_and_withnorm_fuse_only_rowwise_functions():
+    from reformer_tts_b200.model import Chunk, WithNorm
+    calls = []
+
+    class Rowwise(nn.Module):
+        rowwise = True
+
+        def forward(self, x):
+            calls.append(x.shape[-2])
+            return x * 2
+
+    class NotRowwise(nn.Module):
+        def forward(self, x):
+            calls.append(x.shape[-2])
+            return x * 2
+    x = torch.randn(2, 256, 8)
+    assert torch.equal(Chunk(100, Rowwise(), along_dim=-2)(x), x * 2) and calls == [256]
+    calls.clear()
+    assert torch.equal(Chunk(100, NotRowwise(), along_dim=-2)(x), x * 2) and len(calls) == 86     # torch.chunk(256, 100) -> 86 pieces
+    wn = WithNorm(nn.LayerNorm, 8, NotRowwise())
+    assert not wn.rowwise and WithNorm(nn.LayerNorm, 8, Rowwise()).rowwise
+    assert torch.allclose(wn(x), nn.functional.layer_norm(x, (8,)) * 2, atol=1e-6)
+
+
+def test_shard_batch_partitions_exactly():
+    from reformer_tts_b200.distributed import shard_batch
+    for total, world in [(64, 8), (20, 8), (7, 2), (3, 4)]:
+        spans = [shard_batch(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from torch import nn
+from reformer_tts_b200.distributed import GradientAverager, shard_batch
+from reformer_tts_b200.model.reversible import ReversibleBlock, ReversibleSequence
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+torch.manual_seed(0)
+def mlp(): return nn.Sequential(nn.LayerNorm(8), nn.Linear(8, 16), nn.ReLU(), nn.Linear(16, 8))
+class Net(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.inp = nn.Linear(8, 8)
+        self.layers = ReversibleSequence(nn.ModuleList([ReversibleBlock(mlp(), mlp()) for _ in range(3)]))
+    def forward(self, x):
+        h = self.inp(x)
+        return self.layers(torch.cat([h, h], -1), kwargs_list=[{}] * 3).sum()
+net = Net()
+data = torch.randn(6, 5, 8)
+lo, hi = shard_batch(6, dist.get_rank(), 2)
+avg = GradientAverager(net, overlap=(sys.argv[4] == "1"))
+(net(data[lo:hi]) / (hi - lo)).backward()
+avg.finish()
+if dist.get_rank() == 0:
+    ref = Net(); ref.load_state_dict(net.state_dict())
+    (0.5 * (ref(data[:3]) / 3 + ref(data[3:]) / 3)).backward()
+    err = max((p.grad - q.grad).abs().max().item() for p, q in zip(net.parameters(), ref.parameters()))
+    print("MAXERR", err)
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("overlap", ["0", "1"])
+def test_data_parallel_gradient_average_gloo_world2(tmp_path, overlap):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + (os.getpid() % 400) + (50 if overlap == "1" else 0))
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), overlap], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    err = float(re.search(r"MAXERR ([0-9.e+-]+)", outs[0][0]).group(1))
+    assert err <= 1e-5, err

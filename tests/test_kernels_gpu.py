@@ -1,0 +1,231 @@
+"""Stage-wise parity of every kernel against the CPU oracle, called through the C ABI (reformer_tts_b200.ops is a
+ctypes shim over libreformer_b200.so).  Each stage is fed the oracle's inputs: integer stages must be
+bit-exact, floating-point stages within the tolerances of tests/_util.py."""
+import pytest
+import torch
+
+from _util import TOL_BF16_STORED, TOL_FP32, rel_l2, to_bh
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from reformer_tts_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def core():
+    from oracle import lsh_core
+    return lsh_core
+
+
+# ---------------------------------------------------------------------------------------------- hash / sort
+@pytest.mark.parametrize("nb,per_head,pad,T", [(4, False, False, 256), (8, False, False, 1024), (16, False, False, 1024),
+                                               (16, True, True, 1024), (8, True, False, 256), (256, False, False, 2048)])
+def test_hash_bit_exact(ops, core, nb, per_head, pad, T):
+    torch.manual_seed(nb + T)
+    B, H, R = 3, 8, 8 if nb < 256 else 4
+    qk = torch.randn(B, T, H * 64, device=DEV).bfloat16()
+    rot = torch.randn(H if per_head else 1, 64, R, nb // 2, device=DEV)
+    mask = None
+    if pad:
+        mask = torch.ones(B, T, dtype=torch.bool, device=DEV)
+        mask[0, -37:] = False
+    got = ops.lsh_hash(qk, rot, H, R, nb, None if mask is None else mask.to(torch.uint8), pad).cpu().view(B * H, -1).long()
+    q = to_bh(qk, H)
+    rt = rot.cpu()
+    rt = rt[None].expand(B, -1, -1, -1, -1).reshape(B * H, 64, R, nb // 2) if per_head else rt
+    m = None if mask is None else mask[:, None, :].expand(B, H, T).reshape(B * H, T).cpu()
+    want = core.hash_buckets(q, rt, R, nb, m)
+    # exact wherever the fp64 top-2 margin is not a rounding-level tie (SURVEY.md 7 hard parts)
+    proj = torch.einsum("ntd,ndri->nrti", q.double(), rt.double().expand(B * H, -1, -1, -1))
+    top2 = torch.cat([proj, -proj], -1).topk(2, dim=-1).values
+    safe = ((top2[..., 0] - top2[..., 1]) > 1e-5 * q.double().norm(dim=-1)[:, None, :]).reshape(B * H, -1)
+    assert torch.equal(got[safe], want[safe])
+    assert int((got != want).sum()) <= max(2, int(2e-5 * want.numel())), "more flips than fp32 ties can explain"
+
+
+@pytest.mark.parametrize("T,R,nb,extra", [(256, 8, 4, 0), (1024, 8, 16, 0), (1024, 8, 16, 1), (2048, 4, 32, 0), (16384, 4, 256, 0), (128, 1, 2, 0)])
+def test_sort_bit_exact(ops, core, T, R, nb, extra):
+    torch.manual_seed(T + nb)
+    rows = 5
+    ids = nb + extra
+    buckets = torch.randint(0, ids, (rows, R, T)) + ids * torch.arange(R).view(1, R, 1)
+    buckets = buckets.view(rows, R * T)
+    if T >= 1024:
+        buckets[0] = (torch.arange(R).view(R, 1) * ids).expand(R, T).reshape(-1)      # everything in one bucket per round
+    sticker, undo = ops.lsh_sort(buckets.to(torch.int32).to(DEV), T, R, ids)
+    want_s, want_u = core.sort_buckets(buckets, T)
+    assert torch.equal(sticker.cpu().long(), want_s)
+    assert torch.equal(undo.cpu().long(), want_u)
+
+
+# ---------------------------------------------------------------------------------------------- attention forward / merge / backward
+def _attention_case(core, impl, causal, pad, bucket, B=2, T=512, H=2, R=4, seed=0, clustered=False):
+    torch.manual_seed(seed)
+    qk = torch.randn(B, T, H * 64, device=DEV).bfloat16()
+    v = torch.randn(B, T, H * 64, device=DEV).bfloat16()
+    nb = T // bucket
+    buckets = torch.randint(0, nb, (B * H, R, T))
+    if clustered:       # unbalanced buckets: chunks straddle bucket boundaries
+        buckets = (buckets.float() ** 2 / nb).long().clamp_(0, nb - 1)
+    buckets = (buckets + nb * torch.arange(R).view(1, R, 1)).view(B * H, R * T)
+    mask = None
+    if pad:
+        mask = torch.ones(B, T, dtype=torch.bool)
+        mask[0, -100:] = False
+        mask[1, -3:] = False
+    spec_o = (core.LSHSpec.reformer_pytorch if impl == "rp" else core.LSHSpec.huggingface)(64, causal)
+    m_bh = None if mask is None else mask[:, None, :].expand(B, H, T).reshape(B * H, T)
+    return dict(qk=qk, v=v, buckets=buckets, mask=mask, m_bh=m_bh, spec_o=spec_o, nb=nb, B=B, T=T, H=H, R=R, bucket=bucket, impl=impl, causal=causal)
+
+
+def _gpu_spec(ops, c):
+    return (ops.LSHSpec.reformer_pytorch if c["impl"] == "rp" else ops.LSHSpec.huggingface)(64, c["causal"])
+
+
+@pytest.mark.parametrize("bucket", [64, 128])
+@pytest.mark.parametrize("impl", ["rp", "hf"])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("pad", [False, True])
+def test_attention_forward_and_merge(ops, core, bucket, impl, causal, pad):
+    c = _attention_case(core, impl, causal, pad, bucket, clustered=pad)
+    B, T, H, R = c["B"], c["T"], c["H"], c["R"]
+    sticker, undo = core.sort_buckets(c["buckets"], T)
+    so, slse = core.chunk_attention(to_bh(c["qk"], H), to_bh(c["v"], H), sticker, bucket, R, c["spec_o"], c["m_bh"])
+    out_ref, o_ref, lse_ref = core.unsort_and_merge(so, slse, undo, R)
+    mk = None if c["mask"] is None else c["mask"].to(torch.uint8).to(DEV)
+    o, lse = ops.lsh_attn_fwd(c["qk"], c["v"], sticker.to(torch.int32).to(DEV).view(B, H, R * T), mk, _gpu_spec(ops, c), H, R, bucket)
+    assert rel_l2(o.view(B * H, R, T, 64), o_ref) <= TOL_BF16_STORED
+    # lse is fp32: absolute 1e-4, except rows whose only target is themselves (lse = self_value ~ -5e4: one fp32 ulp = 4e-3)
+    assert ((lse.cpu().view(B * H, R, T) - lse_ref).abs() <= 1e-4 + 2e-7 * lse_ref.abs()).all()
+    out, lse_tot = ops.lsh_merge_fwd(o, lse)
+    assert rel_l2(to_bh(out, H), out_ref) <= TOL_BF16_STORED
+    want_tot = torch.logsumexp(lse_ref, 1)
+    assert ((lse_tot.cpu().view(B * H, T) - want_tot).abs() <= 1e-4 + 2e-7 * want_tot.abs()).all()
+
+
+@pytest.mark.parametrize("bucket", [64, 128])
+@pytest.mark.parametrize("impl", ["rp", "hf"])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("pad", [False, True])
+def test_attention_backward(ops, core, bucket, impl, causal, pad):
+    c = _attention_case(core, impl, causal, pad, bucket, seed=1)
+    B, T, H, R = c["B"], c["T"], c["H"], c["R"]
+    dout = torch.randn(B, T, H * 64, device=DEV).bfloat16()
+    q32 = to_bh(c["qk"], H).requires_grad_(True)
+    v32 = to_bh(c["v"], H).requires_grad_(True)
+    res = core.lsh_attention(q32, v32, c["buckets"], bucket, R, c["spec_o"], c["m_bh"])
+    (res["out"] * to_bh(dout, H)).sum().backward()
+    sticker, undo = ops.lsh_sort(c["buckets"].to(torch.int32).to(DEV).view(B, H, R * T), T, R, c["nb"])
+    mk = None if c["mask"] is None else c["mask"].to(torch.uint8).to(DEV)
+    spec = _gpu_spec(ops, c)
+    o, lse_r = ops.lsh_attn_fwd(c["qk"], c["v"], sticker, mk, spec, H, R, bucket)
+    out, lse = ops.lsh_merge_fwd(o, lse_r)
+    delta = ops.lsh_delta(dout, out, H)
+    dqk, dv = ops.lsh_attn_bwd(c["qk"], c["v"], sticker, undo, mk, spec, dout, lse, delta, H, R, bucket)
+    assert rel_l2(to_bh(dqk, H), q32.grad) <= TOL_BF16_STORED
+    assert rel_l2(to_bh(dv, H), v32.grad) <= TOL_BF16_STORED
+
+
+def test_attention_first_chunk_looks_back_at_last_chunk_of_previous_round(ops, core):
+    """Look-one-back wraps: chunk 0 of round r sees the last chunk of round r-1, and chunk 0 of round 0 the very last
+    chunk (rp R6).  One distinctive value row in the last chunk must reach queries of the first chunk."""
+    B, T, H, R, bucket = 1, 256, 1, 2, 64
+    qk = torch.randn(B, T, 64, device=DEV).bfloat16()
+    v = torch.zeros(B, T, 64, device=DEV).bfloat16()
+    nb = T // bucket
+    buckets = (torch.arange(T) // bucket).view(1, 1, T) + nb * torch.arange(R).view(1, R, 1)     # identity sort
+    buckets = buckets.view(1, R * T)
+    v[0, T - 1] = 7.0      # last token of the last chunk
+    sticker, undo = core.sort_buckets(buckets, T)
+    spec_o = core.LSHSpec.reformer_pytorch(64, False)
+    ref = core.lsh_attention(to_bh(qk, 1), to_bh(v, 1), buckets, bucket, R, spec_o)
+    o, lse = ops.lsh_attn_fwd(qk, v, sticker.to(torch.int32).to(DEV).view(1, 1, -1), None, ops.LSHSpec.reformer_pytorch(64, False), 1, R, bucket)
+    out, _ = ops.lsh_merge_fwd(o, lse)
+    assert ref["out"][0, :bucket].abs().min() > 0        # oracle: first chunk sees token T-1
+    assert rel_l2(to_bh(out, 1), ref["out"]) <= TOL_BF16_STORED
+
+
+def test_attention_sizes_of_baseline_configs(ops, core):
+    """Full-size property check (no oracle): merge weights sum to one, outputs finite, and a second run is bit-identical."""
+    B, T, H, R, bucket = 4, 1024, 8, 8, 64
+    torch.manual_seed(3)
+    qk = torch.randn(B, T, H * 64, device=DEV).bfloat16()
+    v = torch.ones(B, T, H * 64, device=DEV).bfloat16()      # constant V: every convex combination returns exactly 1
+    rot = torch.randn(1, 64, R, (T // bucket) // 2, device=DEV)
+    buckets = ops.lsh_hash(qk, rot, H, R, T // bucket)
+    sticker, undo = ops.lsh_sort(buckets, T, R, T // bucket)
+    idx = torch.arange(R * T, device=DEV, dtype=torch.int32).expand(B, H, -1)
+    assert torch.equal(torch.gather(undo, 2, sticker.long()), idx)                                  # undo inverts sticker
+    sorted_b = torch.gather(buckets, 2, sticker.long())
+    assert bool((sorted_b[..., 1:] >= sorted_b[..., :-1]).all())                                    # sortedness
+    spec = ops.LSHSpec.reformer_pytorch(64, True)
+    o1, l1 = ops.lsh_attn_fwd(qk, v, sticker, None, spec, H, R, bucket)
+    o2, l2 = ops.lsh_attn_fwd(qk, v, sticker, None, spec, H, R, bucket)
+    assert torch.equal(o1, o2) and torch.equal(l1, l2)                                              # deterministic
+    out, lse = ops.lsh_merge_fwd(o1, l1)
+    assert torch.isfinite(out.float()).all() and (out.float() - 1).abs().max().item() <= 2 ** -7    # rows of P sum to 1
+
+
+# ---------------------------------------------------------------------------------------------- GEMM / row-wise kernels
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (256, 384, 512), (2048, 2048, 512), (1024, 512, 2048)])
+def test_gemm_layouts_and_epilogues(ops, m, n, k):
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k, device=DEV).bfloat16()
+    b = torch.randn(n, k, device=DEV).bfloat16()
+    ref = a.double() @ b.double().t()
+    at, bt = a.t().contiguous(), b.t().contiguous()
+    for amn, bmn in [(False, False), (True, False), (False, True), (True, True)]:
+        c = ops.gemm(at if amn else a, bt if bmn else b, a_mn_major=amn, b_mn_major=bmn)
+        assert rel_l2(c, ref) <= 1e-5, (amn, bmn)
+    bias = torch.randn(n, device=DEV)
+    gate = torch.randn(m, n, device=DEV).bfloat16()
+    assert rel_l2(ops.gemm(a, b, bias=bias, relu=True, out_dtype=torch.bfloat16), torch.relu(ref + bias.double())) <= TOL_BF16_STORED
+    cs = torch.zeros(n, device=DEV)
+    gated = ops.gemm(a, b, gate=gate, colsum=cs, out_dtype=torch.bfloat16)
+    want = ref * (gate.double() > 0)
+    assert rel_l2(gated, want) <= TOL_BF16_STORED and rel_l2(cs, want.sum(0)) <= 1e-4
+    if k >= 512:
+        acc = torch.full((m, n), 2.0, device=DEV)
+        ops.gemm(at, bt, a_mn_major=True, b_mn_major=True, out=acc, accumulate=True, split_k=4)
+        assert rel_l2(acc, ref + 2) <= 1e-5
+
+
+def test_gemm_rejects_bad_shapes(ops):
+    a = torch.randn(100, 64, device=DEV).bfloat16()
+    b = torch.randn(128, 64, device=DEV).bfloat16()
+    with pytest.raises(RuntimeError, match="multiples of 128"):
+        ops.gemm(a, b)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.gemm(a.cpu(), b.cpu())
+
+
+@pytest.mark.parametrize("dim", [128, 512])
+def test_layernorm_forward_backward(ops, dim):
+    torch.manual_seed(dim)
+    x = torch.randn(4096 + 8, dim, device=DEV) * 2 + 0.5
+    g, bt = torch.randn(dim, device=DEV), torch.randn(dim, device=DEV)
+    y, mean, rstd = ops.layernorm_fwd(x, g, bt)
+    xr, gr, br = x.clone().requires_grad_(True), g.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (dim,), gr, br, 1e-5)
+    assert rel_l2(y, yr) <= TOL_BF16_STORED
+    dy = torch.randn_like(x)
+    yr.backward(dy)
+    dg, db = torch.ones(dim, device=DEV), torch.ones(dim, device=DEV)       # accumulate semantics: += on top of 1
+    dx = ops.layernorm_bwd(dy, x, g, mean, rstd, dg, db)
+    assert rel_l2(dx, xr.grad) <= 1e-5 and rel_l2(dg - 1, gr.grad) <= 1e-4 and rel_l2(db - 1, br.grad) <= 1e-4
+
+
+def test_cast_colsum_and_delta(ops):
+    x = torch.randn(1000, 512, device=DEV)
+    cs = torch.zeros(512, device=DEV)
+    y = ops.cast_bf16_colsum(x, cs)
+    assert torch.equal(y, x.bfloat16()) and rel_l2(cs, x.sum(0)) <= 1e-5
+    a = torch.randn(3, 256, 512, device=DEV).bfloat16()
+    o = torch.randn(3, 256, 512, device=DEV).bfloat16()
+    want = (a.float() * o.float()).view(3, 256, 8, 64).sum(-1).permute(0, 2, 1)
+    assert rel_l2(ops.lsh_delta(a, o, 8), want) <= 1e-5
