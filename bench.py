@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""ReformerTTS training-step benchmark (BASELINE.json metric: train mel-frames/s, fwd+bwd, and LSH-attention % of roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config NAME] [--batch B]
+
+Contract (see the task description): one JSON line on rank 0.  A "step" is one full training step of the named reference
+config on a synthetic LJSpeech-shaped batch: forward, TTSLoss, backward through the reversible stacks
+(with recompute), gradient all-reduce when N > 1, and a fused AdamW update.  ``value`` is measured with the batch resident
+in HBM; ``e2e`` repeats the measurement through the public module API with the batch in pinned HOST memory (H2D copies and
+the D2H read of the loss inside the timed region).  ``--impl reference`` times the CPU restatement of the reference path
+(oracle/model.py - the reference itself cannot travel to the GPU box and reformer_pytorch is not installable) on all host
+cores, on a bounded sample of the same workload.  The oracle is only ever the checker / the timed baseline here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_CONFIG = "bucket-size-64-18-06"       # BASELINE.json configs[1]: the configuration the metric is quoted on
+PHONEMES, FRAMES, N_MELS = 200, 800, 80       # "~200 phonemes -> ~800x80 mel frames" (BASELINE.json configs[0])
+
+
+def synthetic_batch(batch: int, frames: int = FRAMES, phonemes: int = PHONEMES, seed: int = 42, pin: bool = False):
+    """Layout of the reference collate function (ref:reformer_tts/dataset/utils.py:5-42), SURVEY.md 8(d)."""
+    g = torch.Generator().manual_seed(seed)
+    ph = torch.randint(1, 77, (batch, phonemes), generator=g)
+    spec = torch.zeros(batch, frames + 1, N_MELS)
+    spec[:, 1:] = (torch.randn(batch, frames, N_MELS, generator=g) * 2 - 5).clamp_(-11.5129, 2.0)
+    stop = torch.zeros(batch, frames)
+    stop[:, -1] = 1
+    mask = torch.ones(batch, frames, N_MELS)
+    out = {"phonemes": ph, "spectrogram": spec, "stop_tokens": stop, "loss_mask": mask}
+    return {k: v.pin_memory() for k, v in out.items()} if pin else out
+
+
+def train_step(model, loss_fn, optimizer, batch, averager=None):
+    """ref:reformer_tts/training/wrappers.py:53-105 (forward + TTSLoss) + backward + AdamW."""
+    spec = batch["spectrogram"]
+    raw, post, stop, _ = model(batch["phonemes"], spec[:, :-1], batch["loss_mask"].mean(dim=-1))
+    loss = loss_fn(raw, post, stop.view(stop.shape[0], -1), spec[:, 1:], batch["stop_tokens"], batch["loss_mask"])[0]
+    loss.backward()
+    if averager is not None:
+        averager.finish()
+    optimizer.step()
+    optimizer.zero_grad(set_to_none=True)
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}   # B200_PROFILING.md
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.path = f"/tmp/rtts_clocks_{os.getpid()}.csv"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.proc.wait()
+        sm, mx, reasons = [], 0, set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0]))
+            mx = max(mx, int(f[1]))
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        busy = [c for c in sm if c > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def lsh_layer_shapes(kwargs, batch):
+    """(name, B, T, R, bucket, D) of the encoder / decoder LSH layers at the padded lengths."""
+    pad = kwargs["pad_base"]
+    tp, tm = -(-PHONEMES // pad) * pad, -(-FRAMES // pad) * pad
+    e, d = kwargs["enc_reformer_kwargs"], kwargs["dec_reformer_kwargs"]
+    return {"enc": (batch, tp, e["attn_kwargs"]["n_hashes"], e["attn_kwargs"]["bucket_size"], kwargs["embedding_dim"], e["depth"]),
+            "dec": (batch, tm, d["self_attn_kwargs"]["n_hashes"], d["self_attn_kwargs"]["bucket_size"], kwargs["embedding_dim"], d["depth"])}
+
+
+# ------------------------------------------------------------------------------------------------------------------ arms
+def run_reference(args, kwargs, world, rank):
+    """CPU arm: oracle restatement of the reference path, all host threads, bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle.model import ReformerTTSOracle
+    from reformer_tts_b200.model.loss import TTSLoss
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(42)
+    model = ReformerTTSOracle(**kwargs).train()
+    loss_fn = TTSLoss(torch.tensor(5.))
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    # bounded sample: ONE utterance; shorten it (fewer mel frames, same phoneme/frame ratio) until the whole run fits ~4 minutes
+    frames, budget = FRAMES, 240.0
+    total_steps = args.steps + args.warmup
+    while True:
+        batch = synthetic_batch(1, frames=frames, phonemes=max(8, frames // 4))
+        t0 = time.perf_counter()
+        train_step(model, loss_fn, opt, batch)
+        t_probe = time.perf_counter() - t0
+        if t_probe * total_steps <= budget or frames <= 100:
+            break
+        frames //= 2
+    for _ in range(max(0, args.warmup - 1)):
+        train_step(model, loss_fn, opt, batch)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        train_step(model, loss_fn, opt, batch)
+    dt = time.perf_counter() - t0
+    value = frames * args.steps / dt
+    sample = f"1 utterance x {frames} mel frames ({max(8, frames // 4)} phonemes) per step, {args.steps} steps, fp32, torch {torch.__version__} CPU"
+    line = {"impl": "reference", "metric": "train_mel_frames_per_sec", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"ReformerTTS config/{args.config}.yml training step (fwd + loss + reversible bwd + AdamW)", "bounded_sample": sample},
+            "cpu_baseline": {"value": value, "unit": "mel-frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(kwargs, seconds_budget=40.0):
+    """Rank-0, N=1 only: the oracle port timed beside the GPU number on a bounded sample (one short utterance, one step)."""
+    from oracle.model import ReformerTTSOracle
+    from reformer_tts_b200.model.loss import TTSLoss
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(42)
+    model = ReformerTTSOracle(**kwargs).train()
+    loss_fn = TTSLoss(torch.tensor(5.))
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    frames = 200
+    batch = synthetic_batch(1, frames=frames, phonemes=50)
+    t0 = time.perf_counter()
+    train_step(model, loss_fn, opt, batch)
+    dt = time.perf_counter() - t0
+    return {"value": frames / dt, "unit": "mel-frames/s", "cores": cores, "kind": "port",
+            "sample": f"1 utterance x {frames} mel frames (50 phonemes), 1 step incl. first-call overheads, fp32 CPU oracle (oracle/model.py)"}
+
+
+def run_ours(args, kwargs, world, rank, local_rank):
+    import torch.distributed as dist
+    from reformer_tts_b200 import _lib, ops
+    from reformer_tts_b200.distributed import GradientAverager
+    from reformer_tts_b200.model import ReformerTTS
+    from reformer_tts_b200.model.loss import TTSLoss
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = True      # non-hot-path torch modules (cross-attention, pre/post nets): fp32 storage, TF32 math
+    torch.backends.cudnn.allow_tf32 = True
+    torch.manual_seed(42)                               # same initial weights on every rank
+    model = ReformerTTS(**kwargs).to(dev).train()
+    torch.manual_seed(42 + rank)                        # ref:reformer_tts/training/train.py:16 seeds 42; ranks draw different rotations / dropout
+    loss_fn = TTSLoss(torch.tensor(5.)).to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-6, fused=True)
+    averager = GradientAverager(model) if world > 1 else None
+    batch_size = args.batch
+    host = synthetic_batch(batch_size, seed=42 + rank, pin=True)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        train_step(model, loss_fn, opt, resident, averager)
+    sync()
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------------------------------
+    shapes = lsh_layer_shapes(kwargs, batch_size)
+    timer = ops.KernelTimer(only=("lsh_attn_fwd", "lsh_attn_bwd"))
+    ops.set_kernel_timer(timer)
+    launches0 = ops.launch_count()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    start.record()
+    for _ in range(args.steps):
+        train_step(model, loss_fn, opt, resident, averager)
+    end.record()
+    sync()
+    ms = start.elapsed_time(end)
+    clock_info = clocks.stop() if clocks else None
+    launches = ops.launch_count() - launches0
+    kernel_ms = timer.summary()
+    ops.set_kernel_timer(None)
+    # ---- timed region 2: end to end from pinned host memory, loss read back every step -------------------------------------
+    sync()
+    start.record()
+    for _ in range(args.steps):
+        on_dev = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        loss = train_step(model, loss_fn, opt, on_dev, averager)
+        loss_host = loss.item()
+    end.record()
+    sync()
+    ms_e2e = start.elapsed_time(end)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    frames_per_step = batch_size * FRAMES * world
+    value = frames_per_step * args.steps / (ms / 1e3)
+    e2e = frames_per_step * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        b, t, r, bucket, d, depth = shapes["dec"]
+        flops_fwd = 8.0 * b * r * t * bucket * d          # QK^T + PV over a bucket x 2*bucket window, per decoder layer launch
+        key_fwd, key_bwd = f"lsh_attn_fwd[T={t}]", f"lsh_attn_bwd[T={t}]"
+        fwd_ms, bwd_ms = kernel_ms.get(key_fwd, {}).get("avg_ms"), kernel_ms.get(key_bwd, {}).get("avg_ms")
+        peak = peaks["bf16_tflops_sustained"]
+        roofline = {"bound": "tensor", "kernel": "lsh_attn_fwd_kernel<64> (decoder shape)", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
+                    "traffic": None, "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)"}
+        if fwd_ms:
+            roofline["achieved"] = flops_fwd / (fwd_ms * 1e-3) / 1e12
+            roofline["frac"] = roofline["achieved"] / peak
+            roofline["avg_launch_ms"] = fwd_ms
+            roofline["launches_timed"] = kernel_ms[key_fwd]["count"]
+        if bwd_ms:
+            roofline["bwd_kernel"] = {"kernel": "lsh_attn_bwd_kernel<64> (decoder shape)", "avg_launch_ms": bwd_ms,
+                                      "achieved": 2.5 * flops_fwd / (bwd_ms * 1e-3) / 1e12, "frac": 2.5 * flops_fwd / (bwd_ms * 1e-3) / 1e12 / peak}
+        roofline["share_of_step"] = {k: v["total_ms"] / ms for k, v in kernel_ms.items()}
+        cpu = cpu_baseline_leg(kwargs) if world == 1 and not args.no_cpu_baseline else None
+        line = {"metric": "train_mel_frames_per_sec", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"ReformerTTS config/{args.config}.yml training step (fwd + loss + reversible bwd + AdamW)",
+                           "per_gpu_batch": batch_size, "global_batch": batch_size * world, "phonemes": PHONEMES, "mel_frames": FRAMES,
+                           "padded_lengths": [shapes["enc"][1], shapes["dec"][1]], "parallelism": f"dp{world}",
+                           "precision": "bf16 MMA operands, fp32 accumulate, fp32 residual stream / master weights; non-hot-path torch modules fp32 storage + TF32",
+                           "l2": "no flush: one step streams several GB of activations (>> 126 MB L2) through HBM",
+                           "optimizer": "torch AdamW(fused=True) inside the timed region"},
+                "e2e": {"value": e2e, "unit": "mel-frames/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "last_loss": loss_host},
+                "gpu_launches": launches, "clocks": clock_info, "roofline": roofline}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=DEFAULT_CONFIG)
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the reference config's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    from reformer_tts_b200.model import config as C
+    kwargs = C.reference_model_kwargs(args.config)
+    if args.batch is None:
+        args.batch = C.REFERENCE_BATCH[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch multi-GPU runs with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N bench.py --gpus N ...")
+    if args.impl == "reference":
+        run_reference(args, kwargs, world, rank)
+    else:
+        run_ours(args, kwargs, world, rank, local_rank)
+
+
+if __name__ == "__main__":
+    main()

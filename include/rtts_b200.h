@@ -79,7 +79,7 @@ int rtts_lsh_delta(const void* dout, const void* out, int64_t ld, float* delta, 
 
 /* Backward of rtts_lsh_attn_fwd + rtts_lsh_merge_fwd with in-kernel recompute of the scores
  * (autograd of rp R4-R11; the per-round o / lse of the forward are not needed).  Inputs: qk, v, sticker,
- * mask as in forward; dout bf16 [B,T,H*dh] = gradient of the merged output; lse [B,H,T] from
+ * mask as in forward; dout bf16 [B,T,H*dh] (ld_dout) = gradient of the merged output; lse [B,H,T] from
  * rtts_lsh_merge_fwd; delta [B,H,T] from rtts_lsh_delta.  Outputs, fp32 [B,H,R,T,dh], scattered to the
  * UNSORTED slot like the forward:
  *   dq_a  query-role gradient from the keys of the CTA that owns the slot as a key,
@@ -88,8 +88,8 @@ int rtts_lsh_delta(const void* dout, const void* out, int64_t ld, float* delta, 
  *   dxk   key-role gradient with the key-normalisation Jacobian already applied,
  *   dv    value gradient. */
 int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
-                      const rtts_lsh_spec* spec_host, const void* dout, const float* lse, const float* delta,
-                      float* dq_a, float* dq_b, float* dxk, float* dv_rounds, int B, int T, int H, int dh, int R,
+                      const rtts_lsh_spec* spec_host, const void* dout, int64_t ld_dout, const float* lse,
+                      const float* delta, float* dq_a, float* dq_b, float* dxk, float* dv_rounds, int B, int T, int H, int dh, int R,
                       int bucket, void* stream);
 
 /* Sum the per-round gradients over the R rounds: dqk = sum_r (dq_a + dq_b + dxk), dv = sum_r dv_rounds,

@@ -36,7 +36,8 @@ struct AttnBwdParams {
   const __nv_bfloat16* qk;
   const __nv_bfloat16* v;
   const __nv_bfloat16* dout;
-  int64_t ld;
+  int64_t ld;      // token stride of qk / v
+  int64_t ld_do;   // token stride of dout
   const int32_t* sticker;
   const uint8_t* mask;
   const float* lse;     // [B,H,T]
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(128) lsh_attn_bwd_kernel(const AttnBwdParams p
       const int64_t off = (static_cast<int64_t>(b) * p.T + pos[i]) * p.ld + head_off;
       const uint32_t so = sw128_offset(j, c);
       cp_async16(sX + so, p.qk + off);
-      cp_async16(sDO + so, p.dout + off);
+      cp_async16(sDO + so, p.dout + (static_cast<int64_t>(b) * p.T + pos[i]) * p.ld_do + head_off);
       if (j < kKeyRows) cp_async16(sV + so, p.v + off);
     }
     cp_async_commit();
@@ -394,20 +395,20 @@ int launch_attn_bwd(const AttnBwdParams& p, int ctas, cudaStream_t stream) {
 using namespace rtts;
 
 extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
-                                 const rtts_lsh_spec* spec, const void* dout, const float* lse, const float* delta, float* dq_a,
+                                 const rtts_lsh_spec* spec, const void* dout, int64_t ld_dout, const float* lse, const float* delta, float* dq_a,
                                  float* dq_b, float* dxk, float* dv_rounds, int B, int T, int H, int dh, int R, int bucket,
                                  void* stream) {
   RTTS_REQUIRE(qk && v && sticker && spec && dout && lse && delta && dq_a && dq_b && dxk && dv_rounds, "rtts_lsh_attn_bwd: null pointer");
   RTTS_REQUIRE(dh == kBDh, "rtts_lsh_attn_bwd: head size %d unsupported (64 only)", dh);
   RTTS_REQUIRE(bucket == 64 || bucket == 128, "rtts_lsh_attn_bwd: bucket size %d unsupported (64 or 128)", bucket);
   RTTS_REQUIRE(T % (2 * bucket) == 0, "rtts_lsh_attn_bwd: T=%d must be a multiple of 2*bucket", T);
-  RTTS_REQUIRE(ld % 8 == 0 && ((reinterpret_cast<uintptr_t>(qk) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0,
+  RTTS_REQUIRE(ld % 8 == 0 && ld_dout % 8 == 0 && ((reinterpret_cast<uintptr_t>(qk) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0,
                "rtts_lsh_attn_bwd: tensors must be 16-byte aligned");
   AttnBwdParams p;
   p.qk = static_cast<const __nv_bfloat16*>(qk);
   p.v = static_cast<const __nv_bfloat16*>(v);
   p.dout = static_cast<const __nv_bfloat16*>(dout);
-  p.ld = ld; p.sticker = sticker; p.mask = mask; p.lse = lse; p.delta = delta;
+  p.ld = ld; p.ld_do = ld_dout; p.sticker = sticker; p.mask = mask; p.lse = lse; p.delta = delta;
   p.dq_a = dq_a; p.dq_b = dq_b; p.dxk = dxk; p.dv = dv_rounds;
   p.T = T; p.H = H; p.R = R; p.tiles_per_row = R * T / kKeyRows;
   p.score_scale = spec->score_scale;

@@ -41,6 +41,66 @@ class LSHSpec:
                                   int(self.causal))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Launch accounting and optional per-kernel CUDA-event timing (bench.py: gpu_launches, roofline.achieved)
+_LAUNCHES = 0
+_TIMER = None
+
+
+class KernelTimer:
+    """Records a CUDA-event pair on the launching stream around selected kernels; ``summary()`` after a synchronize."""
+
+    def __init__(self, only=None):
+        self.only = None if only is None else tuple(only)
+        self.records = []      # (name, start, end)
+
+    def wants(self, name: str) -> bool:
+        return self.only is None or name.split("[")[0] in self.only
+
+    def summary(self):
+        out = {}
+        for name, a, b in self.records:
+            e = out.setdefault(name, {"count": 0, "total_ms": 0.0})
+            e["count"] += 1
+            e["total_ms"] += a.elapsed_time(b)
+        for e in out.values():
+            e["avg_ms"] = e["total_ms"] / e["count"]
+        return out
+
+
+def set_kernel_timer(timer: Optional["KernelTimer"]):
+    global _TIMER
+    _TIMER = timer
+
+
+def launch_count() -> int:
+    """Number of kernels of libreformer_b200.so launched so far by this process."""
+    return _LAUNCHES
+
+
+def _launch(tag: str, name: str, *args):
+    global _LAUNCHES
+    _LAUNCHES += 1
+    timer = _TIMER
+    if timer is not None and timer.wants(tag):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.call(name, *args)
+        b.record()
+        timer.records.append((tag, a, b))
+    else:
+        _lib.call(name, *args)
+
+
+def _tag(name: str, scope: dict) -> str:
+    """Kernel name plus the shape key the benchmark groups by (sequence length for the LSH kernels, MxNxK for GEMMs)."""
+    if name.startswith("lsh_") and "t" in scope and isinstance(scope["t"], int):
+        return f"{name}[T={scope['t']}]"
+    if name == "gemm_bf16":
+        return f"gemm_bf16[{scope['m']}x{scope['n']}x{scope['k']}]"
+    return name
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -81,7 +141,7 @@ def lsh_hash(qk: torch.Tensor, rot: torch.Tensor, n_heads: int, n_rounds: int, n
         _check(pad_mask, torch.uint8, "pad_mask")
         pad_mask = pad_mask.contiguous()
     out = torch.empty((b, n_heads, n_rounds * t), dtype=torch.int32, device=qk.device)
-    _lib.call("rtts_lsh_hash", _ptr(qk), ld, _ptr(rot), rot.shape[0], _ptr(pad_mask), int(use_pad_bucket), _ptr(out),
+    _launch(_tag("lsh_hash", locals()), "rtts_lsh_hash", _ptr(qk), ld, _ptr(rot), rot.shape[0], _ptr(pad_mask), int(use_pad_bucket), _ptr(out),
               b, t, n_heads, dh, n_rounds, n_buckets, _stream())
     return out
 
@@ -92,7 +152,7 @@ def lsh_sort(buckets: torch.Tensor, seq_len: int, n_rounds: int, ids_per_round: 
     buckets = buckets.contiguous()
     rows = buckets.numel() // (n_rounds * seq_len)
     sticker, undo = torch.empty_like(buckets), torch.empty_like(buckets)
-    _lib.call("rtts_lsh_sort", _ptr(buckets), _ptr(sticker), _ptr(undo), rows, seq_len, n_rounds, ids_per_round, _stream())
+    _launch(_tag("lsh_sort", locals()), "rtts_lsh_sort", _ptr(buckets), _ptr(sticker), _ptr(undo), rows, seq_len, n_rounds, ids_per_round, _stream())
     return sticker, undo
 
 
@@ -112,7 +172,7 @@ def lsh_attn_fwd(qk: torch.Tensor, v: torch.Tensor, sticker: torch.Tensor, mask:
     o = torch.empty((b, n_heads, n_rounds, t, dh), dtype=torch.bfloat16, device=qk.device)
     lse = torch.empty((b, n_heads, n_rounds, t), dtype=torch.float32, device=qk.device)
     st = spec.struct()
-    _lib.call("rtts_lsh_attn_fwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(mask), ctypes.byref(st), _ptr(o), _ptr(lse),
+    _launch(_tag("lsh_attn_fwd", locals()), "rtts_lsh_attn_fwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(mask), ctypes.byref(st), _ptr(o), _ptr(lse),
               b, t, n_heads, dh, n_rounds, bucket, _stream())
     return o, lse
 
@@ -125,7 +185,7 @@ def lsh_merge_fwd(o_rounds: torch.Tensor, lse_rounds: torch.Tensor) -> Tuple[tor
     assert o_rounds.is_contiguous() and lse_rounds.is_contiguous()
     out = torch.empty((b, t, h * dh), dtype=torch.bfloat16, device=o_rounds.device)
     lse = torch.empty((b, h, t), dtype=torch.float32, device=o_rounds.device)
-    _lib.call("rtts_lsh_merge_fwd", _ptr(o_rounds), _ptr(lse_rounds), _ptr(out), h * dh, _ptr(lse), b, t, h, dh, r, _stream())
+    _launch(_tag("lsh_merge_fwd", locals()), "rtts_lsh_merge_fwd", _ptr(o_rounds), _ptr(lse_rounds), _ptr(out), h * dh, _ptr(lse), b, t, h, dh, r, _stream())
     return out, lse
 
 
@@ -135,7 +195,7 @@ def lsh_delta(dout: torch.Tensor, out: torch.Tensor, n_heads: int) -> torch.Tens
         raise RuntimeError("dout and out must share the token stride")
     b, t, c = dout.shape
     delta = torch.empty((b, n_heads, t), dtype=torch.float32, device=dout.device)
-    _lib.call("rtts_lsh_delta", _ptr(dout), _ptr(out), ld, _ptr(delta), b, t, n_heads, c // n_heads, _stream())
+    _launch(_tag("lsh_delta", locals()), "rtts_lsh_delta", _ptr(dout), _ptr(out), ld, _ptr(delta), b, t, n_heads, c // n_heads, _stream())
     return delta
 
 
@@ -143,8 +203,9 @@ def lsh_attn_bwd(qk, v, sticker, undo, mask, spec: LSHSpec, dout, lse, delta, n_
                  out_dqk: Optional[torch.Tensor] = None, out_dv: Optional[torch.Tensor] = None):
     """Backward of lsh_attn_fwd + lsh_merge_fwd (scores recomputed in-kernel) -> dqk, dv bf16 [B,T,H*64]."""
     ld = _token_major(qk, "qk")
-    if _token_major(v, "v") != ld or _token_major(dout, "dout") != ld:
-        raise RuntimeError("qk, v and dout must share the token stride")
+    if _token_major(v, "v") != ld:
+        raise RuntimeError("qk and v must share the token stride")
+    ld_do = _token_major(dout, "dout")
     b, t, c = qk.shape
     dh = c // n_heads
     _check(lse, torch.float32, "lse")
@@ -154,7 +215,7 @@ def lsh_attn_bwd(qk, v, sticker, undo, mask, spec: LSHSpec, dout, lse, delta, n_
     # fp32 per-round partials [4, B,H,R,T,dh]: dq_a, dq_b, dxk, dv
     part = torch.empty((4, b, n_heads, n_rounds, t, dh), dtype=torch.float32, device=qk.device)
     st = spec.struct()
-    _lib.call("rtts_lsh_attn_bwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(mask), ctypes.byref(st), _ptr(dout),
+    _launch(_tag("lsh_attn_bwd", locals()), "rtts_lsh_attn_bwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(mask), ctypes.byref(st), _ptr(dout), ld_do,
               _ptr(lse), _ptr(delta), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), _ptr(part[3]), b, t, n_heads, dh, n_rounds,
               bucket, _stream())
     dqk = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device) if out_dqk is None else out_dqk
@@ -162,7 +223,7 @@ def lsh_attn_bwd(qk, v, sticker, undo, mask, spec: LSHSpec, dout, lse, delta, n_
     ld_out = _token_major(dqk, "out_dqk")
     if _token_major(dv, "out_dv") != ld_out:
         raise RuntimeError("out_dqk and out_dv must share the token stride")
-    _lib.call("rtts_lsh_grad_reduce", _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), _ptr(part[3]), _ptr(undo), _ptr(dqk),
+    _launch(_tag("lsh_grad_reduce", locals()), "rtts_lsh_grad_reduce", _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), _ptr(part[3]), _ptr(undo), _ptr(dqk),
               _ptr(dv), ld_out, b, t, n_heads, dh, n_rounds, bucket, _stream())
     return dqk, dv
 
@@ -176,7 +237,7 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
-    _lib.call("rtts_layernorm_fwd", _ptr(x), _ptr(gamma.contiguous()), _ptr(beta.contiguous()), _ptr(y), _ptr(mean), _ptr(rstd),
+    _launch(_tag("layernorm_fwd", locals()), "rtts_layernorm_fwd", _ptr(x), _ptr(gamma.contiguous()), _ptr(beta.contiguous()), _ptr(y), _ptr(mean), _ptr(rstd),
               rows, dim, eps, _stream())
     return y, mean, rstd
 
@@ -187,7 +248,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta):
     dy, x = dy.contiguous(), x.contiguous()
     dim = x.shape[-1]
     dx = torch.empty_like(x)
-    _lib.call("rtts_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(gamma.contiguous()), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma),
+    _launch(_tag("layernorm_bwd", locals()), "rtts_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(gamma.contiguous()), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma),
               _ptr(dbeta), x.numel() // dim, dim, _stream())
     return dx
 
@@ -222,7 +283,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     if out is None:
         out = torch.empty((m, n), dtype=out_dtype, device=a.device)
     assert out.shape == (m, n) and out.stride(1) == 1
-    _lib.call("rtts_gemm_bf16", _ptr(a), a.stride(0), int(a_mn_major), _ptr(b), b.stride(0), int(b_mn_major), _ptr(out),
+    _launch(_tag("gemm_bf16", locals()), "rtts_gemm_bf16", _ptr(a), a.stride(0), int(a_mn_major), _ptr(b), b.stride(0), int(b_mn_major), _ptr(out),
               out.stride(0), _ptr(bias), _ptr(gate), 0 if gate is None else gate.stride(0), _ptr(colsum), m, n, k, flags, split_k,
               _stream())
     return out
@@ -234,5 +295,5 @@ def cast_bf16_colsum(x: torch.Tensor, colsum: Optional[torch.Tensor] = None) -> 
     x = x.contiguous()
     cols = x.shape[-1]
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    _lib.call("rtts_cast_bf16_colsum", _ptr(x), _ptr(y), _ptr(colsum), x.numel() // cols, cols, _stream())
+    _launch(_tag("cast_bf16_colsum", locals()), "rtts_cast_bf16_colsum", _ptr(x), _ptr(y), _ptr(colsum), x.numel() // cols, cols, _stream())
     return y
