@@ -82,22 +82,22 @@ int rtts_lsh_delta(const void* dout, const void* out, int64_t ld, float* delta, 
  * mask as in forward; dout bf16 [B,T,H*dh] (ld_dout) = gradient of the merged output; lse [B,H,T] from
  * rtts_lsh_merge_fwd; delta [B,H,T] from rtts_lsh_delta.  Outputs, fp32 [B,H,R,T,dh], scattered to the
  * UNSORTED slot like the forward:
- *   dq_a  query-role gradient from the keys of the CTA that owns the slot as a key,
- *   dq_b  query-role gradient from the previous CTA (slot seen as look-ahead chunk); written for every
- *         slot when bucket == 128 and only for slots in even sorted chunks when bucket == 64,
- *   dxk   key-role gradient with the key-normalisation Jacobian already applied,
- *   dv    value gradient. */
+ *   dqk_main  gradient w.r.t. the qk row of the slot from the CTA that owns it as a key: its key-role gradient
+ *             (key-normalisation Jacobian applied) plus the query-role gradient from that CTA's keys,
+ *   dq_b      query-role gradient from the previous CTA (slot seen as look-ahead chunk); written for every
+ *             slot when bucket == 128 and only for slots in even sorted chunks when bucket == 64,
+ *   dv_rounds value gradient. */
 int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
                       const rtts_lsh_spec* spec_host, const void* dout, int64_t ld_dout, const float* lse,
-                      const float* delta, float* dq_a, float* dq_b, float* dxk, float* dv_rounds, int B, int T, int H, int dh, int R,
-                      int bucket, void* stream);
+                      const float* delta, float* dqk_main, float* dq_b, float* dv_rounds, int B, int T, int H, int dh,
+                      int R, int bucket, void* stream);
 
-/* Sum the per-round gradients over the R rounds: dqk = sum_r (dq_a + dq_b + dxk), dv = sum_r dv_rounds,
+/* Sum the per-round gradients over the R rounds: dqk = sum_r (dqk_main + dq_b), dv = sum_r dv_rounds,
  * both bf16 [B,T,H*dh] (ld).  undo (from rtts_lsh_sort) tells which slots have a dq_b entry; may be NULL
  * when bucket == 128. */
-int rtts_lsh_grad_reduce(const float* dq_a, const float* dq_b, const float* dxk, const float* dv_rounds,
-                         const int32_t* undo, void* dqk, void* dv, int64_t ld, int B, int T, int H, int dh, int R,
-                         int bucket, void* stream);
+int rtts_lsh_grad_reduce(const float* dqk_main, const float* dq_b, const float* dv_rounds, const int32_t* undo,
+                         void* dqk, void* dv, int64_t ld, int B, int T, int H, int dh, int R, int bucket,
+                         void* stream);
 
 /* ---- LayerNorm (ref:reformer_tts/model/reformer.py:25-33, eps 1e-5, affine) -------------------- */
 

@@ -42,9 +42,8 @@ struct AttnBwdParams {
   const uint8_t* mask;
   const float* lse;     // [B,H,T]
   const float* delta;   // [B,H,T]
-  float* dq_a;
-  float* dq_b;
-  float* dxk;
+  float* dqk_main;   // per key slot: query-role gradient from this CTA's keys + key-role gradient (Jacobian applied)
+  float* dq_b;       // per look-ahead slot: query-role gradient from this CTA's keys
   float* dv;
   int T, H, R, tiles_per_row;
   float score_scale;
@@ -103,39 +102,53 @@ __global__ void __launch_bounds__(128) lsh_attn_bwd_kernel(const AttnBwdParams p
   }
 
   // ---- gather qk / dout rows of the query slots, v rows of the key slots ---------------------------------
+  // pos = sticker - round*T with the round taken from the slot index (see the forward kernel).
   {
     const int g = tid >> 3, c = tid & 7;
     constexpr int kPasses = kQRows / 16;
-    int pos[kPasses];
+    const int ahead_first = first_slot + kKeyRows >= RT ? first_slot + kKeyRows - RT : first_slot + kKeyRows;   // look-ahead chunk
+    const int base_main = (first_slot / p.T) * p.T, base_ahead = (ahead_first / p.T) * p.T;
+    int st[kPasses];
 #pragma unroll
     for (int i = 0; i < kPasses; ++i) {
       const int j = i * 16 + g;
-      int slot = first_slot + j;
-      slot = slot >= RT ? slot - RT : slot;
-      const int st = __ldg(stk + slot);
-      pos[i] = st % p.T;
-      if (c == 0) {
-        int enc = pos[i];
-        if (p.mask != nullptr && __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos[i]) == 0) enc |= kBPadFlag;
-        int limit = p.causal ? pos[i] : (kBPadFlag - 1);
-        if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && (enc & kBPadFlag)) limit = -1;
-        q_meta[j] = make_int2(enc, limit);
-        const int64_t sidx = static_cast<int64_t>(row_bh) * p.T + pos[i];
-        q_stat[j] = make_float2(__ldg(p.lse + sidx) * kBLog2e, __ldg(p.delta + sidx));
-        q_slot[j] = st;
-      }
+      st[i] = __ldg(stk + (j < kKeyRows ? first_slot + j : ahead_first + (j - kKeyRows)));
     }
+    int pos[kPasses];
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i) pos[i] = st[i] - ((i * 16 + g) < kKeyRows ? base_main : base_ahead);
     const int64_t head_off = static_cast<int64_t>(h) * kBDh + c * 8;
 #pragma unroll
     for (int i = 0; i < kPasses; ++i) {
       const int j = i * 16 + g;
-      const int64_t off = (static_cast<int64_t>(b) * p.T + pos[i]) * p.ld + head_off;
+      const int64_t tok = static_cast<int64_t>(b) * p.T + pos[i];
       const uint32_t so = sw128_offset(j, c);
-      cp_async16(sX + so, p.qk + off);
-      cp_async16(sDO + so, p.dout + (static_cast<int64_t>(b) * p.T + pos[i]) * p.ld_do + head_off);
-      if (j < kKeyRows) cp_async16(sV + so, p.v + off);
+      cp_async16(sX + so, p.qk + tok * p.ld + head_off);
+      cp_async16(sDO + so, p.dout + tok * p.ld_do + head_off);
+      if (j < kKeyRows) cp_async16(sV + so, p.v + tok * p.ld + head_off);
     }
     cp_async_commit();
+    if (c == 0) {
+      float lse_v[kPasses], delta_v[kPasses];
+      uint8_t valid[kPasses];
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) {
+        const int64_t sidx = static_cast<int64_t>(row_bh) * p.T + pos[i];
+        lse_v[i] = __ldg(p.lse + sidx);
+        delta_v[i] = __ldg(p.delta + sidx);
+        valid[i] = p.mask != nullptr ? __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos[i]) : uint8_t(1);
+      }
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) {
+        const int j = i * 16 + g;
+        const int enc = valid[i] ? pos[i] : (pos[i] | kBPadFlag);
+        int limit = p.causal ? pos[i] : (kBPadFlag - 1);
+        if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && !valid[i]) limit = -1;
+        q_meta[j] = make_int2(enc, limit);
+        q_stat[j] = make_float2(lse_v[i] * kBLog2e, delta_v[i]);
+        q_slot[j] = st[i];
+      }
+    }
     cp_async_wait<0>();
   }
   __syncthreads();
@@ -201,11 +214,17 @@ __global__ void __launch_bounds__(128) lsh_attn_bwd_kernel(const AttnBwdParams p
       tmem_ld32(t_row + cDP + half * 32, rp);
       tmem_ld_wait();
       float pe[32], de[32];
+      int2 qmv[32];
+      float2 qsv[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {     // 16-byte broadcast loads of two columns' metadata at a time
+        *reinterpret_cast<int4*>(qmv + 2 * i) = *reinterpret_cast<const int4*>(q_meta + qb * 64 + half * 32 + 2 * i);
+        *reinterpret_cast<float4*>(qsv + 2 * i) = *reinterpret_cast<const float4*>(q_stat + qb * 64 + half * 32 + 2 * i);
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int qi = qb * 64 + half * 32 + i;
-        const int2 qm = q_meta[qi];
-        const float2 qs = q_stat[qi];
+        const int2 qm = qmv[i];
+        const float2 qs = qsv[i];
         const bool masked = k_enc > qm.y;
         const bool self = k_enc == qm.x;
         float s = __uint_as_float(rs[i]) * cs;
@@ -296,26 +315,23 @@ __global__ void __launch_bounds__(128) lsh_attn_bwd_kernel(const AttnBwdParams p
       }
     }
     const float coef = inv * inv * dot;   // dh == 64: the L2 and the RMS/sqrt(dh) norms share |k|^-2 = inv^2
-    float4* dx_dst = reinterpret_cast<float4*>(p.dxk + (out_base + q_slot[j]) * kBDh);
-#pragma unroll
-    for (int q = 0; q < 16; ++q)
-      dx_dst[q] = make_float4(g[q * 4] - x[q * 4] * coef, g[q * 4 + 1] - x[q * 4 + 1] * coef, g[q * 4 + 2] - x[q * 4 + 2] * coef,
-                              g[q * 4 + 3] - x[q * 4 + 3] * coef);
-  }
-  {
-    // dQ: accumulator 0 = query rows 0..127 (the key slots themselves) -> dq_a;
-    //     accumulator 1 = query rows 128.. (the look-ahead chunk, BUCKET rows) -> dq_b
-    float4* dst = reinterpret_cast<float4*>(p.dq_a + (out_base + q_slot[j]) * kBDh);
+    // this slot's query-role gradient from the keys of this CTA (accumulator 0, row j) is added in registers
+    float4* dst = reinterpret_cast<float4*>(p.dqk_main + (out_base + q_slot[j]) * kBDh);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       uint32_t r[32];
       tmem_ld32(t_row + cDQ0 + half * 32, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        dst[half * 8 + q] = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
-                                        __uint_as_float(r[q * 4 + 3]));
+      for (int q = 0; q < 8; ++q) {
+        const int e = half * 32 + q * 4;
+        dst[half * 8 + q] = make_float4(__uint_as_float(r[q * 4]) + g[e] - x[e] * coef, __uint_as_float(r[q * 4 + 1]) + g[e + 1] - x[e + 1] * coef,
+                                        __uint_as_float(r[q * 4 + 2]) + g[e + 2] - x[e + 2] * coef, __uint_as_float(r[q * 4 + 3]) + g[e + 3] - x[e + 3] * coef);
+      }
     }
+  }
+  {
+    // accumulator 1 = query rows 128.. (the look-ahead chunk, BUCKET rows) -> dq_b.
     // every warp must execute the (warp-collective) TMEM loads; only rows < BUCKET are stored
     const bool live = j < BUCKET;
     float4* dst_b = reinterpret_cast<float4*>(p.dq_b + (out_base + q_slot[live ? kKeyRows + j : 0]) * kBDh);
@@ -342,8 +358,8 @@ __global__ void __launch_bounds__(128) lsh_attn_bwd_kernel(const AttnBwdParams p
 // dq_b is written for every slot when bucket == 128, and only for slots in even chunks when bucket == 64
 // (the chunk index comes from `undo`).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lsh_grad_reduce_kernel(const float* __restrict__ dq_a, const float* __restrict__ dq_b,
-                                                              const float* __restrict__ dxk, const float* __restrict__ dvr,
+__global__ void __launch_bounds__(256) lsh_grad_reduce_kernel(const float* __restrict__ dqk_main, const float* __restrict__ dq_b,
+                                                              const float* __restrict__ dvr,
                                                               const int32_t* __restrict__ undo, __nv_bfloat16* __restrict__ dqk,
                                                               __nv_bfloat16* __restrict__ dv, int64_t ld, int T, int H, int R,
                                                               int bucket, int64_t rows) {
@@ -355,10 +371,9 @@ __global__ void __launch_bounds__(256) lsh_grad_reduce_kernel(const float* __res
   float4 aq = make_float4(0, 0, 0, 0), av = make_float4(0, 0, 0, 0);
   for (int r = 0; r < R; ++r) {
     const int64_t idx = (bh * R + r) * T + t;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(dq_a + idx * kBDh) + c);
-    const float4 k = __ldg(reinterpret_cast<const float4*>(dxk + idx * kBDh) + c);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(dqk_main + idx * kBDh) + c);
     const float4 w = __ldg(reinterpret_cast<const float4*>(dvr + idx * kBDh) + c);
-    aq.x += a.x + k.x; aq.y += a.y + k.y; aq.z += a.z + k.z; aq.w += a.w + k.w;
+    aq.x += a.x; aq.y += a.y; aq.z += a.z; aq.w += a.w;
     av.x += w.x; av.y += w.y; av.z += w.z; av.w += w.w;
     bool has_b = true;
     if (bucket == 64) has_b = ((__ldg(undo + idx) >> 6) & 1) == 0;
@@ -395,10 +410,10 @@ int launch_attn_bwd(const AttnBwdParams& p, int ctas, cudaStream_t stream) {
 using namespace rtts;
 
 extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
-                                 const rtts_lsh_spec* spec, const void* dout, int64_t ld_dout, const float* lse, const float* delta, float* dq_a,
-                                 float* dq_b, float* dxk, float* dv_rounds, int B, int T, int H, int dh, int R, int bucket,
+                                 const rtts_lsh_spec* spec, const void* dout, int64_t ld_dout, const float* lse, const float* delta, float* dqk_main,
+                                 float* dq_b, float* dv_rounds, int B, int T, int H, int dh, int R, int bucket,
                                  void* stream) {
-  RTTS_REQUIRE(qk && v && sticker && spec && dout && lse && delta && dq_a && dq_b && dxk && dv_rounds, "rtts_lsh_attn_bwd: null pointer");
+  RTTS_REQUIRE(qk && v && sticker && spec && dout && lse && delta && dqk_main && dq_b && dv_rounds, "rtts_lsh_attn_bwd: null pointer");
   RTTS_REQUIRE(dh == kBDh, "rtts_lsh_attn_bwd: head size %d unsupported (64 only)", dh);
   RTTS_REQUIRE(bucket == 64 || bucket == 128, "rtts_lsh_attn_bwd: bucket size %d unsupported (64 or 128)", bucket);
   RTTS_REQUIRE(T % (2 * bucket) == 0, "rtts_lsh_attn_bwd: T=%d must be a multiple of 2*bucket", T);
@@ -409,7 +424,7 @@ extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, cons
   p.v = static_cast<const __nv_bfloat16*>(v);
   p.dout = static_cast<const __nv_bfloat16*>(dout);
   p.ld = ld; p.ld_do = ld_dout; p.sticker = sticker; p.mask = mask; p.lse = lse; p.delta = delta;
-  p.dq_a = dq_a; p.dq_b = dq_b; p.dxk = dxk; p.dv = dv_rounds;
+  p.dqk_main = dqk_main; p.dq_b = dq_b; p.dv = dv_rounds;
   p.T = T; p.H = H; p.R = R; p.tiles_per_row = R * T / kKeyRows;
   p.score_scale = spec->score_scale;
   p.mask_value_log2 = fmaxf(spec->mask_value * kBLog2e, -3.0e38f);
@@ -421,15 +436,14 @@ extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, cons
   return bucket == 64 ? launch_attn_bwd<64>(p, static_cast<int>(ctas), s) : launch_attn_bwd<128>(p, static_cast<int>(ctas), s);
 }
 
-extern "C" int rtts_lsh_grad_reduce(const float* dq_a, const float* dq_b, const float* dxk, const float* dv_rounds,
-                                    const int32_t* undo, void* dqk, void* dv, int64_t ld, int B, int T, int H, int dh, int R,
+extern "C" int rtts_lsh_grad_reduce(const float* dqk_main, const float* dq_b, const float* dv_rounds, const int32_t* undo, void* dqk, void* dv, int64_t ld, int B, int T, int H, int dh, int R,
                                     int bucket, void* stream) {
-  RTTS_REQUIRE(dq_a && dq_b && dxk && dv_rounds && dqk && dv, "rtts_lsh_grad_reduce: null pointer");
+  RTTS_REQUIRE(dqk_main && dq_b && dv_rounds && dqk && dv, "rtts_lsh_grad_reduce: null pointer");
   RTTS_REQUIRE(dh == kBDh && ld % 8 == 0, "rtts_lsh_grad_reduce: head size 64 and 16-byte rows required");
   RTTS_REQUIRE(bucket == 128 || (bucket == 64 && undo), "rtts_lsh_grad_reduce: bucket 64 needs undo");
   const int64_t rows = static_cast<int64_t>(B) * H * T;
   const int64_t blocks = (rows * 16 + 255) / 256;
   lsh_grad_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dq_a, dq_b, dxk, dv_rounds, undo, static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), ld, T, H, R, bucket, rows);
+      dqk_main, dq_b, dv_rounds, undo, static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), ld, T, H, R, bucket, rows);
   return check_launch("rtts_lsh_grad_reduce");
 }

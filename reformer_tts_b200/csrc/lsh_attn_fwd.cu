@@ -94,23 +94,25 @@ __global__ void __launch_bounds__(128) lsh_attn_fwd_kernel(const AttnFwdParams p
   }
 
   // ---- gather: 8 lanes per row, 16 rows per pass -------------------------------------------------
+  // sticker[slot] = round*T + pos and sorted slots keep the rounds contiguous, so pos = sticker - (slot / T) * T:
+  // the round comes from the slot index, not from the loaded value (no integer division on the load's critical path).
   {
     const int g = tid >> 3, c = tid & 7;
     constexpr int kPasses = kKeyRows / 16;
-    int pos[kPasses];
+    const int prev_first = first_slot < 0 ? first_slot + RT : first_slot;       // slot of key-tile row 0 (look-back chunk)
+    const int base_prev = (prev_first / p.T) * p.T, base_main = ((tile * kQRows) / p.T) * p.T;
+    int st[kPasses];
 #pragma unroll
     for (int i = 0; i < kPasses; ++i) {
-      int slot = first_slot + i * 16 + g;
-      slot = slot < 0 ? slot + RT : slot;
-      const int st = __ldg(stk + slot);
-      pos[i] = st % p.T;
-      if (c == 0) {
-        const int j = i * 16 + g;
-        int enc = pos[i];
-        if (p.mask != nullptr && __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos[i]) == 0) enc |= kPadFlag;
-        key_pos[j] = enc;
-        if (j >= kQOff) q_slot[j - kQOff] = st;
-      }
+      const int j = i * 16 + g;
+      st[i] = __ldg(stk + (j < BUCKET ? prev_first + j : first_slot + j));
+    }
+    int pos[kPasses];
+    uint8_t valid[kPasses];
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i) {
+      pos[i] = st[i] - ((i * 16 + g) < BUCKET ? base_prev : base_main);
+      valid[i] = (p.mask != nullptr && c == 0) ? __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos[i]) : uint8_t(1);
     }
     const int64_t head_off = static_cast<int64_t>(h) * kDh + c * 8;
 #pragma unroll
@@ -122,6 +124,14 @@ __global__ void __launch_bounds__(128) lsh_attn_fwd_kernel(const AttnFwdParams p
       cp_async16(sV + so, p.v + off);
     }
     cp_async_commit();
+    if (c == 0) {
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) {
+        const int j = i * 16 + g;
+        key_pos[j] = valid[i] ? pos[i] : (pos[i] | kPadFlag);
+        if (j >= kQOff) q_slot[j - kQOff] = st[i];
+      }
+    }
     cp_async_wait<0>();
   }
   __syncthreads();
@@ -180,12 +190,18 @@ __global__ void __launch_bounds__(128) lsh_attn_fwd_kernel(const AttnFwdParams p
     uint32_t r[32];
     tmem_ld32(t_row + win0 + c0, r);
     tmem_ld_wait();
+    int kp[32];
+    float ks[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {      // win0 + c0 is a multiple of 32: 16-byte aligned broadcast loads
+      *reinterpret_cast<int4*>(kp + 4 * i) = *reinterpret_cast<const int4*>(key_pos + win0 + c0 + 4 * i);
+      *reinterpret_cast<float4*>(ks + 4 * i) = *reinterpret_cast<const float4*>(key_scale + win0 + c0 + 4 * i);
+    }
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const int kp = key_pos[win0 + c0 + i];
-      float s = __uint_as_float(r[i]) * key_scale[win0 + c0 + i];
-      s = kp > q_limit ? mv : s;
-      s = kp == q_enc ? sv : s;
+      float s = __uint_as_float(r[i]) * ks[i];
+      s = kp[i] > q_limit ? mv : s;
+      s = kp[i] == q_enc ? sv : s;
       row_max = fmaxf(row_max, s);
     }
   }
@@ -197,12 +213,18 @@ __global__ void __launch_bounds__(128) lsh_attn_fwd_kernel(const AttnFwdParams p
     tmem_ld32(t_row + win0 + c0, r);
     tmem_ld_wait();
     float e[32];
+    int kp[32];
+    float ks[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      *reinterpret_cast<int4*>(kp + 4 * i) = *reinterpret_cast<const int4*>(key_pos + win0 + c0 + 4 * i);
+      *reinterpret_cast<float4*>(ks + 4 * i) = *reinterpret_cast<const float4*>(key_scale + win0 + c0 + 4 * i);
+    }
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const int kp = key_pos[win0 + c0 + i];
-      float s = __uint_as_float(r[i]) * key_scale[win0 + c0 + i];
-      s = kp > q_limit ? mv : s;
-      s = kp == q_enc ? sv : s;
+      float s = __uint_as_float(r[i]) * ks[i];
+      s = kp[i] > q_limit ? mv : s;
+      s = kp[i] == q_enc ? sv : s;
       e[i] = exp2f(s - row_max);
       row_sum += e[i];
     }

@@ -212,18 +212,18 @@ def lsh_attn_bwd(qk, v, sticker, undo, mask, spec: LSHSpec, dout, lse, delta, n_
     _check(delta, torch.float32, "delta")
     _check(undo, torch.int32, "undo")
     assert lse.is_contiguous() and delta.is_contiguous() and sticker.is_contiguous() and undo.is_contiguous()
-    # fp32 per-round partials [4, B,H,R,T,dh]: dq_a, dq_b, dxk, dv
-    part = torch.empty((4, b, n_heads, n_rounds, t, dh), dtype=torch.float32, device=qk.device)
+    # fp32 per-round partials [3, B,H,R,T,dh]: dqk_main, dq_b, dv
+    part = torch.empty((3, b, n_heads, n_rounds, t, dh), dtype=torch.float32, device=qk.device)
     st = spec.struct()
     _launch(_tag("lsh_attn_bwd", locals()), "rtts_lsh_attn_bwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(mask), ctypes.byref(st), _ptr(dout), ld_do,
-              _ptr(lse), _ptr(delta), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), _ptr(part[3]), b, t, n_heads, dh, n_rounds,
+              _ptr(lse), _ptr(delta), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), b, t, n_heads, dh, n_rounds,
               bucket, _stream())
     dqk = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device) if out_dqk is None else out_dqk
     dv = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device) if out_dv is None else out_dv
     ld_out = _token_major(dqk, "out_dqk")
     if _token_major(dv, "out_dv") != ld_out:
         raise RuntimeError("out_dqk and out_dv must share the token stride")
-    _launch(_tag("lsh_grad_reduce", locals()), "rtts_lsh_grad_reduce", _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), _ptr(part[3]), _ptr(undo), _ptr(dqk),
+    _launch(_tag("lsh_grad_reduce", locals()), "rtts_lsh_grad_reduce", _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), _ptr(undo), _ptr(dqk),
               _ptr(dv), ld_out, b, t, n_heads, dh, n_rounds, bucket, _stream())
     return dqk, dv
 
