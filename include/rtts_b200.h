@@ -48,10 +48,14 @@ int rtts_abi_version(void);
  * qk bf16 [B,T,H*dh] (ld elements per token), rot fp32 [rot_heads, dh, R, n_buckets/2] with rot_heads
  * = 1 (rp: shared) or H (hf: per head).  pad_mask uint8 [B,T] (1 = real token) or NULL; when
  * use_pad_bucket != 0 padded tokens get bucket n_buckets and the round stride is n_buckets+1 (hf:740-747).
- * buckets int32 [B,H,R*T] (value = round*stride + id).  Arithmetic: fp32 FMA on the bf16 inputs. */
+ * buckets int32 [B,H,R*T] (value = round*stride + id).  Arithmetic: fp32 FMA on the bf16 inputs.
+ * sumsq (nullable) fp32 [B,H,T] receives |qk row|^2, the input of the key normalisation (rp R5 / hf:1042-1056). */
 int rtts_lsh_hash(const void* qk, int64_t ld, const float* rot, int rot_heads, const uint8_t* pad_mask,
-                  int use_pad_bucket, int32_t* buckets, int B, int T, int H, int dh, int R, int n_buckets,
-                  void* stream);
+                  int use_pad_bucket, int32_t* buckets, float* sumsq, int B, int T, int H, int dh, int R,
+                  int n_buckets, void* stream);
+
+/* sumsq fp32 [B,H,T] = |qk[b,t,h,:]|^2 on its own (same values rtts_lsh_hash emits). */
+int rtts_lsh_sumsq(const void* qk, int64_t ld, float* sumsq, int B, int T, int H, int dh, void* stream);
 
 /* Stable sort by (bucket, position) per (batch*head) row, and its inverse (rp R3; hf:150-156,762-779).
  * sticker[i] = round*T + pos sitting at sorted slot i; undo[sticker[i]] = i.  ids_per_round = round
@@ -63,9 +67,9 @@ int rtts_lsh_sort(const int32_t* buckets, int32_t* sticker, int32_t* undo, int r
 
 /* Gather by sticker, key normalisation, look-one-back, QK^T, masks, softmax, PV and un-sort in one
  * kernel (rp R4-R10; hf:563-599,801-906,1067-1096).  bucket in {64,128}, dh = 64, T % 128 == 0.
- * mask uint8 [B,T] (1 = real token) or NULL.  Outputs, already UNSORTED:
+ * sumsq fp32 [B,H,T] = |qk row|^2.  mask uint8 [B,T] (1 = real token) or NULL.  Outputs, already UNSORTED:
  *   o_rounds bf16 [B,H,R,T,dh], lse_rounds fp32 [B,H,R,T]. */
-int rtts_lsh_attn_fwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
+int rtts_lsh_attn_fwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const float* sumsq, const uint8_t* mask,
                       const rtts_lsh_spec* spec_host, void* o_rounds, float* lse_rounds, int B, int T, int H,
                       int dh, int R, int bucket, void* stream);
 
@@ -78,7 +82,7 @@ int rtts_lsh_delta(const void* dout, const void* out, int64_t ld, float* delta, 
                    void* stream);
 
 /* Backward of rtts_lsh_attn_fwd + rtts_lsh_merge_fwd with in-kernel recompute of the scores
- * (autograd of rp R4-R11; the per-round o / lse of the forward are not needed).  Inputs: qk, v, sticker,
+ * (autograd of rp R4-R11; the per-round o / lse of the forward are not needed).  Inputs: qk, v, sticker, sumsq,
  * mask as in forward; dout bf16 [B,T,H*dh] (ld_dout) = gradient of the merged output; lse [B,H,T] from
  * rtts_lsh_merge_fwd; delta [B,H,T] from rtts_lsh_delta.  Outputs, fp32 [B,H,R,T,dh], scattered to the
  * UNSORTED slot like the forward:
@@ -87,7 +91,7 @@ int rtts_lsh_delta(const void* dout, const void* out, int64_t ld, float* delta, 
  *   dq_b      query-role gradient from the previous CTA (slot seen as look-ahead chunk); written for every
  *             slot when bucket == 128 and only for slots in even sorted chunks when bucket == 64,
  *   dv_rounds value gradient. */
-int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
+int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const float* sumsq, const uint8_t* mask,
                       const rtts_lsh_spec* spec_host, const void* dout, int64_t ld_dout, const float* lse,
                       const float* delta, float* dqk_main, float* dq_b, float* dv_rounds, int B, int T, int H, int dh,
                       int R, int bucket, void* stream);

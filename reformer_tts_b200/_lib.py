@@ -23,12 +23,13 @@ _SPEC = POINTER(LSHSpecStruct)
 
 # name -> argtypes, in header order
 SIGNATURES = {
-    "rtts_lsh_hash": [_P, _L, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "rtts_lsh_hash": [_P, _L, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "rtts_lsh_sumsq": [_P, _L, _P, _I, _I, _I, _I, _P],
     "rtts_lsh_sort": [_P, _P, _P, _I, _I, _I, _I, _P],
-    "rtts_lsh_attn_fwd": [_P, _P, _L, _P, _P, _SPEC, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "rtts_lsh_attn_fwd": [_P, _P, _L, _P, _P, _P, _SPEC, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "rtts_lsh_merge_fwd": [_P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P],
     "rtts_lsh_delta": [_P, _P, _L, _P, _I, _I, _I, _I, _P],
-    "rtts_lsh_attn_bwd": [_P, _P, _L, _P, _P, _SPEC, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "rtts_lsh_attn_bwd": [_P, _P, _L, _P, _P, _P, _SPEC, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "rtts_lsh_grad_reduce": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
     "rtts_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
     "rtts_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],

@@ -54,8 +54,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded spin: a protocol bug traps (launch failure reported to the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 24); ++spin)
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     if (mbar_try_wait(bar, parity)) return;
+    if (spin > 2) __nanosleep(40);      // back off: a spinning waiter must not take issue slots from the warp it waits for
+  }
   __trap();
 }
 

@@ -39,6 +39,7 @@ struct AttnBwdParams {
   int64_t ld;      // token stride of qk / v
   int64_t ld_do;   // token stride of dout
   const int32_t* sticker;
+  const float* sumsq;   // [B,H,T] |qk row|^2
   const uint8_t* mask;
   const float* lse;     // [B,H,T]
   const float* delta;   // [B,H,T]
@@ -409,11 +410,11 @@ int launch_attn_bwd(const AttnBwdParams& p, int ctas, cudaStream_t stream) {
 
 using namespace rtts;
 
-extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
+extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const float* sumsq, const uint8_t* mask,
                                  const rtts_lsh_spec* spec, const void* dout, int64_t ld_dout, const float* lse, const float* delta, float* dqk_main,
                                  float* dq_b, float* dv_rounds, int B, int T, int H, int dh, int R, int bucket,
                                  void* stream) {
-  RTTS_REQUIRE(qk && v && sticker && spec && dout && lse && delta && dqk_main && dq_b && dv_rounds, "rtts_lsh_attn_bwd: null pointer");
+  RTTS_REQUIRE(qk && v && sticker && sumsq && spec && dout && lse && delta && dqk_main && dq_b && dv_rounds, "rtts_lsh_attn_bwd: null pointer");
   RTTS_REQUIRE(dh == kBDh, "rtts_lsh_attn_bwd: head size %d unsupported (64 only)", dh);
   RTTS_REQUIRE(bucket == 64 || bucket == 128, "rtts_lsh_attn_bwd: bucket size %d unsupported (64 or 128)", bucket);
   RTTS_REQUIRE(T % (2 * bucket) == 0, "rtts_lsh_attn_bwd: T=%d must be a multiple of 2*bucket", T);
@@ -423,7 +424,7 @@ extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, cons
   p.qk = static_cast<const __nv_bfloat16*>(qk);
   p.v = static_cast<const __nv_bfloat16*>(v);
   p.dout = static_cast<const __nv_bfloat16*>(dout);
-  p.ld = ld; p.ld_do = ld_dout; p.sticker = sticker; p.mask = mask; p.lse = lse; p.delta = delta;
+  p.ld = ld; p.ld_do = ld_dout; p.sticker = sticker; p.sumsq = sumsq; p.mask = mask; p.lse = lse; p.delta = delta;
   p.dqk_main = dqk_main; p.dq_b = dq_b; p.dv = dv_rounds;
   p.T = T; p.H = H; p.R = R; p.tiles_per_row = R * T / kKeyRows;
   p.score_scale = spec->score_scale;

@@ -34,6 +34,7 @@ struct AttnFwdParams {
   const __nv_bfloat16* v;
   int64_t ld;
   const int32_t* sticker;
+  const float* sumsq;   // [B,H,T] |qk row|^2
   const uint8_t* mask;
   __nv_bfloat16* o_rounds;
   float* lse_rounds;
@@ -44,254 +45,369 @@ struct AttnFwdParams {
   int key_norm, mask_mode, causal;
 };
 
+// Persistent, warp-specialised pipeline: one CTA per SM walks tiles t = blockIdx.x, += gridDim.x.
+//   warp 12     : TMEM allocation; lane 0 issues every tcgen05.mma  (S(n) as soon as K lands, then PV(n-1) when P(n-1) is ready)
+//   warps 8-11  : loaders - sticker -> position -> qk and V rows by 16-byte cp.async into swizzled tiles, key scale from sumsq;
+//                 they run up to kStages tiles ahead of the consumers
+//   warps 0-3   : softmax group 0 (tiles n even);  warps 4-7: softmax group 1 (tiles n odd); thread = query row = TMEM lane
+// Shared memory: kStages stage sets {K|P tile, V tile, key scale / position / slot arrays}; P aliases the K tile of its stage
+// (K is dead once S(n) has completed, which s_full certifies).  TMEM: one 256-column region per softmax group: S in
+// [0, kKeyRows), O in [192, 256) for bucket 64 (disjoint) or aliased onto S[0, 64) for bucket 128.
+// mbarriers: kv_full[stage] (128 loader arrivals) -> s_full[group] (tcgen05.commit) -> p_full[group] (128 softmax arrivals)
+//            -> o_full[group] + kv_free[stage] (tcgen05.commit after PV) -> o_free[group] (128 arrivals after the epilogue).
+//
+// Softmax is single-pass: keys are unit vectors after normalisation, so |s_ij| <= |q_i| * score_scale (Cauchy-Schwarz) and
+// m_i = that bound is a valid stabiliser known before any score is read; masked / self entries give exp2() == 0 exactly.  If a
+// row sums to zero (its only visible key is itself - masked to self_value - or, for absurd norms, everything underflowed) the
+// warp re-does that row with the exact two-pass arithmetic of the reference (row max first), so results never depend on the bound.
+constexpr int kFwdThreads = 416;
+constexpr int kLoaderThreads = 128;
+// Warp roles by index.  The SM's issue arbiter favours higher warp ids, so the producers that everything else waits on get
+// the top ids: warps 0-7 softmax groups, warps 8-11 loaders, warp 12 MMA issuer.
+constexpr int kFirstLoaderWarp = 8;
+constexpr int kMmaWarp = 12;
+
 template <int BUCKET>
 struct AttnFwdSmem {
   static constexpr int kKeyRows = kQRows + BUCKET;
+  static constexpr int kStages = BUCKET == 64 ? 3 : 2;
   static constexpr int kKeyBytes = kKeyRows * 128;
-  static constexpr int kPBytes = kQRows * kKeyRows * 2;   // P tile, bf16
-  // layout (all tile bases 1024-B aligned):  [ K tile | V tile | P tile | small arrays ]
-  static constexpr int kOffK = 0;
-  static constexpr int kOffV = kKeyBytes;
-  static constexpr int kOffP = 2 * kKeyBytes;
-  static constexpr int kOffScale = kOffP + kPBytes;                 // float[kKeyRows]
-  static constexpr int kOffPos = kOffScale + kKeyRows * 4;          // int[kKeyRows]
-  static constexpr int kOffSlot = kOffPos + kKeyRows * 4;           // int[kQRows]  unsorted slot of each query
-  static constexpr int kOffBar = kOffSlot + kQRows * 4;             // uint64 mbarrier
-  static constexpr int kOffTmem = kOffBar + 8;                      // uint32
+  static constexpr int kPBytes = kQRows * kKeyRows * 2;   // P tile, bf16 (>= kKeyBytes): shares its storage with the K tile
+  // per stage (all tile bases 1024-B aligned):  [ K|P tile | V tile | scale | pos | slot ]
+  static constexpr int kOffKP = 0;
+  static constexpr int kOffV = kPBytes;
+  static constexpr int kOffScale = kOffV + kKeyBytes;                // float[kKeyRows]
+  static constexpr int kOffPos = kOffScale + kKeyRows * 4;           // int[kKeyRows]
+  static constexpr int kOffSlot = kOffPos + kKeyRows * 4;            // int[kQRows]  unsorted slot of each query
+  static constexpr int kStageBytes = ((kOffSlot + kQRows * 4 + 1023) / 1024) * 1024;
+  static constexpr int kOffBar = kStages * kStageBytes;              // 2*kStages + 8 mbarriers
+  static constexpr int kOffTmem = kOffBar + (2 * kStages + 8) * 8;
   static constexpr int kTotal = kOffTmem + 8;
-  static constexpr int kDynamic = kTotal + 1024;                    // slack for manual 1024-B alignment
+  static constexpr int kDynamic = kTotal + 1024;                     // slack for manual 1024-B alignment
 };
 
 template <int BUCKET>
-__global__ void __launch_bounds__(128) lsh_attn_fwd_kernel(const AttnFwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const AttnFwdParams p, const int num_tiles) {
   using L = AttnFwdSmem<BUCKET>;
-  constexpr int kKeyRows = L::kKeyRows;
+  constexpr int kKeyRows = L::kKeyRows, kStages = L::kStages;
   constexpr int kQOff = BUCKET;           // first query row inside the key tile
   constexpr int kWin = 2 * BUCKET;        // attention window per query
-  constexpr uint32_t kTmemCols = 256;     // S uses kKeyRows (<=256) columns; O aliases S[0..64)
+  constexpr bool kAliasO = BUCKET == 128; // bucket 128: S fills all 256 columns of the region, O reuses S[0, 64)
+  constexpr uint32_t kColO = kAliasO ? 0 : 192;
+  constexpr uint32_t kTmemCols = 512;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t sK = smem_u32(smem + L::kOffK), sV = smem_u32(smem + L::kOffV), sP = smem_u32(smem + L::kOffP);
-  float* key_scale = reinterpret_cast<float*>(smem + L::kOffScale);
-  int* key_pos = reinterpret_cast<int*>(smem + L::kOffPos);
-  int* q_slot = reinterpret_cast<int*>(smem + L::kOffSlot);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* kv_full = bars;                    // [kStages]
+  uint64_t* kv_free = bars + kStages;          // [kStages]
+  uint64_t* s_full = bars + 2 * kStages;       // [2]
+  uint64_t* p_full = s_full + 2;               // [2]
+  uint64_t* o_full = s_full + 4;               // [2]
+  uint64_t* o_free = s_full + 6;               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int row_bh = blockIdx.x / p.tiles_per_row;           // (batch*H + head)
-  const int tile = blockIdx.x - row_bh * p.tiles_per_row;
-  const int b = row_bh / p.H, h = row_bh - b * p.H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int RT = p.R * p.T;
-  const int32_t* stk = p.sticker + static_cast<int64_t>(row_bh) * RT;
-  const int first_slot = tile * kQRows - BUCKET;               // sorted slot of key-tile row 0 (may be < 0: wraps)
 
-  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   if (tid == 0) {
-    mbar_init(bar, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(kv_full + s, kLoaderThreads);
+      mbar_init(kv_free + s, 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(s_full + g, 1);
+      mbar_init(p_full + g, kQRows);
+      mbar_init(o_full + g, 1);
+      mbar_init(o_free + g, kQRows);
+    }
     fence_mbar_init();
   }
-
-  // ---- gather: 8 lanes per row, 16 rows per pass -------------------------------------------------
-  // sticker[slot] = round*T + pos and sorted slots keep the rounds contiguous, so pos = sticker - (slot / T) * T:
-  // the round comes from the slot index, not from the loaded value (no integer division on the load's critical path).
-  {
-    const int g = tid >> 3, c = tid & 7;
-    constexpr int kPasses = kKeyRows / 16;
-    const int prev_first = first_slot < 0 ? first_slot + RT : first_slot;       // slot of key-tile row 0 (look-back chunk)
-    const int base_prev = (prev_first / p.T) * p.T, base_main = ((tile * kQRows) / p.T) * p.T;
-    int st[kPasses];
-#pragma unroll
-    for (int i = 0; i < kPasses; ++i) {
-      const int j = i * 16 + g;
-      st[i] = __ldg(stk + (j < BUCKET ? prev_first + j : first_slot + j));
-    }
-    int pos[kPasses];
-    uint8_t valid[kPasses];
-#pragma unroll
-    for (int i = 0; i < kPasses; ++i) {
-      pos[i] = st[i] - ((i * 16 + g) < BUCKET ? base_prev : base_main);
-      valid[i] = (p.mask != nullptr && c == 0) ? __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos[i]) : uint8_t(1);
-    }
-    const int64_t head_off = static_cast<int64_t>(h) * kDh + c * 8;
-#pragma unroll
-    for (int i = 0; i < kPasses; ++i) {
-      const int j = i * 16 + g;
-      const int64_t off = (static_cast<int64_t>(b) * p.T + pos[i]) * p.ld + head_off;
-      const uint32_t so = sw128_offset(j, c);
-      cp_async16(sK + so, p.qk + off);
-      cp_async16(sV + so, p.v + off);
-    }
-    cp_async_commit();
-    if (c == 0) {
-#pragma unroll
-      for (int i = 0; i < kPasses; ++i) {
-        const int j = i * 16 + g;
-        key_pos[j] = valid[i] ? pos[i] : (pos[i] | kPadFlag);
-        if (j >= kQOff) q_slot[j - kQOff] = st[i];
-      }
-    }
-    cp_async_wait<0>();
-  }
-  __syncthreads();
-
-  // ---- per-key scale: 1/|k| (or rms variant) * score_scale * log2(e) --------------------------------
-  for (int j = tid; j < kKeyRows; j += 128) {
-    float ss = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 u = *reinterpret_cast<const uint4*>(smem + L::kOffK + sw128_offset(j, c));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
-        ss = fmaf(lo, lo, ss);
-        ss = fmaf(hi, hi, ss);
-      }
-    }
-    float inv;
-    if (p.key_norm == RTTS_KEYNORM_L2) inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-    else inv = rsqrtf(ss * (1.f / kDh) + 1e-6f) * 0.125f;   // 1/sqrt(64)
-    key_scale[j] = inv * p.score_scale_log2;
-  }
-  fence_proxy_async_smem();   // cp.async / st.shared data -> visible to the tensor-core (async) proxy
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
-  // ---- S = Q K^T -------------------------------------------------------------------------------------
-  if (tid == 0) {
-    constexpr uint32_t idesc = umma_idesc_bf16(128, kKeyRows, false, false);
+  if (warp == kMmaWarp) {
+    // ================================================= MMA issuer =================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKeyRows, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kDh, false, true);
+      auto issue_pv = [&](int m) {      // O(m) = P(m) V(m)
+        const int g = m & 1, st = m % kStages;
+        const uint32_t sP = smem_u32(smem + st * L::kStageBytes + L::kOffKP), sV = smem_u32(smem + st * L::kStageBytes + L::kOffV);
+        mbar_wait(p_full + g, (m >> 1) & 1);
+        if (!kAliasO) mbar_wait(o_free + g, ((m >> 1) & 1) ^ 1);      // epilogue of tile m-2 has drained O of this group
+        tc_fence_after_sync();
 #pragma unroll
-    for (int k = 0; k < kDh / 16; ++k) {
-      const uint64_t da = umma_desc_sw128(sK + kQOff * 128 + k * 32, 16, 1024);
-      const uint64_t db = umma_desc_sw128(sK + k * 32, 16, 1024);
-      umma_ss(tmem, da, db, idesc, k > 0);
-    }
-    umma_commit(bar);
-  }
-  mbar_wait(bar, 0);
-  tc_fence_after_sync();
-
-  // ---- softmax over this thread's query row ----------------------------------------------------------
-  const int m = tid;
-  const int q_enc = key_pos[kQOff + m];
-  int q_limit = p.causal ? (q_enc & ~kPadFlag) : (kPadFlag - 1);
-  if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && (q_enc & kPadFlag)) q_limit = -1;   // padded query: all masked
-  const int win0 = (m / BUCKET) * BUCKET;                      // first key-tile row of this query's window
-  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const float mv = p.mask_value_log2, sv = p.self_value_log2;
-
-  float row_max = -FLT_MAX;
-#pragma unroll 1
-  for (int c0 = 0; c0 < kWin; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(t_row + win0 + c0, r);
-    tmem_ld_wait();
-    int kp[32];
-    float ks[32];
+        for (int j = 0; j < kKeyRows / 16; ++j)
+          umma_ss(tmem + g * 256 + kColO, umma_desc_sw128(sP + (j >> 2) * (kQRows * 128) + (j & 3) * 32, 16, 1024),
+                  umma_desc_sw128(sV + j * 2048, 0, 1024), idesc_o, j > 0);
+        umma_commit(o_full + g);
+        umma_commit(kv_free + st);      // the stage's K|P and V tiles are no longer read
+      };
+      int n = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
+        const int g = n & 1, st = n % kStages;
+        const uint32_t sKP = smem_u32(smem + st * L::kStageBytes + L::kOffKP);
+        mbar_wait(kv_full + st, (n / kStages) & 1);
+        if (kAliasO) mbar_wait(o_free + g, ((n >> 1) & 1) ^ 1);       // S(n) overwrites O(n-2): its epilogue must be done
+        tc_fence_after_sync();
+        // S region of group g is free: PV(n-2) was issued (program order) after p_full(n-2), i.e. after the last read of S(n-2)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {      // win0 + c0 is a multiple of 32: 16-byte aligned broadcast loads
-      *reinterpret_cast<int4*>(kp + 4 * i) = *reinterpret_cast<const int4*>(key_pos + win0 + c0 + 4 * i);
-      *reinterpret_cast<float4*>(ks + 4 * i) = *reinterpret_cast<const float4*>(key_scale + win0 + c0 + 4 * i);
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float s = __uint_as_float(r[i]) * ks[i];
-      s = kp[i] > q_limit ? mv : s;
-      s = kp[i] == q_enc ? sv : s;
-      row_max = fmaxf(row_max, s);
-    }
-  }
-  float row_sum = 0.f;
-  uint8_t* p_row_base = smem + L::kOffP;
-#pragma unroll 1
-  for (int c0 = 0; c0 < kWin; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(t_row + win0 + c0, r);
-    tmem_ld_wait();
-    float e[32];
-    int kp[32];
-    float ks[32];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      *reinterpret_cast<int4*>(kp + 4 * i) = *reinterpret_cast<const int4*>(key_pos + win0 + c0 + 4 * i);
-      *reinterpret_cast<float4*>(ks + 4 * i) = *reinterpret_cast<const float4*>(key_scale + win0 + c0 + 4 * i);
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float s = __uint_as_float(r[i]) * ks[i];
-      s = kp[i] > q_limit ? mv : s;
-      s = kp[i] == q_enc ? sv : s;
-      e[i] = exp2f(s - row_max);
-      row_sum += e[i];
-    }
-    // keys win0+c0 .. +31 -> P tile k-block (col/64), 16-byte chunk (col%64)/8
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      const int col = win0 + c0 + q4 * 8;
-      uint4 u;
-      u.x = pack_bf16(e[q4 * 8 + 0], e[q4 * 8 + 1]);
-      u.y = pack_bf16(e[q4 * 8 + 2], e[q4 * 8 + 3]);
-      u.z = pack_bf16(e[q4 * 8 + 4], e[q4 * 8 + 5]);
-      u.w = pack_bf16(e[q4 * 8 + 6], e[q4 * 8 + 7]);
-      *reinterpret_cast<uint4*>(p_row_base + (col >> 6) * (kQRows * 128) + sw128_offset(m, (col & 63) >> 3)) = u;
-    }
-  }
-  if (BUCKET == 64) {
-    // the 64 key rows outside this query's window contribute nothing: zero that k-block of P
-    const int dead_block = (m < 64) ? 2 : 0;
-    const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      *reinterpret_cast<uint4*>(p_row_base + dead_block * (kQRows * 128) + sw128_offset(m, c)) = z;
-  }
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
-  __syncthreads();          // every row of S has been consumed; P is complete
-  tc_fence_after_sync();
-
-  // ---- O = P V  (O aliases the first 64 columns of S) ---------------------------------------------------
-  if (tid == 0) {
-    constexpr uint32_t idesc = umma_idesc_bf16(128, kDh, false, true);
-#pragma unroll
-    for (int j = 0; j < kKeyRows / 16; ++j) {
-      const uint64_t da = umma_desc_sw128(sP + (j >> 2) * (kQRows * 128) + (j & 3) * 32, 16, 1024);
-      const uint64_t db = umma_desc_sw128(sV + j * 2048, 0, 1024);
-      umma_ss(tmem, da, db, idesc, j > 0);
-    }
-    umma_commit(bar);
-  }
-  mbar_wait(bar, 1);
-  tc_fence_after_sync();
-
-  // ---- epilogue -------------------------------------------------------------------------------------------
-  {
-    const float inv_sum = 1.f / row_sum;
-    const int64_t slot = static_cast<int64_t>(row_bh) * RT + q_slot[m];
-    uint4* dst = reinterpret_cast<uint4*>(p.o_rounds + slot * kDh);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t r[32];
-      tmem_ld32(t_row + half * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(r[q4 * 8 + 0]) * inv_sum, __uint_as_float(r[q4 * 8 + 1]) * inv_sum);
-        u.y = pack_bf16(__uint_as_float(r[q4 * 8 + 2]) * inv_sum, __uint_as_float(r[q4 * 8 + 3]) * inv_sum);
-        u.z = pack_bf16(__uint_as_float(r[q4 * 8 + 4]) * inv_sum, __uint_as_float(r[q4 * 8 + 5]) * inv_sum);
-        u.w = pack_bf16(__uint_as_float(r[q4 * 8 + 6]) * inv_sum, __uint_as_float(r[q4 * 8 + 7]) * inv_sum);
-        dst[half * 4 + q4] = u;
+        for (int k = 0; k < kDh / 16; ++k)
+          umma_ss(tmem + g * 256, umma_desc_sw128(sKP + kQOff * 128 + k * 32, 16, 1024), umma_desc_sw128(sKP + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(s_full + g);
+        if (n > 0) issue_pv(n - 1);
       }
+      if (n > 0) issue_pv(n - 1);
     }
-    p.lse_rounds[slot] = (row_max + log2f(row_sum)) * kLn2;
+  } else if (warp >= kFirstLoaderWarp && warp < kMmaWarp) {
+    // ================================================= loaders ====================================================
+    // sticker[slot] = round*T + pos and sorted slots keep the rounds contiguous, so pos = sticker - (slot / T) * T with the
+    // round taken from the slot index (no integer division on the load's critical path).
+    const int lt = tid - kFirstLoaderWarp * 32;  // 0..127
+    const int grp = lt >> 3, c = lt & 7;         // 16 row groups of 8 lanes; lane c owns 16-byte chunk c of a row
+    constexpr int kPasses = kKeyRows / 16;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
+      const int st_i = n % kStages;
+      uint8_t* stage = smem + st_i * L::kStageBytes;
+      const uint32_t sKP = smem_u32(stage + L::kOffKP), sV = smem_u32(stage + L::kOffV);
+      float* key_scale = reinterpret_cast<float*>(stage + L::kOffScale);
+      int* key_pos = reinterpret_cast<int*>(stage + L::kOffPos);
+      int* q_slot = reinterpret_cast<int*>(stage + L::kOffSlot);
+      const int row_bh = tile / p.tiles_per_row, t_in = tile - row_bh * p.tiles_per_row;
+      const int b = row_bh / p.H, h = row_bh - b * p.H;
+      const int32_t* stk = p.sticker + static_cast<int64_t>(row_bh) * RT;
+      const int first_slot = t_in * kQRows - BUCKET;
+      const int prev_first = first_slot < 0 ? first_slot + RT : first_slot;
+      const int base_prev = (prev_first / p.T) * p.T, base_main = ((t_in * kQRows) / p.T) * p.T;
+      int st[kPasses];
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) {
+        const int j = i * 16 + grp;
+        st[i] = __ldg(stk + (j < BUCKET ? prev_first + j : first_slot + j));
+      }
+      float ssq[kPasses];
+      uint8_t valid[kPasses];
+      if (c == 0) {
+        const float* sq = p.sumsq + static_cast<int64_t>(row_bh) * p.T;
+#pragma unroll
+        for (int i = 0; i < kPasses; ++i) {
+          const int pos = st[i] - ((i * 16 + grp) < BUCKET ? base_prev : base_main);
+          ssq[i] = __ldg(sq + pos);
+          valid[i] = p.mask != nullptr ? __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos) : uint8_t(1);
+        }
+      }
+      mbar_wait(kv_free + st_i, ((n / kStages) & 1) ^ 1);       // PV of the tile that used this stage has completed
+      const __nv_bfloat16* qk_b = p.qk + static_cast<int64_t>(b) * p.T * p.ld + h * kDh + c * 8;
+      const __nv_bfloat16* v_b = p.v + static_cast<int64_t>(b) * p.T * p.ld + h * kDh + c * 8;
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) {
+        const int j = i * 16 + grp;
+        const int64_t off = static_cast<int64_t>(st[i] - (j < BUCKET ? base_prev : base_main)) * p.ld;
+        const uint32_t so = sw128_offset(j, c);
+        cp_async16(sKP + so, qk_b + off);
+        cp_async16(sV + so, v_b + off);
+      }
+      cp_async_commit();
+      if (c == 0) {
+#pragma unroll
+        for (int i = 0; i < kPasses; ++i) {
+          const int j = i * 16 + grp;
+          const int pos = st[i] - (j < BUCKET ? base_prev : base_main);
+          float inv;
+          if (p.key_norm == RTTS_KEYNORM_L2) inv = 1.f / fmaxf(sqrtf(ssq[i]), 1e-12f);
+          else inv = rsqrtf(ssq[i] * (1.f / kDh) + 1e-6f) * 0.125f;   // 1/sqrt(64)
+          key_scale[j] = inv * p.score_scale_log2;
+          key_pos[j] = valid[i] ? pos : (pos | kPadFlag);
+          if (j >= kQOff) q_slot[j - kQOff] = st[i];
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();     // cp.async / st.shared data -> visible to the tensor-core (async) proxy
+      mbar_arrive(kv_full + st_i);
+    }
+  } else {
+    // ================================================= softmax groups =============================================
+    const int wg = warp >> 2;                       // 0 | 1
+    const int m = tid - wg * 128;                   // query row = TMEM lane
+    const uint32_t t_row = tmem + wg * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const int win0 = (m / BUCKET) * BUCKET;          // first key-tile row of this query's window
+    const float mv = p.mask_value_log2, sv = p.self_value_log2;
+    int n = wg;
+    for (int tile = blockIdx.x + wg * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, n += 2) {
+      const uint32_t ph = (n >> 1) & 1;
+      const int st_i = n % kStages;
+      uint8_t* stage = smem + st_i * L::kStageBytes;
+      const float* key_scale = reinterpret_cast<const float*>(stage + L::kOffScale);
+      const int* key_pos = reinterpret_cast<const int*>(stage + L::kOffPos);
+      uint8_t* p_row_base = stage + L::kOffKP;
+      const int row_bh = tile / p.tiles_per_row;
+      mbar_wait(kv_full + st_i, (n / kStages) & 1);  // metadata of this stage is visible
+      const int q_enc = key_pos[kQOff + m];
+      int q_limit = p.causal ? (q_enc & ~kPadFlag) : (kPadFlag - 1);
+      if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && (q_enc & kPadFlag)) q_limit = -1;   // padded query: all masked
+      const int my_slot = reinterpret_cast<const int*>(stage + L::kOffSlot)[m];
+      // stabiliser: |q_i| * score_scale * log2(e) = score_scale_log2^2 / key_scale[own row] for both key-norm variants ...
+      // (key_scale = score_scale_log2 / |x| up to the norm's epsilon), times (1 + 2^-10) so rounding cannot push a score above it
+      const float row_bound = p.score_scale_log2 * p.score_scale_log2 / key_scale[kQOff + m] * 1.001f;
+      mbar_wait(s_full + wg, ph);
+      tc_fence_after_sync();
+
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c0 = 0; c0 < kWin; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + win0 + c0, r);
+        float e[32];
+        int kp[32];
+        float ks[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {      // win0 + c0 is a multiple of 32: 16-byte aligned broadcast loads
+          *reinterpret_cast<int4*>(kp + 4 * i) = *reinterpret_cast<const int4*>(key_pos + win0 + c0 + 4 * i);
+          *reinterpret_cast<float4*>(ks + 4 * i) = *reinterpret_cast<const float4*>(key_scale + win0 + c0 + 4 * i);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float ex = exp2f(fmaf(__uint_as_float(r[i]), ks[i], -row_bound));
+          e[i] = (kp[i] > q_limit || kp[i] == q_enc) ? 0.f : ex;       // exp2(mask_value - m) == exp2(self_value - m) == 0
+          sum4[i & 3] += e[i];
+        }
+        // keys win0+c0 .. +31 -> P tile k-block (col/64), 16-byte chunk (col%64)/8.  (Overwrites the K tile: S is complete.)
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int col = win0 + c0 + q4 * 8;
+          uint4 u;
+          u.x = pack_bf16(e[q4 * 8 + 0], e[q4 * 8 + 1]);
+          u.y = pack_bf16(e[q4 * 8 + 2], e[q4 * 8 + 3]);
+          u.z = pack_bf16(e[q4 * 8 + 4], e[q4 * 8 + 5]);
+          u.w = pack_bf16(e[q4 * 8 + 6], e[q4 * 8 + 7]);
+          *reinterpret_cast<uint4*>(p_row_base + (col >> 6) * (kQRows * 128) + sw128_offset(m, (col & 63) >> 3)) = u;
+        }
+      }
+      float row_sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      float row_max = row_bound;
+      bool redo = !(row_sum > 1e-30f);
+      if (redo) {
+        // Usual cause: every visible key is masked and only the query itself (masked to self_value) remains - then the
+        // softmax is one-hot on the self column (rp R8 "except when no other targets are available").  Decide from the
+        // position ids alone (no TMEM access, so this branch may diverge).
+        int n_self = 0;
+        bool any_visible = false;
+        for (int col = 0; col < kWin; ++col) {
+          const int kpi = key_pos[win0 + col];
+          if (kpi == q_enc) ++n_self;
+          else if (!(kpi > q_limit)) any_visible = true;
+        }
+        if (!any_visible && n_self > 0) {
+          // the fast pass stored zeros everywhere; give every self column weight 1 (the token can sit in the window twice:
+          // in its own chunk and, at a round boundary, in the previous round's last chunk)
+          for (int col = 0; col < kWin; ++col) {
+            if (key_pos[win0 + col] == q_enc) {
+              const int kc = win0 + col;
+              *reinterpret_cast<uint16_t*>(p_row_base + (kc >> 6) * (kQRows * 128) + sw128_offset(m, (kc & 63) >> 3) + (kc & 7) * 2) = 0x3F80;
+            }
+          }
+          row_sum = static_cast<float>(n_self);
+          row_max = sv;
+          redo = false;
+        }
+      }
+      if (__any_sync(0xffffffffu, redo)) {
+        // exact two-pass arithmetic for the rows that need it; the TMEM loads are warp-collective, so every lane walks the loop
+        float mx = -FLT_MAX;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kWin; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + win0 + c0, r);
+          tmem_ld_wait();
+          if (redo) {
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+              const int kpi = key_pos[win0 + c0 + i];
+              float sc = __uint_as_float(r[i]) * key_scale[win0 + c0 + i];
+              sc = kpi > q_limit ? mv : sc;
+              sc = kpi == q_enc ? sv : sc;
+              mx = fmaxf(mx, sc);
+            }
+          }
+        }
+        float sm = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kWin; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + win0 + c0, r);
+          tmem_ld_wait();
+          if (redo) {
+#pragma unroll 1
+            for (int q8 = 0; q8 < 4; ++q8) {
+              float e8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int col = win0 + c0 + q8 * 8 + i;
+                const int kpi = key_pos[col];
+                float sc = __uint_as_float(r[q8 * 8 + i]) * key_scale[col];
+                sc = kpi > q_limit ? mv : sc;
+                sc = kpi == q_enc ? sv : sc;
+                e8[i] = exp2f(sc - mx);
+                sm += e8[i];
+              }
+              const int col = win0 + c0 + q8 * 8;
+              uint4 u;
+              u.x = pack_bf16(e8[0], e8[1]); u.y = pack_bf16(e8[2], e8[3]);
+              u.z = pack_bf16(e8[4], e8[5]); u.w = pack_bf16(e8[6], e8[7]);
+              *reinterpret_cast<uint4*>(p_row_base + (col >> 6) * (kQRows * 128) + sw128_offset(m, (col & 63) >> 3)) = u;
+            }
+          }
+        }
+        if (redo) { row_max = mx; row_sum = sm; }
+      }
+      if (BUCKET == 64) {
+        // the 64 key rows outside this query's window contribute nothing: zero that k-block of P
+        const int dead_block = (m < 64) ? 2 : 0;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(p_row_base + dead_block * (kQRows * 128) + sw128_offset(m, c)) = z;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();       // this thread's TMEM reads of S precede the MMAs that overwrite the region
+      mbar_arrive(p_full + wg);
+
+      mbar_wait(o_full + wg, ph);
+      tc_fence_after_sync();
+      {
+        const float inv_sum = 1.f / row_sum;
+        const int64_t slot = static_cast<int64_t>(row_bh) * RT + my_slot;
+        uint4* dst = reinterpret_cast<uint4*>(p.o_rounds + slot * kDh);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld32(t_row + kColO + half * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(r[q4 * 8 + 0]) * inv_sum, __uint_as_float(r[q4 * 8 + 1]) * inv_sum);
+            u.y = pack_bf16(__uint_as_float(r[q4 * 8 + 2]) * inv_sum, __uint_as_float(r[q4 * 8 + 3]) * inv_sum);
+            u.z = pack_bf16(__uint_as_float(r[q4 * 8 + 4]) * inv_sum, __uint_as_float(r[q4 * 8 + 5]) * inv_sum);
+            u.w = pack_bf16(__uint_as_float(r[q4 * 8 + 6]) * inv_sum, __uint_as_float(r[q4 * 8 + 7]) * inv_sum);
+            dst[half * 4 + q4] = u;
+          }
+        }
+        p.lse_rounds[slot] = (row_max + log2f(row_sum)) * kLn2;
+      }
+      tc_fence_before_sync();
+      mbar_arrive(o_free + wg);     // O columns of this group may be overwritten
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -340,7 +456,8 @@ int launch_attn_fwd(const AttnFwdParams& p, int ctas, cudaStream_t stream) {
     if (e != cudaSuccess) return fail(kErrCuda, "rtts_lsh_attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  lsh_attn_fwd_kernel<BUCKET><<<ctas, 128, L::kDynamic, stream>>>(p);
+  const int grid = ctas < kNumSMs ? ctas : kNumSMs;     // persistent: one CTA per SM
+  lsh_attn_fwd_kernel<BUCKET><<<grid, kFwdThreads, L::kDynamic, stream>>>(p, ctas);
   return check_launch("rtts_lsh_attn_fwd");
 }
 
@@ -348,10 +465,10 @@ int launch_attn_fwd(const AttnFwdParams& p, int ctas, cudaStream_t stream) {
 
 using namespace rtts;
 
-extern "C" int rtts_lsh_attn_fwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const uint8_t* mask,
+extern "C" int rtts_lsh_attn_fwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const float* sumsq, const uint8_t* mask,
                                  const rtts_lsh_spec* spec, void* o_rounds, float* lse_rounds, int B, int T, int H, int dh,
                                  int R, int bucket, void* stream) {
-  RTTS_REQUIRE(qk && v && sticker && spec && o_rounds && lse_rounds, "rtts_lsh_attn_fwd: null pointer");
+  RTTS_REQUIRE(qk && v && sticker && sumsq && spec && o_rounds && lse_rounds, "rtts_lsh_attn_fwd: null pointer");
   RTTS_REQUIRE(dh == kDh, "rtts_lsh_attn_fwd: head size %d unsupported (64 only)", dh);
   RTTS_REQUIRE(bucket == 64 || bucket == 128, "rtts_lsh_attn_fwd: bucket size %d unsupported (64 or 128)", bucket);
   RTTS_REQUIRE(T % (2 * bucket) == 0, "rtts_lsh_attn_fwd: T=%d must be a multiple of 2*bucket", T);
@@ -364,6 +481,7 @@ extern "C" int rtts_lsh_attn_fwd(const void* qk, const void* v, int64_t ld, cons
   p.v = static_cast<const __nv_bfloat16*>(v);
   p.ld = ld;
   p.sticker = sticker;
+  p.sumsq = sumsq;
   p.mask = mask;
   p.o_rounds = static_cast<__nv_bfloat16*>(o_rounds);
   p.lse_rounds = lse_rounds;

@@ -22,8 +22,8 @@ template <int DH>
 __global__ void __launch_bounds__(kHashThreads) lsh_hash_kernel(const __nv_bfloat16* __restrict__ qk, int64_t ld,
                                                                 const float* __restrict__ rot, int rot_heads,
                                                                 const uint8_t* __restrict__ pad_mask, int use_pad_bucket,
-                                                                int32_t* __restrict__ buckets, int T, int H, int R,
-                                                                int n_buckets) {
+                                                                int32_t* __restrict__ buckets, float* __restrict__ sumsq, int T, int H,
+                                                                int R, int n_buckets) {
   __shared__ __align__(16) float rot_s[kProjBlock * kRotLd];
   const int half = n_buckets >> 1;
   const int P = R * half;  // projections per vector
@@ -45,6 +45,12 @@ __global__ void __launch_bounds__(kHashThreads) lsh_hash_kernel(const __nv_bfloa
   } else {
 #pragma unroll
     for (int k = 0; k < DH; ++k) x[k] = 0.f;
+  }
+  if (sumsq != nullptr && live) {     // |x|^2 of the row, reused by the attention kernels for the key normalisation
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < DH; ++k) ss = fmaf(x[k], x[k], ss);
+    sumsq[(static_cast<int64_t>(b) * H + h) * T + t] = ss;
   }
   const float* rot_h = rot + static_cast<int64_t>(rot_heads == 1 ? 0 : h) * DH * P;
   const bool padded = use_pad_bucket && pad_mask != nullptr && live && pad_mask[static_cast<int64_t>(b) * T + t] == 0;
@@ -164,8 +170,8 @@ __global__ void __launch_bounds__(kSortThreads) lsh_sort_kernel(const int32_t* _
 using namespace rtts;
 
 extern "C" int rtts_lsh_hash(const void* qk, int64_t ld, const float* rot, int rot_heads, const uint8_t* pad_mask,
-                             int use_pad_bucket, int32_t* buckets, int B, int T, int H, int dh, int R, int n_buckets,
-                             void* stream) {
+                             int use_pad_bucket, int32_t* buckets, float* sumsq, int B, int T, int H, int dh, int R,
+                             int n_buckets, void* stream) {
   RTTS_REQUIRE(qk && rot && buckets, "rtts_lsh_hash: null pointer");
   RTTS_REQUIRE(dh == 64, "rtts_lsh_hash: head size %d unsupported (64 only)", dh);
   RTTS_REQUIRE(n_buckets >= 2 && n_buckets % 2 == 0, "rtts_lsh_hash: n_buckets must be even, got %d", n_buckets);
@@ -174,7 +180,7 @@ extern "C" int rtts_lsh_hash(const void* qk, int64_t ld, const float* rot, int r
   RTTS_REQUIRE(B > 0 && T > 0 && H > 0 && R > 0 && B < 65536 && H < 65536, "rtts_lsh_hash: bad sizes");
   dim3 grid((T + kHashThreads - 1) / kHashThreads, H, B);
   lsh_hash_kernel<64><<<grid, kHashThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qk), ld, rot, rot_heads, pad_mask, use_pad_bucket, buckets, T, H, R, n_buckets);
+      static_cast<const __nv_bfloat16*>(qk), ld, rot, rot_heads, pad_mask, use_pad_bucket, buckets, sumsq, T, H, R, n_buckets);
   return check_launch("rtts_lsh_hash");
 }
 

@@ -161,6 +161,29 @@ __global__ void __launch_bounds__(256) lsh_delta_kernel(const __nv_bfloat16* __r
   if (row < rows && c == 0) delta[(b * H + h) * T + t] = s;
 }
 
+// sumsq[(b*H+h)*T + t] = |qk[b,t,h,:]|^2 (fp32), 8 lanes per 64-wide head slice.  Same quantity rtts_lsh_hash can emit.
+__global__ void __launch_bounds__(256) lsh_sumsq_kernel(const __nv_bfloat16* __restrict__ qk, int64_t ld, float* __restrict__ sumsq, int T, int H,
+                                                        int64_t rows) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) >> 3;   // (b*T + t)*H + h
+  const int c = threadIdx.x & 7;
+  float s = 0.f;
+  int64_t b = 0; int t = 0, h = 0;
+  if (row < rows) {
+    const int64_t bt = row / H;
+    h = static_cast<int>(row - bt * H);
+    b = bt / T;
+    t = static_cast<int>(bt - b * T);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(qk + bt * ld + h * 64) + c);
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s += bf16_lo(w[e]) * bf16_lo(w[e]) + bf16_hi(w[e]) * bf16_hi(w[e]);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (row < rows && c == 0) sumsq[(b * H + h) * T + t] = s;
+}
+
 }  // namespace rtts
 
 using namespace rtts;
@@ -223,4 +246,14 @@ extern "C" int rtts_lsh_delta(const void* dout, const void* out, int64_t ld, flo
   lsh_delta_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(out), ld, delta, T, H, rows);
   return check_launch("rtts_lsh_delta");
+}
+
+extern "C" int rtts_lsh_sumsq(const void* qk, int64_t ld, float* sumsq, int B, int T, int H, int dh, void* stream) {
+  RTTS_REQUIRE(qk && sumsq, "rtts_lsh_sumsq: null pointer");
+  RTTS_REQUIRE(dh == 64 && ld % 8 == 0, "rtts_lsh_sumsq: head size 64 and 16-byte rows required");
+  const int64_t rows = static_cast<int64_t>(B) * T * H;
+  const int64_t blocks = (rows * 8 + 255) / 256;
+  lsh_sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(qk), ld, sumsq, T, H,
+                                                                                                  rows);
+  return check_launch("rtts_lsh_sumsq");
 }

@@ -55,9 +55,9 @@ class _LSHAttentionFn(torch.autograd.Function):
             xn, mean, rstd = ops.cast_bf16_colsum(x2), None, None
         qkv = ops.gemm(xn, wqkv_bf16, out_dtype=torch.bfloat16).view(b, t, 2 * d)
         qk, v = qkv[..., :d], qkv[..., d:]
-        buckets = ops.lsh_hash(qk, rot, h, r, nb, mask_u8 if pad_bucket else None, pad_bucket)
+        buckets, sumsq = ops.lsh_hash(qk, rot, h, r, nb, mask_u8 if pad_bucket else None, pad_bucket, return_sumsq=True)
         sticker, undo = ops.lsh_sort(buckets, t, r, nb + 1 if pad_bucket else nb)
-        o_rounds, lse_rounds = ops.lsh_attn_fwd(qk, v, sticker, mask_u8, spec, h, r, bucket)
+        o_rounds, lse_rounds = ops.lsh_attn_fwd(qk, v, sticker, mask_u8, spec, h, r, bucket, sumsq=sumsq)
         out, lse = ops.lsh_merge_fwd(o_rounds, lse_rounds)
         if wout_bf16 is not None:
             y = ops.gemm(out.view(b * t, d), wout_bf16, bias=b_out).view(b, t, d)
@@ -65,13 +65,13 @@ class _LSHAttentionFn(torch.autograd.Function):
             y = out.float()
         ctx.cfg = cfg
         ctx.has_ln, ctx.has_out = ln_w is not None, wout_bf16 is not None
-        ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, sticker, undo, out, lse, mask_u8, wqkv_bf16, wout_bf16)
+        ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, sticker, undo, out, lse, mask_u8, wqkv_bf16, wout_bf16, sumsq)
         cfg["_last_buckets"] = buckets
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, ln_w, mean, rstd, xn, qkv, sticker, undo, out, lse, mask_u8, wqkv_bf16, wout_bf16 = ctx.saved_tensors
+        x, ln_w, mean, rstd, xn, qkv, sticker, undo, out, lse, mask_u8, wqkv_bf16, wout_bf16, sumsq = ctx.saved_tensors
         cfg = ctx.cfg
         b, t, d = x.shape
         h, r, bucket, spec = cfg["heads"], cfg["n_hashes"], cfg["bucket_size"], cfg["spec"]
@@ -89,7 +89,7 @@ class _LSHAttentionFn(torch.autograd.Function):
         delta = ops.lsh_delta(dout, out, h)
         qk, v = qkv[..., :d], qkv[..., d:]
         dqkv = torch.empty((b, t, 2 * d), dtype=torch.bfloat16, device=dev)
-        ops.lsh_attn_bwd(qk, v, sticker, undo, mask_u8, spec, dout, lse, delta, h, r, bucket, out_dqk=dqkv[..., :d], out_dv=dqkv[..., d:])
+        ops.lsh_attn_bwd(qk, v, sticker, undo, mask_u8, spec, dout, lse, delta, h, r, bucket, out_dqk=dqkv[..., :d], out_dv=dqkv[..., d:], sumsq=sumsq)
         dqkv2 = dqkv.view(b * t, 2 * d)
         g_wqkv = torch.zeros((2 * d, d), dtype=torch.float32, device=dev)
         ops.gemm(dqkv2, xn, a_mn_major=True, b_mn_major=True, out=g_wqkv, accumulate=True, split_k=_split_k(b * t))

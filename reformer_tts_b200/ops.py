@@ -129,8 +129,8 @@ def _token_major(t: torch.Tensor, name: str) -> int:
 
 
 def lsh_hash(qk: torch.Tensor, rot: torch.Tensor, n_heads: int, n_rounds: int, n_buckets: int,
-             pad_mask: Optional[torch.Tensor] = None, use_pad_bucket: bool = False) -> torch.Tensor:
-    """qk bf16 [B,T,H*64]; rot fp32 [1|H, 64, R, nb/2]  ->  buckets int32 [B,H,R*T]."""
+             pad_mask: Optional[torch.Tensor] = None, use_pad_bucket: bool = False, return_sumsq: bool = False):
+    """qk bf16 [B,T,H*64]; rot fp32 [1|H, 64, R, nb/2]  ->  buckets int32 [B,H,R*T] (and |qk row|^2 fp32 [B,H,T])."""
     ld = _token_major(qk, "qk")
     b, t, c = qk.shape
     dh = c // n_heads
@@ -141,9 +141,19 @@ def lsh_hash(qk: torch.Tensor, rot: torch.Tensor, n_heads: int, n_rounds: int, n
         _check(pad_mask, torch.uint8, "pad_mask")
         pad_mask = pad_mask.contiguous()
     out = torch.empty((b, n_heads, n_rounds * t), dtype=torch.int32, device=qk.device)
+    sumsq = torch.empty((b, n_heads, t), dtype=torch.float32, device=qk.device) if return_sumsq else None
     _launch(_tag("lsh_hash", locals()), "rtts_lsh_hash", _ptr(qk), ld, _ptr(rot), rot.shape[0], _ptr(pad_mask), int(use_pad_bucket), _ptr(out),
-              b, t, n_heads, dh, n_rounds, n_buckets, _stream())
-    return out
+              _ptr(sumsq), b, t, n_heads, dh, n_rounds, n_buckets, _stream())
+    return (out, sumsq) if return_sumsq else out
+
+
+def lsh_sumsq(qk: torch.Tensor, n_heads: int) -> torch.Tensor:
+    """|qk[b,t,h,:]|^2 -> fp32 [B,H,T]."""
+    ld = _token_major(qk, "qk")
+    b, t, c = qk.shape
+    sumsq = torch.empty((b, n_heads, t), dtype=torch.float32, device=qk.device)
+    _launch(_tag("lsh_sumsq", locals()), "rtts_lsh_sumsq", _ptr(qk), ld, _ptr(sumsq), b, t, n_heads, c // n_heads, _stream())
+    return sumsq
 
 
 def lsh_sort(buckets: torch.Tensor, seq_len: int, n_rounds: int, ids_per_round: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -157,7 +167,7 @@ def lsh_sort(buckets: torch.Tensor, seq_len: int, n_rounds: int, ids_per_round: 
 
 
 def lsh_attn_fwd(qk: torch.Tensor, v: torch.Tensor, sticker: torch.Tensor, mask: Optional[torch.Tensor], spec: LSHSpec,
-                 n_heads: int, n_rounds: int, bucket: int) -> Tuple[torch.Tensor, torch.Tensor]:
+                 n_heads: int, n_rounds: int, bucket: int, sumsq: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """-> o_rounds bf16 [B,H,R,T,64], lse_rounds fp32 [B,H,R,T] (both already unsorted)."""
     ld = _token_major(qk, "qk")
     if _token_major(v, "v") != ld:
@@ -169,10 +179,14 @@ def lsh_attn_fwd(qk: torch.Tensor, v: torch.Tensor, sticker: torch.Tensor, mask:
     if mask is not None:
         _check(mask, torch.uint8, "mask")
         mask = mask.contiguous()
+    if sumsq is None:
+        sumsq = lsh_sumsq(qk, n_heads)
+    _check(sumsq, torch.float32, "sumsq")
+    assert sumsq.is_contiguous() and sumsq.numel() == b * n_heads * t
     o = torch.empty((b, n_heads, n_rounds, t, dh), dtype=torch.bfloat16, device=qk.device)
     lse = torch.empty((b, n_heads, n_rounds, t), dtype=torch.float32, device=qk.device)
     st = spec.struct()
-    _launch(_tag("lsh_attn_fwd", locals()), "rtts_lsh_attn_fwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(mask), ctypes.byref(st), _ptr(o), _ptr(lse),
+    _launch(_tag("lsh_attn_fwd", locals()), "rtts_lsh_attn_fwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(sumsq), _ptr(mask), ctypes.byref(st), _ptr(o), _ptr(lse),
               b, t, n_heads, dh, n_rounds, bucket, _stream())
     return o, lse
 
@@ -200,7 +214,7 @@ def lsh_delta(dout: torch.Tensor, out: torch.Tensor, n_heads: int) -> torch.Tens
 
 
 def lsh_attn_bwd(qk, v, sticker, undo, mask, spec: LSHSpec, dout, lse, delta, n_heads: int, n_rounds: int, bucket: int,
-                 out_dqk: Optional[torch.Tensor] = None, out_dv: Optional[torch.Tensor] = None):
+                 out_dqk: Optional[torch.Tensor] = None, out_dv: Optional[torch.Tensor] = None, sumsq: Optional[torch.Tensor] = None):
     """Backward of lsh_attn_fwd + lsh_merge_fwd (scores recomputed in-kernel) -> dqk, dv bf16 [B,T,H*64]."""
     ld = _token_major(qk, "qk")
     if _token_major(v, "v") != ld:
@@ -212,10 +226,13 @@ def lsh_attn_bwd(qk, v, sticker, undo, mask, spec: LSHSpec, dout, lse, delta, n_
     _check(delta, torch.float32, "delta")
     _check(undo, torch.int32, "undo")
     assert lse.is_contiguous() and delta.is_contiguous() and sticker.is_contiguous() and undo.is_contiguous()
+    if sumsq is None:
+        sumsq = lsh_sumsq(qk, n_heads)
+    _check(sumsq, torch.float32, "sumsq")
     # fp32 per-round partials [3, B,H,R,T,dh]: dqk_main, dq_b, dv
     part = torch.empty((3, b, n_heads, n_rounds, t, dh), dtype=torch.float32, device=qk.device)
     st = spec.struct()
-    _launch(_tag("lsh_attn_bwd", locals()), "rtts_lsh_attn_bwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(mask), ctypes.byref(st), _ptr(dout), ld_do,
+    _launch(_tag("lsh_attn_bwd", locals()), "rtts_lsh_attn_bwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(sumsq), _ptr(mask), ctypes.byref(st), _ptr(dout), ld_do,
               _ptr(lse), _ptr(delta), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), b, t, n_heads, dh, n_rounds,
               bucket, _stream())
     dqk = torch.empty((b, t, c), dtype=torch.bfloat16, device=qk.device) if out_dqk is None else out_dqk

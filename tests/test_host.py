@@ -28,7 +28,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared - {"rtts_last_error", "rtts_abi_version"} == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
     assert lib.rtts_abi_version() == 1
     # argument validation happens before any CUDA call: a bad head size is reported, not launched
-    rc = lib.rtts_lsh_hash(None, 0, None, 1, None, 0, None, 1, 128, 1, 64, 1, 2, None)
+    rc = lib.rtts_lsh_hash(None, 0, None, 1, None, 0, None, None, 1, 128, 1, 64, 1, 2, None)
     assert rc != 0 and b"null pointer" in lib.rtts_last_error()
 
 
