@@ -41,6 +41,10 @@ class GradientAverager:
         if not params or self.world == 1:
             return
         flat = torch.cat([p.grad.reshape(-1) for p in params])
+        if not self.overlap:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            self._pending.append((None, flat, params))
+            return
         if flat.is_cuda:
             if self._stream is None:
                 self._stream = torch.cuda.Stream()
@@ -53,7 +57,12 @@ class GradientAverager:
         self._pending.append((work, flat, params))
 
     def _on_block_done(self, index, block):
-        self._launch(self._block_params.get(id(block), []))
+        if self.overlap:
+            self._launch(self._block_params.get(id(block), []))
+
+    def disable_overlap(self):
+        """One flat all-reduce after backward on the current stream (what a CUDA-graph capture of the step records)."""
+        self.overlap = False
 
     # -- API -------------------------------------------------------------------------------------------------------
     def finish(self):
@@ -65,9 +74,10 @@ class GradientAverager:
         else:
             self._launch([p for p in self.model.parameters() if p.requires_grad])
         for work, flat, params in self._pending:
-            work.wait()
-            if flat.is_cuda:
-                torch.cuda.current_stream().wait_stream(self._stream)
+            if work is not None:
+                work.wait()
+                if flat.is_cuda:
+                    torch.cuda.current_stream().wait_stream(self._stream)
             flat.div_(self.world)
             offset = 0
             for p in params:

@@ -24,7 +24,9 @@ from .ops import LSHSpec
 
 
 class _WeightCache:
-    """bf16 copies of fp32 master weights, rebuilt only when a weight's version counter moves."""
+    """bf16 copies of fp32 master weights, rebuilt only when a weight's version counter moves.  ``enabled = False`` forces the
+    cast on every call (needed while a CUDA graph is captured: the cast must be part of the graph, weights change on replay)."""
+    enabled = True
 
     def __init__(self):
         self._key = None
@@ -32,7 +34,7 @@ class _WeightCache:
 
     def get(self, *weights: torch.Tensor) -> torch.Tensor:
         key = tuple((w.data_ptr(), w._version) for w in weights)
-        if key != self._key:
+        if key != self._key or not _WeightCache.enabled:
             with torch.no_grad():
                 self._val = torch.cat([w.detach() for w in weights], dim=0).to(torch.bfloat16).contiguous()
             self._key = key

@@ -23,7 +23,16 @@ from torch.utils.checkpoint import get_device_states, set_device_states
 
 class Deterministic(nn.Module):
     """Runs ``net``; can record the RNG state before a run and replay it later (ref:...reversible.py:11-41), so the
-    rotations drawn by the LSH hash and the dropout masks of the recompute equal those of the forward."""
+    rotations drawn by the LSH hash and the dropout masks of the recompute equal those of the forward.
+
+    Two mechanisms give that guarantee:
+    * default - the reference's: save the CPU / CUDA generator states in the forward, restore them inside ``fork_rng`` for the
+      recompute.  Needs host access to the generator state, which CUDA-graph capture forbids.
+    * ``use_private_generators(seed)`` - capture-safe: the module owns two CUDA generators with the same seed; the forward run
+      consumes one, the recompute the other (the default generator is pointed at them with ``graphsafe_set_state`` for the
+      duration of the run), so both see the same stream without ever reading a generator state.  Used by
+      ``reformer_tts_b200.training.TrainStep`` when it captures the step in a CUDA graph.
+    """
 
     def __init__(self, net):
         super().__init__()
@@ -32,6 +41,13 @@ class Deterministic(nn.Module):
         self.cuda_in_fwd = None
         self.gpu_devices = None
         self.gpu_states = None
+        self._private = None        # (device index, forward generator, recompute generator)
+
+    def use_private_generators(self, seed: int, device: torch.device):
+        fwd = torch.Generator(device=device).manual_seed(seed)
+        rec = torch.Generator(device=device).manual_seed(seed)
+        self._private = (device.index if device.index is not None else torch.cuda.current_device(), fwd, rec)
+        return fwd, rec
 
     def record_rng(self, *args):
         self.cpu_state = torch.get_rng_state()
@@ -39,7 +55,18 @@ class Deterministic(nn.Module):
             self.cuda_in_fwd = True
             self.gpu_devices, self.gpu_states = get_device_states(*args)
 
+    def _run_private(self, generator, *args, **kwargs):
+        default = torch.cuda.default_generators[self._private[0]]
+        saved = default.graphsafe_get_state()
+        default.graphsafe_set_state(generator)
+        try:
+            return self.net(*args, **kwargs)
+        finally:
+            default.graphsafe_set_state(saved)
+
     def forward(self, *args, record_rng=False, set_rng=False, **kwargs):
+        if self._private is not None and (record_rng or set_rng):
+            return self._run_private(self._private[2] if set_rng else self._private[1], *args, **kwargs)
         if record_rng:
             self.record_rng(*args)
         if not set_rng:
