@@ -292,30 +292,34 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       float row_sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       float row_max = row_bound;
       bool redo = !(row_sum > 1e-30f);
-      if (redo) {
-        // Usual cause: every visible key is masked and only the query itself (masked to self_value) remains - then the
-        // softmax is one-hot on the self column (rp R8 "except when no other targets are available").  Decide from the
-        // position ids alone (no TMEM access, so this branch may diverge).
-        int n_self = 0;
-        bool any_visible = false;
-        for (int col = 0; col < kWin; ++col) {
-          const int kpi = key_pos[win0 + col];
-          if (kpi == q_enc) ++n_self;
-          else if (!(kpi > q_limit)) any_visible = true;
-        }
-        if (!any_visible && n_self > 0) {
-          // the fast pass stored zeros everywhere; give every self column weight 1 (the token can sit in the window twice:
-          // in its own chunk and, at a round boundary, in the previous round's last chunk)
-          for (int col = 0; col < kWin; ++col) {
-            if (key_pos[win0 + col] == q_enc) {
-              const int kc = win0 + col;
-              *reinterpret_cast<uint16_t*>(p_row_base + (kc >> 6) * (kQRows * 128) + sw128_offset(m, (kc & 63) >> 3) + (kc & 7) * 2) = 0x3F80;
+      if (redo && row_bound < 60.f) {
+        // Every term was exactly zero.  With bound < 60 a visible key cannot underflow (s - bound >= -2*bound > -126), so no key
+        // is visible: only the query itself (masked to self_value) remains and the softmax is uniform over the self columns
+        // (rp R8 "except when no other targets are available").  The query's own column is known; the same token can appear a
+        // second time only when the look-back chunk comes from the previous hash round (first tile of a round).
+        auto set_one = [&](int kc) {
+          *reinterpret_cast<uint16_t*>(p_row_base + (kc >> 6) * (kQRows * 128) + sw128_offset(m, (kc & 63) >> 3) + (kc & 7) * 2) = 0x3F80;
+        };
+        set_one(kQOff + m);
+        int n_self = 1;
+        const int t_in = tile - row_bh * p.tiles_per_row;
+        if ((t_in * kQRows) % p.T == 0 && win0 == 0) {       // window starts with the previous round's last chunk
+#pragma unroll 4
+          for (int c4 = 0; c4 < BUCKET; c4 += 4) {
+            const int4 k4 = *reinterpret_cast<const int4*>(key_pos + c4);
+            const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (kk[i] == q_enc) {
+                set_one(c4 + i);
+                ++n_self;
+              }
             }
           }
-          row_sum = static_cast<float>(n_self);
-          row_max = sv;
-          redo = false;
         }
+        row_sum = static_cast<float>(n_self);
+        row_max = sv;
+        redo = false;
       }
       if (__any_sync(0xffffffffu, redo)) {
         // exact two-pass arithmetic for the rows that need it; the TMEM loads are warp-collective, so every lane walks the loop
