@@ -84,7 +84,7 @@ int rtts_lsh_delta(const void* dout, const void* out, int64_t ld, float* delta, 
 /* Backward of rtts_lsh_attn_fwd + rtts_lsh_merge_fwd with in-kernel recompute of the scores
  * (autograd of rp R4-R11; the per-round o / lse of the forward are not needed).  Inputs: qk, v, sticker, sumsq,
  * mask as in forward; dout bf16 [B,T,H*dh] (ld_dout) = gradient of the merged output; lse [B,H,T] from
- * rtts_lsh_merge_fwd; delta [B,H,T] from rtts_lsh_delta.  Outputs, fp32 [B,H,R,T,dh], scattered to the
+ * rtts_lsh_merge_fwd; delta [B,H,T] from rtts_lsh_delta.  Outputs, bf16 [B,H,R,T,dh], scattered to the
  * UNSORTED slot like the forward:
  *   dqk_main  gradient w.r.t. the qk row of the slot from the CTA that owns it as a key: its key-role gradient
  *             (key-normalisation Jacobian applied) plus the query-role gradient from that CTA's keys,
@@ -93,13 +93,13 @@ int rtts_lsh_delta(const void* dout, const void* out, int64_t ld, float* delta, 
  *   dv_rounds value gradient. */
 int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const float* sumsq, const uint8_t* mask,
                       const rtts_lsh_spec* spec_host, const void* dout, int64_t ld_dout, const float* lse,
-                      const float* delta, float* dqk_main, float* dq_b, float* dv_rounds, int B, int T, int H, int dh,
+                      const float* delta, void* dqk_main, void* dq_b, void* dv_rounds, int B, int T, int H, int dh,
                       int R, int bucket, void* stream);
 
 /* Sum the per-round gradients over the R rounds: dqk = sum_r (dqk_main + dq_b), dv = sum_r dv_rounds,
  * both bf16 [B,T,H*dh] (ld).  undo (from rtts_lsh_sort) tells which slots have a dq_b entry; may be NULL
  * when bucket == 128. */
-int rtts_lsh_grad_reduce(const float* dqk_main, const float* dq_b, const float* dv_rounds, const int32_t* undo,
+int rtts_lsh_grad_reduce(const void* dqk_main, const void* dq_b, const void* dv_rounds, const int32_t* undo,
                          void* dqk, void* dv, int64_t ld, int B, int T, int H, int dh, int R, int bucket,
                          void* stream);
 

@@ -43,14 +43,18 @@ struct AttnBwdParams {
   const uint8_t* mask;
   const float* lse;     // [B,H,T]
   const float* delta;   // [B,H,T]
-  float* dqk_main;   // per key slot: query-role gradient from this CTA's keys + key-role gradient (Jacobian applied)
-  float* dq_b;       // per look-ahead slot: query-role gradient from this CTA's keys
-  float* dv;
+  __nv_bfloat16* dqk_main;   // per key slot: query-role gradient from this CTA's keys + key-role gradient (Jacobian applied)
+  __nv_bfloat16* dq_b;       // per look-ahead slot: query-role gradient from this CTA's keys
+  __nv_bfloat16* dv;
+  long long* trace;   // debug: clock64 stamps of CTA 0 (nullable)
   int T, H, R, tiles_per_row;
   float score_scale;
   float mask_value_log2, self_value_log2;
   int key_norm, mask_mode, causal;
 };
+
+#define RTTS_BSTAMP(k) do { if (p.trace != nullptr && blockIdx.x == 0 && tid == 0) p.trace[(k)] = clock64(); } while (0)
+constexpr int kBwdThreads = 512;     // 4 warpgroups; warpgroup g owns 16 of the 64 query columns of every block / 16 of the 64 output columns
 
 template <int BUCKET>
 struct AttnBwdSmem {
@@ -64,19 +68,21 @@ struct AttnBwdSmem {
   static constexpr int kOffQMeta = kOffDS + 4 * kBlk;      // int2[kQRows]  (enc, limit)
   static constexpr int kOffQStat = kOffQMeta + kQRows * 8; // float2[kQRows] (L*log2e, delta)
   static constexpr int kOffQSlot = kOffQStat + kQRows * 8; // int[kQRows] unsorted slot
-  static constexpr int kOffBar = kOffQSlot + kQRows * 4;
-  static constexpr int kOffTmem = kOffBar + 8;
+  static constexpr int kOffKInv = kOffQSlot + kQRows * 4;  // float[kKeyRows] 1/|k|
+  static constexpr int kOffDot = kOffKInv + kKeyRows * 4;  // float[4][kKeyRows] partial <x, G>
+  static constexpr int kOffBar = kOffDot + 4 * kKeyRows * 4;   // 2 mbarriers (S/dP buffers) + 1 (accumulators)
+  static constexpr int kOffTmem = kOffBar + 3 * 8;
   static constexpr int kTotal = kOffTmem + 8;
   static constexpr int kDynamic = kTotal + 1024;
 };
 
 template <int BUCKET>
-__global__ void __launch_bounds__(128) lsh_attn_bwd_kernel(const AttnBwdParams p) {
+__global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const AttnBwdParams p) {
   using L = AttnBwdSmem<BUCKET>;
   constexpr int kQRows = L::kQRows, kQBlocks = L::kQBlocks;
   constexpr uint32_t kTmemCols = 512;
-  // TMEM columns
-  constexpr uint32_t cS = 0, cDP = 64, cDV = 128, cG = 192, cDQ0 = 256, cDQ1 = 320;
+  // TMEM columns: two (St, dPt) buffers so the tensor core works on block qb+1 while block qb is consumed
+  constexpr uint32_t cS0 = 0, cDP0 = 64, cS1 = 128, cDP1 = 192, cDV = 256, cG = 320, cDQ0 = 384, cDQ1 = 448;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,10 +91,15 @@ __global__ void __launch_bounds__(128) lsh_attn_bwd_kernel(const AttnBwdParams p
   int2* q_meta = reinterpret_cast<int2*>(smem + L::kOffQMeta);
   float2* q_stat = reinterpret_cast<float2*>(smem + L::kOffQStat);
   int* q_slot = reinterpret_cast<int*>(smem + L::kOffQSlot);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  float* k_inv = reinterpret_cast<float*>(smem + L::kOffKInv);
+  float* dot_part = reinterpret_cast<float*>(smem + L::kOffDot);
+  uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + L::kOffBar);     // [2]
+  uint64_t* bar_acc = bar_s + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int wg = tid >> 7;            // column group 0..3
+  const int j = tid & 127;            // key row = TMEM lane
   const int row_bh = blockIdx.x / p.tiles_per_row;
   const int tile = blockIdx.x - row_bh * p.tiles_per_row;
   const int b = row_bh / p.H, h = row_bh - b * p.H;
@@ -96,134 +107,125 @@ __global__ void __launch_bounds__(128) lsh_attn_bwd_kernel(const AttnBwdParams p
   const int32_t* stk = p.sticker + static_cast<int64_t>(row_bh) * RT;
   const int first_slot = tile * kKeyRows;      // sorted slot of row 0; rows >= RT wrap to the start
 
+  RTTS_BSTAMP(0);
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_s + 1, 1);
+    mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
 
   // ---- gather qk / dout rows of the query slots, v rows of the key slots ---------------------------------
   // pos = sticker - round*T with the round taken from the slot index (see the forward kernel).
   {
-    const int g = tid >> 3, c = tid & 7;
-    constexpr int kPasses = kQRows / 16;
+    const int g = tid >> 3, c = tid & 7;          // 64 row groups of 8 lanes
+    constexpr int kPasses = kQRows / 64;
     const int ahead_first = first_slot + kKeyRows >= RT ? first_slot + kKeyRows - RT : first_slot + kKeyRows;   // look-ahead chunk
     const int base_main = (first_slot / p.T) * p.T, base_ahead = (ahead_first / p.T) * p.T;
-    int st[kPasses];
+    int st[kPasses], pos[kPasses];
 #pragma unroll
     for (int i = 0; i < kPasses; ++i) {
-      const int j = i * 16 + g;
-      st[i] = __ldg(stk + (j < kKeyRows ? first_slot + j : ahead_first + (j - kKeyRows)));
+      const int r = i * 64 + g;
+      st[i] = __ldg(stk + (r < kKeyRows ? first_slot + r : ahead_first + (r - kKeyRows)));
     }
-    int pos[kPasses];
-#pragma unroll
-    for (int i = 0; i < kPasses; ++i) pos[i] = st[i] - ((i * 16 + g) < kKeyRows ? base_main : base_ahead);
     const int64_t head_off = static_cast<int64_t>(h) * kBDh + c * 8;
 #pragma unroll
     for (int i = 0; i < kPasses; ++i) {
-      const int j = i * 16 + g;
+      const int r = i * 64 + g;
+      pos[i] = st[i] - (r < kKeyRows ? base_main : base_ahead);
       const int64_t tok = static_cast<int64_t>(b) * p.T + pos[i];
-      const uint32_t so = sw128_offset(j, c);
+      const uint32_t so = sw128_offset(r, c);
       cp_async16(sX + so, p.qk + tok * p.ld + head_off);
       cp_async16(sDO + so, p.dout + tok * p.ld_do + head_off);
-      if (j < kKeyRows) cp_async16(sV + so, p.v + tok * p.ld + head_off);
+      if (r < kKeyRows) cp_async16(sV + so, p.v + tok * p.ld + head_off);
     }
     cp_async_commit();
+    RTTS_BSTAMP(1);
     if (c == 0) {
-      float lse_v[kPasses], delta_v[kPasses];
-      uint8_t valid[kPasses];
 #pragma unroll
       for (int i = 0; i < kPasses; ++i) {
+        const int r = i * 64 + g;
         const int64_t sidx = static_cast<int64_t>(row_bh) * p.T + pos[i];
-        lse_v[i] = __ldg(p.lse + sidx);
-        delta_v[i] = __ldg(p.delta + sidx);
-        valid[i] = p.mask != nullptr ? __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos[i]) : uint8_t(1);
-      }
-#pragma unroll
-      for (int i = 0; i < kPasses; ++i) {
-        const int j = i * 16 + g;
-        const int enc = valid[i] ? pos[i] : (pos[i] | kBPadFlag);
+        const float lse_v = __ldg(p.lse + sidx), delta_v = __ldg(p.delta + sidx);
+        const bool valid = p.mask == nullptr || __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos[i]) != 0;
+        const int enc = valid ? pos[i] : (pos[i] | kBPadFlag);
         int limit = p.causal ? pos[i] : (kBPadFlag - 1);
-        if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && !valid[i]) limit = -1;
-        q_meta[j] = make_int2(enc, limit);
-        q_stat[j] = make_float2(lse_v[i] * kBLog2e, delta_v[i]);
-        q_slot[j] = st[i];
+        if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && !valid) limit = -1;
+        q_meta[r] = make_int2(enc, limit);
+        q_stat[r] = make_float2(lse_v * kBLog2e, delta_v);
+        q_slot[r] = st[i];
+        if (r < kKeyRows) {
+          const float ss = __ldg(p.sumsq + sidx);
+          k_inv[r] = p.key_norm == RTTS_KEYNORM_L2 ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : rsqrtf(ss * (1.f / kBDh) + 1e-6f) * 0.125f;
+        }
       }
     }
+    RTTS_BSTAMP(2);
     cp_async_wait<0>();
   }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
   __syncthreads();
+  tc_fence_after_sync();
+  RTTS_BSTAMP(3);
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 
-  // ---- this thread's key row: 1/|k| and position ---------------------------------------------------------------
-  const int j = tid;
-  float inv;
-  {
-    float ss = 0.f;
+  // descriptor bases (K-major: lbo 16; MN-major: lbo 0 or one block); a k-step / block offset is an add on the address field
+  const uint64_t dX_k = umma_desc_sw128(sX, 16, 1024), dV_k = umma_desc_sw128(sV, 16, 1024), dDO_k = umma_desc_sw128(sDO, 16, 1024);
+  const uint64_t dPT_k = umma_desc_sw128(sPT, 16, 1024), dDS_k = umma_desc_sw128(sDS, 16, 1024);
+  const uint64_t dDO_n = umma_desc_sw128(sDO, 0, 1024), dX_n = umma_desc_sw128(sX, 0, 1024), dDS_n = umma_desc_sw128(sDS, kBlk, 1024);
+  // issue St / dPt of query block qb into TMEM buffer qb & 1 (one thread)
+  auto issue_scores = [&](int qb) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, false, false);
+    const uint32_t cs_ = (qb & 1) ? cS1 : cS0, cdp_ = (qb & 1) ? cDP1 : cDP0;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 u = *reinterpret_cast<const uint4*>(smem + L::kOffX + sw128_offset(j, c));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int k = 0; k < 4; ++k)
+      umma_ss(tmem + cs_, dX_k + (k * 32 >> 4), dX_k + ((qb * 8192 + k * 32) >> 4), idesc, k > 0);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
-        ss = fmaf(lo, lo, ss);
-        ss = fmaf(hi, hi, ss);
-      }
-    }
-    if (p.key_norm == RTTS_KEYNORM_L2) inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-    else inv = rsqrtf(ss * (1.f / kBDh) + 1e-6f) * 0.125f;
+    for (int k = 0; k < 4; ++k)
+      umma_ss(tmem + cdp_, dV_k + (k * 32 >> 4), dDO_k + ((qb * 8192 + k * 32) >> 4), idesc, k > 0);
+    umma_commit(bar_s + (qb & 1));
+  };
+  if (tid == 0) {
+    issue_scores(0);
+    issue_scores(1);
   }
+
+  // this thread's key row
+  const float inv = k_inv[j];
   const float cs = inv * p.score_scale * kBLog2e;   // score scale in log2 units
   const float gs = inv * p.score_scale;             // folded into dSt so one tile serves dQ and G
   const int k_enc = q_meta[j].x;
   const int k_chunk = j / BUCKET;                   // 0|1 for bucket 64, 0 for bucket 128
   const float mv = p.mask_value_log2, sv = p.self_value_log2;
-
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  uint32_t phase = 0;
+  const int col0 = wg * 16;                         // this thread's 16 query columns inside a block
 
 #pragma unroll 1
   for (int qb = 0; qb < kQBlocks; ++qb) {
-    if (tid == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, false, false);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_ss(tmem + cS, umma_desc_sw128(sX + k * 32, 16, 1024), umma_desc_sw128(sX + qb * 8192 + k * 32, 16, 1024), idesc, k > 0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_ss(tmem + cDP, umma_desc_sw128(sV + k * 32, 16, 1024), umma_desc_sw128(sDO + qb * 8192 + k * 32, 16, 1024), idesc, k > 0);
-      umma_commit(bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
+    mbar_wait(bar_s + (qb & 1), (qb >> 1) & 1);
     tc_fence_after_sync();
-
+    RTTS_BSTAMP(4 + qb * 3);
+    const uint32_t cs_ = (qb & 1) ? cS1 : cS0, cdp_ = (qb & 1) ? cDP1 : cDP0;
     // which query chunk is this block, and does it see this thread's key chunk?
     const int q_chunk = (qb * 64) / BUCKET;
     const bool pair_live = (q_chunk == k_chunk) || (q_chunk == k_chunk + 1);
-    uint8_t* pt_row = smem + L::kOffPT + qb * kBlk;
-    uint8_t* ds_row = smem + L::kOffDS + qb * kBlk;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      uint32_t rs[32], rp[32];
-      tmem_ld32(t_row + cS + half * 32, rs);
-      tmem_ld32(t_row + cDP + half * 32, rp);
-      tmem_ld_wait();
-      float pe[32], de[32];
-      int2 qmv[32];
-      float2 qsv[32];
+    {
+      uint32_t rs[16], rp[16];
+      tmem_ld16(t_row + cs_ + col0, rs);
+      tmem_ld16(t_row + cdp_ + col0, rp);
+      int2 qmv[16];
+      float2 qsv[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {     // 16-byte broadcast loads of two columns' metadata at a time
-        *reinterpret_cast<int4*>(qmv + 2 * i) = *reinterpret_cast<const int4*>(q_meta + qb * 64 + half * 32 + 2 * i);
-        *reinterpret_cast<float4*>(qsv + 2 * i) = *reinterpret_cast<const float4*>(q_stat + qb * 64 + half * 32 + 2 * i);
+      for (int i = 0; i < 8; ++i) {     // 16-byte broadcast loads of two columns' metadata at a time
+        *reinterpret_cast<int4*>(qmv + 2 * i) = *reinterpret_cast<const int4*>(q_meta + qb * 64 + col0 + 2 * i);
+        *reinterpret_cast<float4*>(qsv + 2 * i) = *reinterpret_cast<const float4*>(q_stat + qb * 64 + col0 + 2 * i);
       }
+      tmem_ld_wait();
+      float pe[16], de[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < 16; ++i) {
         const int2 qm = qmv[i];
         const float2 qs = qsv[i];
         const bool masked = k_enc > qm.y;
@@ -235,123 +237,124 @@ __global__ void __launch_bounds__(128) lsh_attn_bwd_kernel(const AttnBwdParams p
         pe[i] = pr;
         de[i] = (masked || self) ? 0.f : pr * (__uint_as_float(rp[i]) - qs.y) * gs;
       }
+      uint8_t* pt_row = smem + L::kOffPT + qb * kBlk;
+      uint8_t* ds_row = smem + L::kOffDS + qb * kBlk;
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
+      for (int q2 = 0; q2 < 2; ++q2) {
         uint4 u, w;
-        u.x = pack_bf16(pe[q4 * 8 + 0], pe[q4 * 8 + 1]); u.y = pack_bf16(pe[q4 * 8 + 2], pe[q4 * 8 + 3]);
-        u.z = pack_bf16(pe[q4 * 8 + 4], pe[q4 * 8 + 5]); u.w = pack_bf16(pe[q4 * 8 + 6], pe[q4 * 8 + 7]);
-        w.x = pack_bf16(de[q4 * 8 + 0], de[q4 * 8 + 1]); w.y = pack_bf16(de[q4 * 8 + 2], de[q4 * 8 + 3]);
-        w.z = pack_bf16(de[q4 * 8 + 4], de[q4 * 8 + 5]); w.w = pack_bf16(de[q4 * 8 + 6], de[q4 * 8 + 7]);
-        const uint32_t off = sw128_offset(j, half * 4 + q4);
+        u.x = pack_bf16(pe[q2 * 8 + 0], pe[q2 * 8 + 1]); u.y = pack_bf16(pe[q2 * 8 + 2], pe[q2 * 8 + 3]);
+        u.z = pack_bf16(pe[q2 * 8 + 4], pe[q2 * 8 + 5]); u.w = pack_bf16(pe[q2 * 8 + 6], pe[q2 * 8 + 7]);
+        w.x = pack_bf16(de[q2 * 8 + 0], de[q2 * 8 + 1]); w.y = pack_bf16(de[q2 * 8 + 2], de[q2 * 8 + 3]);
+        w.z = pack_bf16(de[q2 * 8 + 4], de[q2 * 8 + 5]); w.w = pack_bf16(de[q2 * 8 + 6], de[q2 * 8 + 7]);
+        const uint32_t off = sw128_offset(j, wg * 2 + q2);
         *reinterpret_cast<uint4*>(pt_row + off) = u;
         *reinterpret_cast<uint4*>(ds_row + off) = w;
       }
     }
+    RTTS_BSTAMP(5 + qb * 3);
     fence_proxy_async_smem();
     tc_fence_before_sync();
-    __syncthreads();
+    __syncthreads();          // Pt / dSt of this block complete; this block's (St, dPt) buffer fully consumed
     tc_fence_after_sync();
 
     if (tid == 0) {
       constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, false, true);   // A K-major, B MN-major
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_ss(tmem + cDV, umma_desc_sw128(sPT + qb * kBlk + k * 32, 16, 1024),
-                umma_desc_sw128(sDO + qb * 8192 + k * 2048, 0, 1024), idesc_kn, (qb | k) != 0);
+        umma_ss(tmem + cDV, dPT_k + ((qb * kBlk + k * 32) >> 4), dDO_n + ((qb * 8192 + k * 2048) >> 4), idesc_kn, (qb | k) != 0);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_ss(tmem + cG, umma_desc_sw128(sDS + qb * kBlk + k * 32, 16, 1024),
-                umma_desc_sw128(sX + qb * 8192 + k * 2048, 0, 1024), idesc_kn, (qb | k) != 0);
+        umma_ss(tmem + cG, dDS_k + ((qb * kBlk + k * 32) >> 4), dX_n + ((qb * 8192 + k * 2048) >> 4), idesc_kn, (qb | k) != 0);
       if ((qb & 1) || qb == kQBlocks - 1) {
         // dQ for query rows [pair*128, +128): A = dSt blocks (pair*2, pair*2+1) read MN-major (M = queries)
         constexpr uint32_t idesc_nn = umma_idesc_bf16(128, 64, true, true);
         const int pair = qb >> 1;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_ss(tmem + (pair ? cDQ1 : cDQ0), umma_desc_sw128(sDS + pair * 2 * kBlk + k * 2048, kBlk, 1024),
-                  umma_desc_sw128(sX + k * 2048, 0, 1024), idesc_nn, k > 0);
+          umma_ss(tmem + (pair ? cDQ1 : cDQ0), dDS_n + ((pair * 2 * kBlk + k * 2048) >> 4), dX_n + (k * 2048 >> 4), idesc_nn, k > 0);
       }
+      if (qb + 2 < kQBlocks) issue_scores(qb + 2);     // refill the buffer that was just consumed
     }
+    RTTS_BSTAMP(6 + qb * 3);
   }
-  if (tid == 0) umma_commit(bar);
-  mbar_wait(bar, phase);
+  if (tid == 0) umma_commit(bar_acc);
+  mbar_wait(bar_acc, 0);
   tc_fence_after_sync();
+  RTTS_BSTAMP(20);
 
-  // ---- epilogue ---------------------------------------------------------------------------------------------------
+  // ---- epilogue: warpgroup g handles output columns [16g, 16g+16) of every accumulator row ------------------------------------
   const int64_t out_base = static_cast<int64_t>(row_bh) * RT;
+  const int64_t my_row = (out_base + q_slot[j]) * kBDh + col0;
   {
-    // dV row j and dx row j (key-normalisation Jacobian applied to G)
-    float g[64];
-    float4* dv_dst = reinterpret_cast<float4*>(p.dv + (out_base + q_slot[j]) * kBDh);
+    uint32_t r[16];
+    tmem_ld16(t_row + cDV + col0, r);
+    tmem_ld_wait();
+    uint4* dst = reinterpret_cast<uint4*>(p.dv + my_row);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t r[32];
-      tmem_ld32(t_row + cDV + half * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        dv_dst[half * 8 + q] = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
-                                           __uint_as_float(r[q * 4 + 3]));
-    }
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t r[32];
-      tmem_ld32(t_row + cG + half * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) g[half * 32 + i] = __uint_as_float(r[i]);
-    }
-    float x[64];
+    for (int q = 0; q < 2; ++q)
+      dst[q] = make_uint4(pack_bf16(__uint_as_float(r[q * 8]), __uint_as_float(r[q * 8 + 1])), pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3])),
+                          pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5])), pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7])));
+  }
+  float g[16], x[16];
+  {
+    uint32_t r[16];
+    tmem_ld16(t_row + cG + col0, r);
+    tmem_ld_wait();
     float dot = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint4 u = *reinterpret_cast<const uint4*>(smem + L::kOffX + sw128_offset(j, c));
+    for (int c = 0; c < 2; ++c) {
+      const uint4 u = *reinterpret_cast<const uint4*>(smem + L::kOffX + sw128_offset(j, wg * 2 + c));
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         x[c * 8 + 2 * e] = bf16_lo(w[e]);
         x[c * 8 + 2 * e + 1] = bf16_hi(w[e]);
-        dot = fmaf(x[c * 8 + 2 * e], g[c * 8 + 2 * e], dot);
-        dot = fmaf(x[c * 8 + 2 * e + 1], g[c * 8 + 2 * e + 1], dot);
       }
     }
-    const float coef = inv * inv * dot;   // dh == 64: the L2 and the RMS/sqrt(dh) norms share |k|^-2 = inv^2
-    // this slot's query-role gradient from the keys of this CTA (accumulator 0, row j) is added in registers
-    float4* dst = reinterpret_cast<float4*>(p.dqk_main + (out_base + q_slot[j]) * kBDh);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t r[32];
-      tmem_ld32(t_row + cDQ0 + half * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int e = half * 32 + q * 4;
-        dst[half * 8 + q] = make_float4(__uint_as_float(r[q * 4]) + g[e] - x[e] * coef, __uint_as_float(r[q * 4 + 1]) + g[e + 1] - x[e + 1] * coef,
-                                        __uint_as_float(r[q * 4 + 2]) + g[e + 2] - x[e + 2] * coef, __uint_as_float(r[q * 4 + 3]) + g[e + 3] - x[e + 3] * coef);
-      }
+    for (int i = 0; i < 16; ++i) {
+      g[i] = __uint_as_float(r[i]);
+      dot = fmaf(x[i], g[i], dot);
     }
+    dot_part[wg * kKeyRows + j] = dot;
+  }
+  __syncthreads();
+  {
+    // key-normalisation Jacobian dx = G - x |k|^-2 <x, G>  (dh == 64: the L2 and the RMS/sqrt(dh) norms share |k|^-2 = inv^2),
+    // plus this slot's query-role gradient from the keys of this CTA (accumulator 0, row j)
+    const float coef = inv * inv * (dot_part[j] + dot_part[kKeyRows + j] + dot_part[2 * kKeyRows + j] + dot_part[3 * kKeyRows + j]);
+    uint32_t r[16];
+    tmem_ld16(t_row + cDQ0 + col0, r);
+    tmem_ld_wait();
+    float o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]) + g[i] - x[i] * coef;
+    uint4* dst = reinterpret_cast<uint4*>(p.dqk_main + my_row);
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      dst[q] = make_uint4(pack_bf16(o[q * 8], o[q * 8 + 1]), pack_bf16(o[q * 8 + 2], o[q * 8 + 3]), pack_bf16(o[q * 8 + 4], o[q * 8 + 5]),
+                          pack_bf16(o[q * 8 + 6], o[q * 8 + 7]));
   }
   {
     // accumulator 1 = query rows 128.. (the look-ahead chunk, BUCKET rows) -> dq_b.
     // every warp must execute the (warp-collective) TMEM loads; only rows < BUCKET are stored
     const bool live = j < BUCKET;
-    float4* dst_b = reinterpret_cast<float4*>(p.dq_b + (out_base + q_slot[live ? kKeyRows + j : 0]) * kBDh);
+    uint32_t r[16];
+    tmem_ld16(t_row + cDQ1 + col0, r);
+    tmem_ld_wait();
+    if (live) {
+      uint4* dst_b = reinterpret_cast<uint4*>(p.dq_b + (out_base + q_slot[kKeyRows + j]) * kBDh + col0);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t r[32];
-      tmem_ld32(t_row + cDQ1 + half * 32, r);
-      tmem_ld_wait();
-      if (live) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          dst_b[half * 8 + q] = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
-                                            __uint_as_float(r[q * 4 + 3]));
-      }
+      for (int q = 0; q < 2; ++q)
+        dst_b[q] = make_uint4(pack_bf16(__uint_as_float(r[q * 8]), __uint_as_float(r[q * 8 + 1])), pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3])),
+                              pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5])), pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7])));
     }
   }
+  RTTS_BSTAMP(21);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+  RTTS_BSTAMP(22);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -359,39 +362,36 @@ __global__ void __launch_bounds__(128) lsh_attn_bwd_kernel(const AttnBwdParams p
 // dq_b is written for every slot when bucket == 128, and only for slots in even chunks when bucket == 64
 // (the chunk index comes from `undo`).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lsh_grad_reduce_kernel(const float* __restrict__ dqk_main, const float* __restrict__ dq_b,
-                                                              const float* __restrict__ dvr,
-                                                              const int32_t* __restrict__ undo, __nv_bfloat16* __restrict__ dqk,
-                                                              __nv_bfloat16* __restrict__ dv, int64_t ld, int T, int H, int R,
+__global__ void __launch_bounds__(256) lsh_grad_reduce_kernel(const __nv_bfloat16* __restrict__ dqk_main, const __nv_bfloat16* __restrict__ dq_b,
+                                                              const __nv_bfloat16* __restrict__ dvr, const int32_t* __restrict__ undo,
+                                                              __nv_bfloat16* __restrict__ dqk, __nv_bfloat16* __restrict__ dv, int64_t ld, int T, int H, int R,
                                                               int bucket, int64_t rows) {
-  const int64_t row = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) >> 4;   // (b*H + h)*T + t
-  const int c = threadIdx.x & 15;
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) >> 3;   // (b*H + h)*T + t
+  const int c = threadIdx.x & 7;
   if (row >= rows) return;
   const int64_t bh = row / T;
   const int t = static_cast<int>(row - bh * T);
-  float4 aq = make_float4(0, 0, 0, 0), av = make_float4(0, 0, 0, 0);
+  float aq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, av[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto add8 = [](float* acc, const uint4 u) {
+    acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+    acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+  };
   for (int r = 0; r < R; ++r) {
     const int64_t idx = (bh * R + r) * T + t;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(dqk_main + idx * kBDh) + c);
-    const float4 w = __ldg(reinterpret_cast<const float4*>(dvr + idx * kBDh) + c);
-    aq.x += a.x; aq.y += a.y; aq.z += a.z; aq.w += a.w;
-    av.x += w.x; av.y += w.y; av.z += w.z; av.w += w.w;
+    add8(aq, __ldg(reinterpret_cast<const uint4*>(dqk_main + idx * kBDh) + c));
+    add8(av, __ldg(reinterpret_cast<const uint4*>(dvr + idx * kBDh) + c));
     bool has_b = true;
     if (bucket == 64) has_b = ((__ldg(undo + idx) >> 6) & 1) == 0;
-    if (has_b) {
-      const float4 bq = __ldg(reinterpret_cast<const float4*>(dq_b + idx * kBDh) + c);
-      aq.x += bq.x; aq.y += bq.y; aq.z += bq.z; aq.w += bq.w;
-    }
+    if (has_b) add8(aq, __ldg(reinterpret_cast<const uint4*>(dq_b + idx * kBDh) + c));
   }
   const int64_t b = bh / H;
   const int h = static_cast<int>(bh - b * H);
-  const int64_t o = (b * T + t) * ld + h * kBDh + c * 4;
-  uint2 u;
-  u.x = pack_bf16(aq.x, aq.y); u.y = pack_bf16(aq.z, aq.w);
-  *reinterpret_cast<uint2*>(dqk + o) = u;
-  u.x = pack_bf16(av.x, av.y); u.y = pack_bf16(av.z, av.w);
-  *reinterpret_cast<uint2*>(dv + o) = u;
+  const int64_t o = (b * T + t) * ld + h * kBDh + c * 8;
+  *reinterpret_cast<uint4*>(dqk + o) = make_uint4(pack_bf16(aq[0], aq[1]), pack_bf16(aq[2], aq[3]), pack_bf16(aq[4], aq[5]), pack_bf16(aq[6], aq[7]));
+  *reinterpret_cast<uint4*>(dv + o) = make_uint4(pack_bf16(av[0], av[1]), pack_bf16(av[2], av[3]), pack_bf16(av[4], av[5]), pack_bf16(av[6], av[7]));
 }
+
+static long long* g_bwd_trace = nullptr;   // debug only (rtts_debug_set_bwd_trace)
 
 template <int BUCKET>
 int launch_attn_bwd(const AttnBwdParams& p, int ctas, cudaStream_t stream) {
@@ -402,7 +402,7 @@ int launch_attn_bwd(const AttnBwdParams& p, int ctas, cudaStream_t stream) {
     if (e != cudaSuccess) return fail(kErrCuda, "rtts_lsh_attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  lsh_attn_bwd_kernel<BUCKET><<<ctas, 128, L::kDynamic, stream>>>(p);
+  lsh_attn_bwd_kernel<BUCKET><<<ctas, kBwdThreads, L::kDynamic, stream>>>(p);
   return check_launch("rtts_lsh_attn_bwd");
 }
 
@@ -411,8 +411,8 @@ int launch_attn_bwd(const AttnBwdParams& p, int ctas, cudaStream_t stream) {
 using namespace rtts;
 
 extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, const int32_t* sticker, const float* sumsq, const uint8_t* mask,
-                                 const rtts_lsh_spec* spec, const void* dout, int64_t ld_dout, const float* lse, const float* delta, float* dqk_main,
-                                 float* dq_b, float* dv_rounds, int B, int T, int H, int dh, int R, int bucket,
+                                 const rtts_lsh_spec* spec, const void* dout, int64_t ld_dout, const float* lse, const float* delta, void* dqk_main,
+                                 void* dq_b, void* dv_rounds, int B, int T, int H, int dh, int R, int bucket,
                                  void* stream) {
   RTTS_REQUIRE(qk && v && sticker && sumsq && spec && dout && lse && delta && dqk_main && dq_b && dv_rounds, "rtts_lsh_attn_bwd: null pointer");
   RTTS_REQUIRE(dh == kBDh, "rtts_lsh_attn_bwd: head size %d unsupported (64 only)", dh);
@@ -425,7 +425,8 @@ extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, cons
   p.v = static_cast<const __nv_bfloat16*>(v);
   p.dout = static_cast<const __nv_bfloat16*>(dout);
   p.ld = ld; p.ld_do = ld_dout; p.sticker = sticker; p.sumsq = sumsq; p.mask = mask; p.lse = lse; p.delta = delta;
-  p.dqk_main = dqk_main; p.dq_b = dq_b; p.dv = dv_rounds;
+  p.dqk_main = static_cast<__nv_bfloat16*>(dqk_main); p.dq_b = static_cast<__nv_bfloat16*>(dq_b); p.dv = static_cast<__nv_bfloat16*>(dv_rounds);
+  p.trace = g_bwd_trace;
   p.T = T; p.H = H; p.R = R; p.tiles_per_row = R * T / kKeyRows;
   p.score_scale = spec->score_scale;
   p.mask_value_log2 = fmaxf(spec->mask_value * kBLog2e, -3.0e38f);
@@ -437,14 +438,17 @@ extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, cons
   return bucket == 64 ? launch_attn_bwd<64>(p, static_cast<int>(ctas), s) : launch_attn_bwd<128>(p, static_cast<int>(ctas), s);
 }
 
-extern "C" int rtts_lsh_grad_reduce(const float* dqk_main, const float* dq_b, const float* dv_rounds, const int32_t* undo, void* dqk, void* dv, int64_t ld, int B, int T, int H, int dh, int R,
+extern "C" int rtts_lsh_grad_reduce(const void* dqk_main, const void* dq_b, const void* dv_rounds, const int32_t* undo, void* dqk, void* dv, int64_t ld, int B, int T, int H, int dh, int R,
                                     int bucket, void* stream) {
   RTTS_REQUIRE(dqk_main && dq_b && dv_rounds && dqk && dv, "rtts_lsh_grad_reduce: null pointer");
   RTTS_REQUIRE(dh == kBDh && ld % 8 == 0, "rtts_lsh_grad_reduce: head size 64 and 16-byte rows required");
   RTTS_REQUIRE(bucket == 128 || (bucket == 64 && undo), "rtts_lsh_grad_reduce: bucket 64 needs undo");
   const int64_t rows = static_cast<int64_t>(B) * H * T;
-  const int64_t blocks = (rows * 16 + 255) / 256;
+  const int64_t blocks = (rows * 8 + 255) / 256;
   lsh_grad_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dqk_main, dq_b, dv_rounds, undo, static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), ld, T, H, R, bucket, rows);
+      static_cast<const __nv_bfloat16*>(dqk_main), static_cast<const __nv_bfloat16*>(dq_b), static_cast<const __nv_bfloat16*>(dv_rounds), undo, static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), ld, T, H, R, bucket, rows);
   return check_launch("rtts_lsh_grad_reduce");
 }
+
+// Debug hook (not part of the product ABI): device buffer of 32 int64 receiving clock64 stamps of CTA 0, thread 0.
+extern "C" void rtts_debug_set_bwd_trace(void* device_buffer) { g_bwd_trace = static_cast<long long*>(device_buffer); }

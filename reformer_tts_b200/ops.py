@@ -229,8 +229,8 @@ def lsh_attn_bwd(qk, v, sticker, undo, mask, spec: LSHSpec, dout, lse, delta, n_
     if sumsq is None:
         sumsq = lsh_sumsq(qk, n_heads)
     _check(sumsq, torch.float32, "sumsq")
-    # fp32 per-round partials [3, B,H,R,T,dh]: dqk_main, dq_b, dv
-    part = torch.empty((3, b, n_heads, n_rounds, t, dh), dtype=torch.float32, device=qk.device)
+    # bf16 per-round partials [3, B,H,R,T,dh]: dqk_main, dq_b, dv (summed over rounds in fp32 by the reduce kernel)
+    part = torch.empty((3, b, n_heads, n_rounds, t, dh), dtype=torch.bfloat16, device=qk.device)
     st = spec.struct()
     _launch(_tag("lsh_attn_bwd", locals()), "rtts_lsh_attn_bwd", _ptr(qk), _ptr(v), ld, _ptr(sticker), _ptr(sumsq), _ptr(mask), ctypes.byref(st), _ptr(dout), ld_do,
               _ptr(lse), _ptr(delta), _ptr(part[0]), _ptr(part[1]), _ptr(part[2]), b, t, n_heads, dh, n_rounds,

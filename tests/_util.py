@@ -8,6 +8,9 @@ TOL_FP32 = 1e-3     # relative L2 error of anything accumulated and STORED in fp
 # the storage rounding of bf16 (8 significant bits): relative L2 error 2^-9/sqrt(3) = 1.1e-3 per rounding.  Such tensors are
 # compared with the oracle at 3e-3 (two to three roundings in the chain: P, the stored result, and the bf16 gradient operand).
 TOL_BF16_STORED = 3e-3
+# Gradients of the attention core go through four bf16 hops (P~, dS, the per-round partial sums that are written to HBM in bf16 and
+# summed over rounds in fp32, and the final bf16 operand of the projection-gradient GEMM): 4e-3 (measured 2.6e-3 .. 3.1e-3 on N(0,1) data).
+TOL_BF16_GRAD = 4e-3
 
 
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
