@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_kernel(const __grid_co
       } else if (epi & RTTS_EPI_ATOMIC) {
         float* dst = static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(dst + i, r[i]);
+        for (int i = 0; i < 32; i += 4)      // 16-byte vector reduction (sm_90+): a quarter of the atomic instructions
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(r[i]), "f"(r[i + 1]), "f"(r[i + 2]), "f"(r[i + 3]) : "memory");
       } else {
         float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col);
 #pragma unroll

@@ -34,7 +34,7 @@ class _LNFeedForwardFn(torch.autograd.Function):
         rows, d = x2.shape
         f = hid.shape[1]
         dev = x2.device
-        sk = _split_k(rows)
+        sk = _split_k(rows, (d // 128) * (f // 128))
         g_b2 = torch.zeros(d, dtype=torch.float32, device=dev)
         dyb = ops.cast_bf16_colsum(dy.reshape(rows, d), g_b2)
         g_w2 = torch.zeros((d, f), dtype=torch.float32, device=dev)

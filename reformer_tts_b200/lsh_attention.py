@@ -84,7 +84,7 @@ class _LSHAttentionFn(torch.autograd.Function):
             g_bout = torch.zeros(d, dtype=torch.float32, device=dev)
             dyb = ops.cast_bf16_colsum(dy2, g_bout)
             g_wout = torch.zeros((d, d), dtype=torch.float32, device=dev)
-            ops.gemm(dyb, out.view(b * t, d), a_mn_major=True, b_mn_major=True, out=g_wout, accumulate=True, split_k=_split_k(b * t))
+            ops.gemm(dyb, out.view(b * t, d), a_mn_major=True, b_mn_major=True, out=g_wout, accumulate=True, split_k=_split_k(b * t, (d // 128) ** 2))
             dout = ops.gemm(dyb, wout_bf16, b_mn_major=True, out_dtype=torch.bfloat16).view(b, t, d)
         else:
             dout = ops.cast_bf16_colsum(dy2).view(b, t, d)
@@ -94,7 +94,7 @@ class _LSHAttentionFn(torch.autograd.Function):
         ops.lsh_attn_bwd(qk, v, sticker, undo, mask_u8, spec, dout, lse, delta, h, r, bucket, out_dqk=dqkv[..., :d], out_dv=dqkv[..., d:], sumsq=sumsq)
         dqkv2 = dqkv.view(b * t, 2 * d)
         g_wqkv = torch.zeros((2 * d, d), dtype=torch.float32, device=dev)
-        ops.gemm(dqkv2, xn, a_mn_major=True, b_mn_major=True, out=g_wqkv, accumulate=True, split_k=_split_k(b * t))
+        ops.gemm(dqkv2, xn, a_mn_major=True, b_mn_major=True, out=g_wqkv, accumulate=True, split_k=_split_k(b * t, 2 * (d // 128) ** 2))
         dxn = ops.gemm(dqkv2, wqkv_bf16, b_mn_major=True)
         g_lnw = g_lnb = None
         if ctx.has_ln:
@@ -106,12 +106,17 @@ class _LSHAttentionFn(torch.autograd.Function):
         return dx, g_lnw, g_lnb, g_wqkv[:d], g_wqkv[d:], g_wout, g_bout, None, None, None, None, None
 
 
-def _split_k(tokens: int) -> int:
-    """Split factor for the weight-gradient GEMMs (K = tokens): enough CTAs to fill 148 SMs."""
-    for s in (32, 16, 8, 4, 2):
-        if tokens % (64 * s) == 0 and tokens // s >= 256:
-            return s
-    return 1
+def _split_k(tokens: int, out_tiles: int = 64) -> int:
+    """Split factor for the weight-gradient GEMMs (K = tokens, ``out_tiles`` 128x128 output tiles): about two CTAs per SM, and
+    as few splits as that allows - every split adds an fp32 atomic pass over the output."""
+    kb = tokens // 64
+    best = 1
+    for s in (1, 2, 4, 5, 8, 10, 16, 20, 32, 40):
+        if kb % s == 0 and kb // s >= 4:
+            best = s
+            if s * out_tiles >= 256:
+                break
+    return best
 
 
 class _LSHBase(nn.Module):

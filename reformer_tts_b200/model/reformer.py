@@ -79,23 +79,48 @@ class LSHSelfAttentionWrapper(nn.Module):
 
 
 class MultiheadAttentionWrapper(nn.Module):
-    """Decoder-to-encoder attention (ref:...reformer.py:161-186): stock ``nn.MultiheadAttention`` with the argument
-    order the reversible blocks need.  Outside the hot-path scope, kept on library kernels."""
+    """Decoder-to-encoder attention (ref:...reformer.py:161-186): ``nn.MultiheadAttention`` parameters (state-dict keys
+    ``layer.in_proj_weight`` ... ``layer.out_proj.bias``) with the argument order the reversible blocks need.  Outside the hot-path
+    scope and kept on library kernels.  In training the attention weights are never read
+    (ref:...reformer.py:183-184 appends them only in eval), so the training path skips materialising them: batch-first projections and
+    ``scaled_dot_product_attention`` under bf16 autocast (same operand precision as the rest of the step); eval keeps the stock
+    module call and returns the weights."""
 
     def __init__(self, dim: int, attention_matrices: Optional[List[torch.Tensor]] = None, **kwargs):
         super().__init__()
         self.layer = nn.MultiheadAttention(dim, **kwargs)
         self.attention_matrices_ = attention_matrices
 
+    def _fast_path_ok(self, query, extra) -> bool:
+        layer = self.layer
+        return (self.training and query.is_cuda and layer._qkv_same_embed_dim and layer.in_proj_bias is not None and layer.bias_k is None
+                and not layer.add_zero_attn and set(extra) <= {"key_padding_mask"})
+
     def forward(self, query, **kwargs):
         if "key" not in kwargs:
             raise AssertionError("forward expects keyword argument 'key'")
-        memory = kwargs["key"].transpose(0, 1)
         extra = {k: v for k, v in kwargs.items() if k not in ("key", "value")}
+        if self._fast_path_ok(query, extra):
+            return self._forward_training(query, kwargs["key"], extra.get("key_padding_mask"))
+        memory = kwargs["key"].transpose(0, 1)
         out, weights = self.layer(query.transpose(0, 1), memory, memory, **extra)
         if not self.training and self.attention_matrices_ is not None:
             self.attention_matrices_.append(weights)
         return out.transpose(0, 1)
+
+    def _forward_training(self, query, memory, key_padding_mask):
+        layer = self.layer
+        b, t, d = query.shape
+        h = layer.num_heads
+        w, bias = layer.in_proj_weight, layer.in_proj_bias
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            q = nn.functional.linear(query, w[:d], bias[:d]).view(b, t, h, d // h).transpose(1, 2)
+            kv = nn.functional.linear(memory, w[d:], bias[d:]).view(b, memory.shape[1], 2, h, d // h)
+            k, v = kv[:, :, 0].transpose(1, 2), kv[:, :, 1].transpose(1, 2)
+            mask = None if key_padding_mask is None else ~key_padding_mask[:, None, None, :]
+            o = nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=layer.dropout)
+            out = layer.out_proj(o.transpose(1, 2).reshape(b, t, d))
+        return out.float()
 
 
 def _normed_ff(dim, ff_chunks, ff_kwargs):
