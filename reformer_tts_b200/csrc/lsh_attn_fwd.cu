@@ -38,6 +38,7 @@ struct AttnFwdParams {
   const uint8_t* mask;
   __nv_bfloat16* o_rounds;
   float* lse_rounds;
+  long long* trace;     // debug: per-role clock64 stamps of CTA 0 (nullable)
   int T, H, R;
   int tiles_per_row;  // R*T / 128
   float score_scale_log2;  // score_scale * log2(e)
@@ -85,6 +86,44 @@ struct AttnFwdSmem {
   static constexpr int kTotal = kOffTmem + 8;
   static constexpr int kDynamic = kTotal + 1024;                     // slack for manual 1024-B alignment
 };
+
+#define RTTS_STAMP(role, n, k) do { if (p.trace != nullptr && blockIdx.x == 0 && (n) < 32) p.trace[((role) * 32 + (n)) * 8 + (k)] = clock64(); } while (0)
+
+// One 32-column chunk of the single-pass softmax for one query row: scores r -> e = exp2(s * key_scale - bound), zero where the
+// key is masked (MASK) or is the query itself (SELF), accumulate the row sum, store the bf16 P chunk (4 x 16 B, swizzled).
+// a_pos / a_scale: shared addresses of key_pos / key_scale at this chunk's first column; a_p: shared address of P row m, k-block
+// of this chunk; c16: index of the chunk's first 16-byte column group inside that k-block; m7 = m & 7 (swizzle phase).
+template <bool MASK, bool SELF>
+__device__ __forceinline__ void soft_chunk(const uint32_t* r, uint32_t a_pos, uint32_t a_scale, uint32_t a_p, int c16, int m7, float neg_bound,
+                                           int q_limit, int q_enc, float* sum4) {
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const uint4 s0 = lds128(a_scale + q4 * 32), s1 = lds128(a_scale + q4 * 32 + 16);
+    const float ks[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
+                         __uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s1.w)};
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = exp2f(fmaf(__uint_as_float(r[q4 * 8 + i]), ks[i], neg_bound));
+    if (MASK || SELF) {
+      const uint4 p0 = lds128(a_pos + q4 * 32), p1 = lds128(a_pos + q4 * 32 + 16);
+      const int kp[8] = {static_cast<int>(p0.x), static_cast<int>(p0.y), static_cast<int>(p0.z), static_cast<int>(p0.w),
+                         static_cast<int>(p1.x), static_cast<int>(p1.y), static_cast<int>(p1.z), static_cast<int>(p1.w)};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (MASK) e[i] = kp[i] > q_limit ? 0.f : e[i];       // exp2(mask_value - m) == 0
+        if (SELF) e[i] = kp[i] == q_enc ? 0.f : e[i];        // exp2(self_value - m) == 0
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum4[i & 3] += e[i];
+    uint4 u;
+    u.x = pack_bf16(e[0], e[1]);
+    u.y = pack_bf16(e[2], e[3]);
+    u.z = pack_bf16(e[4], e[5]);
+    u.w = pack_bf16(e[6], e[7]);
+    sts128(a_p + (((c16 + q4) ^ m7) << 4), u);
+  }
+}
 
 template <int BUCKET>
 __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const AttnFwdParams p, const int num_tiles) {
@@ -138,6 +177,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
         const int g = m & 1, st = m % kStages;
         const uint32_t sP = smem_u32(smem + st * L::kStageBytes + L::kOffKP), sV = smem_u32(smem + st * L::kStageBytes + L::kOffV);
         mbar_wait(p_full + g, (m >> 1) & 1);
+        RTTS_STAMP(0, m, 2);
         if (!kAliasO) mbar_wait(o_free + g, ((m >> 1) & 1) ^ 1);      // epilogue of tile m-2 has drained O of this group
         tc_fence_after_sync();
 #pragma unroll
@@ -145,13 +185,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           umma_ss(tmem + g * 256 + kColO, umma_desc_sw128(sP + (j >> 2) * (kQRows * 128) + (j & 3) * 32, 16, 1024),
                   umma_desc_sw128(sV + j * 2048, 0, 1024), idesc_o, j > 0);
         umma_commit(o_full + g);
-        umma_commit(kv_free + st);      // the stage's K|P and V tiles are no longer read
+        umma_commit(kv_free + st);
+        RTTS_STAMP(0, m, 3);      // the stage's K|P and V tiles are no longer read
       };
       int n = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
         const int g = n & 1, st = n % kStages;
         const uint32_t sKP = smem_u32(smem + st * L::kStageBytes + L::kOffKP);
         mbar_wait(kv_full + st, (n / kStages) & 1);
+        RTTS_STAMP(0, n, 0);
         if (kAliasO) mbar_wait(o_free + g, ((n >> 1) & 1) ^ 1);       // S(n) overwrites O(n-2): its epilogue must be done
         tc_fence_after_sync();
         // S region of group g is free: PV(n-2) was issued (program order) after p_full(n-2), i.e. after the last read of S(n-2)
@@ -159,6 +201,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
         for (int k = 0; k < kDh / 16; ++k)
           umma_ss(tmem + g * 256, umma_desc_sw128(sKP + kQOff * 128 + k * 32, 16, 1024), umma_desc_sw128(sKP + k * 32, 16, 1024), idesc_s, k > 0);
         umma_commit(s_full + g);
+        RTTS_STAMP(0, n, 1);
         if (n > 0) issue_pv(n - 1);
       }
       if (n > 0) issue_pv(n - 1);
@@ -184,6 +227,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const int first_slot = t_in * kQRows - BUCKET;
       const int prev_first = first_slot < 0 ? first_slot + RT : first_slot;
       const int base_prev = (prev_first / p.T) * p.T, base_main = ((t_in * kQRows) / p.T) * p.T;
+      if (lt == 0) RTTS_STAMP(1, n, 0);
       int st[kPasses];
 #pragma unroll
       for (int i = 0; i < kPasses; ++i) {
@@ -201,7 +245,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           valid[i] = p.mask != nullptr ? __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos) : uint8_t(1);
         }
       }
+      if (lt == 0) RTTS_STAMP(1, n, 1);
       mbar_wait(kv_free + st_i, ((n / kStages) & 1) ^ 1);       // PV of the tile that used this stage has completed
+      if (lt == 0) RTTS_STAMP(1, n, 2);
       const __nv_bfloat16* qk_b = p.qk + static_cast<int64_t>(b) * p.T * p.ld + h * kDh + c * 8;
       const __nv_bfloat16* v_b = p.v + static_cast<int64_t>(b) * p.T * p.ld + h * kDh + c * 8;
 #pragma unroll
@@ -229,6 +275,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       cp_async_wait<0>();
       fence_proxy_async_smem();     // cp.async / st.shared data -> visible to the tensor-core (async) proxy
       mbar_arrive(kv_full + st_i);
+      if (lt == 0) RTTS_STAMP(1, n, 3);
     }
   } else {
     // ================================================= softmax groups =============================================
@@ -246,6 +293,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const int* key_pos = reinterpret_cast<const int*>(stage + L::kOffPos);
       uint8_t* p_row_base = stage + L::kOffKP;
       const int row_bh = tile / p.tiles_per_row;
+      if (m == 0) RTTS_STAMP(2, n, 0);
       mbar_wait(kv_full + st_i, (n / kStages) & 1);  // metadata of this stage is visible
       const int q_enc = key_pos[kQOff + m];
       int q_limit = p.causal ? (q_enc & ~kPadFlag) : (kPadFlag - 1);
@@ -256,40 +304,37 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const float row_bound = p.score_scale_log2 * p.score_scale_log2 / key_scale[kQOff + m] * 1.001f;
       mbar_wait(s_full + wg, ph);
       tc_fence_after_sync();
+      if (m == 0) RTTS_STAMP(2, n, 1);
 
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        // The query's own column sits in exactly one 32-column chunk per warp (warp-uniform); the same token can appear a second
+        // time only in the look-back chunk of the first tile of a hash round.  Only those chunks pay for the self comparison, and
+        // the position mask is skipped altogether when nothing can be masked (non-causal, no padding mask).
+        const bool need_mask = p.causal || p.mask != nullptr;
+        const int t_in_s = tile - row_bh * p.tiles_per_row;
+        const bool round_start = (t_in_s * kQRows) % p.T == 0;
+        const int diag_c0 = (kQOff + (m & ~31)) - win0;           // chunk holding columns of rows 32*(m/32) .. +31
+        const uint32_t a_pos0 = smem_u32(key_pos + win0), a_scale0 = smem_u32(key_scale + win0);
+        const uint32_t a_prow = smem_u32(p_row_base) + m * 128;
+        const int m7 = m & 7;
+        const float neg_bound = -row_bound;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kWin; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_row + win0 + c0, r);
-        float e[32];
-        int kp[32];
-        float ks[32];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {      // win0 + c0 is a multiple of 32: 16-byte aligned broadcast loads
-          *reinterpret_cast<int4*>(kp + 4 * i) = *reinterpret_cast<const int4*>(key_pos + win0 + c0 + 4 * i);
-          *reinterpret_cast<float4*>(ks + 4 * i) = *reinterpret_cast<const float4*>(key_scale + win0 + c0 + 4 * i);
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float ex = exp2f(fmaf(__uint_as_float(r[i]), ks[i], -row_bound));
-          e[i] = (kp[i] > q_limit || kp[i] == q_enc) ? 0.f : ex;       // exp2(mask_value - m) == exp2(self_value - m) == 0
-          sum4[i & 3] += e[i];
-        }
-        // keys win0+c0 .. +31 -> P tile k-block (col/64), 16-byte chunk (col%64)/8.  (Overwrites the K tile: S is complete.)
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int col = win0 + c0 + q4 * 8;
-          uint4 u;
-          u.x = pack_bf16(e[q4 * 8 + 0], e[q4 * 8 + 1]);
-          u.y = pack_bf16(e[q4 * 8 + 2], e[q4 * 8 + 3]);
-          u.z = pack_bf16(e[q4 * 8 + 4], e[q4 * 8 + 5]);
-          u.w = pack_bf16(e[q4 * 8 + 6], e[q4 * 8 + 7]);
-          *reinterpret_cast<uint4*>(p_row_base + (col >> 6) * (kQRows * 128) + sw128_offset(m, (col & 63) >> 3)) = u;
+        for (int c0 = 0; c0 < kWin; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + win0 + c0, r);
+          const int col = win0 + c0;
+          const uint32_t a_p = a_prow + (col >> 6) * (kQRows * 128);
+          const int c16 = (col & 63) >> 3;
+          const bool self_chunk = c0 == diag_c0 || (round_start && col < BUCKET);
+          tmem_ld_wait();
+          if (self_chunk) soft_chunk<true, true>(r, a_pos0 + c0 * 4, a_scale0 + c0 * 4, a_p, c16, m7, neg_bound, q_limit, q_enc, sum4);
+          else if (need_mask) soft_chunk<true, false>(r, a_pos0 + c0 * 4, a_scale0 + c0 * 4, a_p, c16, m7, neg_bound, q_limit, q_enc, sum4);
+          else soft_chunk<false, false>(r, a_pos0 + c0 * 4, a_scale0 + c0 * 4, a_p, c16, m7, neg_bound, q_limit, q_enc, sum4);
         }
       }
       float row_sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      if (m == 0) RTTS_STAMP(2, n, 5);
       float row_max = row_bound;
       bool redo = !(row_sum > 1e-30f);
       if (redo && row_bound < 60.f) {
@@ -381,9 +426,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       fence_proxy_async_smem();
       tc_fence_before_sync();       // this thread's TMEM reads of S precede the MMAs that overwrite the region
       mbar_arrive(p_full + wg);
+      if (m == 0) RTTS_STAMP(2, n, 2);
 
       mbar_wait(o_full + wg, ph);
       tc_fence_after_sync();
+      if (m == 0) RTTS_STAMP(2, n, 3);
       {
         const float inv_sum = 1.f / row_sum;
         const int64_t slot = static_cast<int64_t>(row_bh) * RT + my_slot;
@@ -407,6 +454,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       }
       tc_fence_before_sync();
       mbar_arrive(o_free + wg);     // O columns of this group may be overwritten
+      if (m == 0) RTTS_STAMP(2, n, 4);
     }
   }
   tc_fence_before_sync();
@@ -451,6 +499,8 @@ __global__ void __launch_bounds__(256) lsh_merge_fwd_kernel(const __nv_bfloat16*
   if (c == 0) lse[row] = mx + __logf(den);
 }
 
+static long long* g_fwd_trace = nullptr;   // debug only (rtts_debug_set_fwd_trace)
+
 template <int BUCKET>
 int launch_attn_fwd(const AttnFwdParams& p, int ctas, cudaStream_t stream) {
   using L = AttnFwdSmem<BUCKET>;
@@ -489,6 +539,7 @@ extern "C" int rtts_lsh_attn_fwd(const void* qk, const void* v, int64_t ld, cons
   p.mask = mask;
   p.o_rounds = static_cast<__nv_bfloat16*>(o_rounds);
   p.lse_rounds = lse_rounds;
+  p.trace = g_fwd_trace;
   p.T = T; p.H = H; p.R = R;
   p.tiles_per_row = R * T / kQRows;
   p.score_scale_log2 = spec->score_scale * kLog2e;
@@ -512,3 +563,6 @@ extern "C" int rtts_lsh_merge_fwd(const void* o_rounds, const float* lse_rounds,
       static_cast<const __nv_bfloat16*>(o_rounds), lse_rounds, static_cast<__nv_bfloat16*>(out), ld_out, lse, T, H, R, rows);
   return check_launch("rtts_lsh_merge_fwd");
 }
+
+// Debug hook (not part of the product ABI): device buffer of 3*32*8 int64 receiving clock64 stamps of CTA 0.
+extern "C" void rtts_debug_set_fwd_trace(void* device_buffer) { g_fwd_trace = static_cast<long long*>(device_buffer); }

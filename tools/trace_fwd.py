@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 lib.rtts_debug_set_fwd_trace(None)
 t = trace.cpu().view(3, 32, 8)
 t0 = int(t[t > 0].min())
-names = {0: ["kv_full ok", "S issued", "p_full ok", "PV issued"], 1: ["start", "stk loaded", "kv_free ok", "arrived"], 2: ["start", "s_full ok", "P done", "o_full ok", "epi done", "fast done", "analytic done", "slowmask"]}
+names = {0: ["kv_full ok", "S issued", "p_full ok", "PV issued"], 1: ["start", "stk loaded", "kv_free ok", "arrived"], 2: ["start", "s_full ok", "P done", "o_full ok", "epi done", "fast done"]}
 for n in range(4, 14):
     print(f"--- tile {n}")
     for role, rn in ((1, "loader"), (0, "mma"), (2, "softmax")):
