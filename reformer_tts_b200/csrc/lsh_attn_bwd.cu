@@ -54,7 +54,8 @@ struct AttnBwdParams {
 };
 
 #define RTTS_BSTAMP(k) do { if (p.trace != nullptr && blockIdx.x == 0 && tid == 0) p.trace[(k)] = clock64(); } while (0)
-constexpr int kBwdThreads = 512;     // 4 warpgroups; warpgroup g owns 16 of the 64 query columns of every block / 16 of the 64 output columns
+constexpr int kBwdWorkers = 512;     // 4 warpgroups; warpgroup g owns 16 of the 64 query columns of every block / 16 of the 64 output columns
+constexpr int kBwdThreads = kBwdWorkers + 32;   // + one warp whose lane 0 issues every tcgen05.mma (the workers never wait on the issue itself)
 
 template <int BUCKET>
 struct AttnBwdSmem {
@@ -70,8 +71,8 @@ struct AttnBwdSmem {
   static constexpr int kOffQSlot = kOffQStat + kQRows * 8; // int[kQRows] unsorted slot
   static constexpr int kOffKInv = kOffQSlot + kQRows * 4;  // float[kKeyRows] 1/|k|
   static constexpr int kOffDot = kOffKInv + kKeyRows * 4;  // float[4][kKeyRows] partial <x, G>
-  static constexpr int kOffBar = kOffDot + 4 * kKeyRows * 4;   // 2 mbarriers (S/dP buffers) + 1 (accumulators)
-  static constexpr int kOffTmem = kOffBar + 3 * 8;
+  static constexpr int kOffBar = kOffDot + 4 * kKeyRows * 4;   // 2 mbarriers (S/dP buffers) + 2 (block consumed) + 1 (accumulators)
+  static constexpr int kOffTmem = kOffBar + 5 * 8;
   static constexpr int kTotal = kOffTmem + 8;
   static constexpr int kDynamic = kTotal + 1024;
 };
@@ -94,7 +95,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
   float* k_inv = reinterpret_cast<float*>(smem + L::kOffKInv);
   float* dot_part = reinterpret_cast<float*>(smem + L::kOffDot);
   uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + L::kOffBar);     // [2]
-  uint64_t* bar_acc = bar_s + 2;
+  uint64_t* bar_blk = bar_s + 2;                                        // [2] 512 worker arrivals: Pt / dSt of a block written
+  uint64_t* bar_acc = bar_s + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -112,13 +114,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
   if (tid == 0) {
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 1, 1);
+    mbar_init(bar_blk, kBwdWorkers);
+    mbar_init(bar_blk + 1, kBwdWorkers);
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
 
   // ---- gather qk / dout rows of the query slots, v rows of the key slots ---------------------------------
   // pos = sticker - round*T with the round taken from the slot index (see the forward kernel).
-  {
+  if (tid < kBwdWorkers) {
     const int g = tid >> 3, c = tid & 7;          // 64 row groups of 8 lanes
     constexpr int kPasses = kQRows / 64;
     const int ahead_first = first_slot + kKeyRows >= RT ? first_slot + kKeyRows - RT : first_slot + kKeyRows;   // look-ahead chunk
@@ -188,30 +192,53 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
       umma_ss(tmem + cdp_, dV_k + (k * 32 >> 4), dDO_k + ((qb * 8192 + k * 32) >> 4), idesc, k > 0);
     umma_commit(bar_s + (qb & 1));
   };
-  if (tid == 0) {
-    issue_scores(0);
-    issue_scores(1);
-  }
-
-  // this thread's key row
-  const float inv = k_inv[j];
-  const float cs = inv * p.score_scale * kBLog2e;   // score scale in log2 units
-  const float gs = inv * p.score_scale;             // folded into dSt so one tile serves dQ and G
-  const int k_enc = q_meta[j].x;
-  const int k_chunk = j / BUCKET;                   // 0|1 for bucket 64, 0 for bucket 128
-  const float mv = p.mask_value_log2, sv = p.self_value_log2;
-  const int col0 = wg * 16;                         // this thread's 16 query columns inside a block
+  if (warp == kBwdWorkers / 32) {
+    // ================================================= MMA issuer =================================================
+    if ((tid & 31) == 0) {
+      issue_scores(0);
+      issue_scores(1);
+      constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, false, true);   // A K-major, B MN-major
+      constexpr uint32_t idesc_nn = umma_idesc_bf16(128, 64, true, true);
+#pragma unroll 1
+      for (int qb = 0; qb < kQBlocks; ++qb) {
+        mbar_wait(bar_blk + (qb & 1), (qb >> 1) & 1);      // Pt / dSt of block qb written, its (St, dPt) buffer fully consumed
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + cDV, dPT_k + ((qb * kBlk + k * 32) >> 4), dDO_n + ((qb * 8192 + k * 2048) >> 4), idesc_kn, (qb | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem + cG, dDS_k + ((qb * kBlk + k * 32) >> 4), dX_n + ((qb * 8192 + k * 2048) >> 4), idesc_kn, (qb | k) != 0);
+        if ((qb & 1) || qb == kQBlocks - 1) {
+          // dQ for query rows [pair*128, +128): A = dSt blocks (pair*2, pair*2+1) read MN-major (M = queries)
+          const int pair = qb >> 1;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_ss(tmem + (pair ? cDQ1 : cDQ0), dDS_n + ((pair * 2 * kBlk + k * 2048) >> 4), dX_n + (k * 2048 >> 4), idesc_nn, k > 0);
+        }
+        if (qb + 2 < kQBlocks) issue_scores(qb + 2);     // refill the buffer that was just consumed
+      }
+      umma_commit(bar_acc);
+    }
+  } else {
+    // ================================================= workers ====================================================
+    // this thread's key row
+    const float inv = k_inv[j];
+    const float cs = inv * p.score_scale * kBLog2e;   // score scale in log2 units
+    const float gs = inv * p.score_scale;             // folded into dSt so one tile serves dQ and G
+    const int k_enc = q_meta[j].x;
+    const int k_chunk = j / BUCKET;                   // 0|1 for bucket 64, 0 for bucket 128
+    const float mv = p.mask_value_log2, sv = p.self_value_log2;
+    const int col0 = wg * 16;                         // this thread's 16 query columns inside a block
 
 #pragma unroll 1
-  for (int qb = 0; qb < kQBlocks; ++qb) {
-    mbar_wait(bar_s + (qb & 1), (qb >> 1) & 1);
-    tc_fence_after_sync();
-    RTTS_BSTAMP(4 + qb * 3);
-    const uint32_t cs_ = (qb & 1) ? cS1 : cS0, cdp_ = (qb & 1) ? cDP1 : cDP0;
-    // which query chunk is this block, and does it see this thread's key chunk?
-    const int q_chunk = (qb * 64) / BUCKET;
-    const bool pair_live = (q_chunk == k_chunk) || (q_chunk == k_chunk + 1);
-    {
+    for (int qb = 0; qb < kQBlocks; ++qb) {
+      mbar_wait(bar_s + (qb & 1), (qb >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t cs_ = (qb & 1) ? cS1 : cS0, cdp_ = (qb & 1) ? cDP1 : cDP0;
+      // which query chunk is this block, and does it see this thread's key chunk?
+      const int q_chunk = (qb * 64) / BUCKET;
+      const bool pair_live = (q_chunk == k_chunk) || (q_chunk == k_chunk + 1);
       uint32_t rs[16], rp[16];
       tmem_ld16(t_row + cs_ + col0, rs);
       tmem_ld16(t_row + cdp_ + col0, rp);
@@ -230,10 +257,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
         const float2 qs = qsv[i];
         const bool masked = k_enc > qm.y;
         const bool self = k_enc == qm.x;
-        float s = __uint_as_float(rs[i]) * cs;
-        s = masked ? mv : s;
-        s = self ? sv : s;
-        const float pr = pair_live ? exp2f(s - qs.x) : 0.f;
+        float sc = __uint_as_float(rs[i]) * cs;
+        sc = masked ? mv : sc;
+        sc = self ? sv : sc;
+        const float pr = pair_live ? exp2f(sc - qs.x) : 0.f;
         pe[i] = pr;
         de[i] = (masked || self) ? 0.f : pr * (__uint_as_float(rp[i]) - qs.y) * gs;
       }
@@ -250,106 +277,83 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
         *reinterpret_cast<uint4*>(pt_row + off) = u;
         *reinterpret_cast<uint4*>(ds_row + off) = w;
       }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(bar_blk + (qb & 1));
     }
-    RTTS_BSTAMP(5 + qb * 3);
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();          // Pt / dSt of this block complete; this block's (St, dPt) buffer fully consumed
+    mbar_wait(bar_acc, 0);
     tc_fence_after_sync();
 
-    if (tid == 0) {
-      constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, false, true);   // A K-major, B MN-major
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_ss(tmem + cDV, dPT_k + ((qb * kBlk + k * 32) >> 4), dDO_n + ((qb * 8192 + k * 2048) >> 4), idesc_kn, (qb | k) != 0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_ss(tmem + cG, dDS_k + ((qb * kBlk + k * 32) >> 4), dX_n + ((qb * 8192 + k * 2048) >> 4), idesc_kn, (qb | k) != 0);
-      if ((qb & 1) || qb == kQBlocks - 1) {
-        // dQ for query rows [pair*128, +128): A = dSt blocks (pair*2, pair*2+1) read MN-major (M = queries)
-        constexpr uint32_t idesc_nn = umma_idesc_bf16(128, 64, true, true);
-        const int pair = qb >> 1;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss(tmem + (pair ? cDQ1 : cDQ0), dDS_n + ((pair * 2 * kBlk + k * 2048) >> 4), dX_n + (k * 2048 >> 4), idesc_nn, k > 0);
-      }
-      if (qb + 2 < kQBlocks) issue_scores(qb + 2);     // refill the buffer that was just consumed
-    }
-    RTTS_BSTAMP(6 + qb * 3);
-  }
-  if (tid == 0) umma_commit(bar_acc);
-  mbar_wait(bar_acc, 0);
-  tc_fence_after_sync();
-  RTTS_BSTAMP(20);
-
-  // ---- epilogue: warpgroup g handles output columns [16g, 16g+16) of every accumulator row ------------------------------------
-  const int64_t out_base = static_cast<int64_t>(row_bh) * RT;
-  const int64_t my_row = (out_base + q_slot[j]) * kBDh + col0;
-  {
-    uint32_t r[16];
-    tmem_ld16(t_row + cDV + col0, r);
-    tmem_ld_wait();
-    uint4* dst = reinterpret_cast<uint4*>(p.dv + my_row);
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-      dst[q] = make_uint4(pack_bf16(__uint_as_float(r[q * 8]), __uint_as_float(r[q * 8 + 1])), pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3])),
-                          pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5])), pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7])));
-  }
-  float g[16], x[16];
-  {
-    uint32_t r[16];
-    tmem_ld16(t_row + cG + col0, r);
-    tmem_ld_wait();
-    float dot = 0.f;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const uint4 u = *reinterpret_cast<const uint4*>(smem + L::kOffX + sw128_offset(j, wg * 2 + c));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        x[c * 8 + 2 * e] = bf16_lo(w[e]);
-        x[c * 8 + 2 * e + 1] = bf16_hi(w[e]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      g[i] = __uint_as_float(r[i]);
-      dot = fmaf(x[i], g[i], dot);
-    }
-    dot_part[wg * kKeyRows + j] = dot;
-  }
-  __syncthreads();
-  {
-    // key-normalisation Jacobian dx = G - x |k|^-2 <x, G>  (dh == 64: the L2 and the RMS/sqrt(dh) norms share |k|^-2 = inv^2),
-    // plus this slot's query-role gradient from the keys of this CTA (accumulator 0, row j)
-    const float coef = inv * inv * (dot_part[j] + dot_part[kKeyRows + j] + dot_part[2 * kKeyRows + j] + dot_part[3 * kKeyRows + j]);
-    uint32_t r[16];
-    tmem_ld16(t_row + cDQ0 + col0, r);
-    tmem_ld_wait();
-    float o[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]) + g[i] - x[i] * coef;
-    uint4* dst = reinterpret_cast<uint4*>(p.dqk_main + my_row);
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-      dst[q] = make_uint4(pack_bf16(o[q * 8], o[q * 8 + 1]), pack_bf16(o[q * 8 + 2], o[q * 8 + 3]), pack_bf16(o[q * 8 + 4], o[q * 8 + 5]),
-                          pack_bf16(o[q * 8 + 6], o[q * 8 + 7]));
-  }
-  {
-    // accumulator 1 = query rows 128.. (the look-ahead chunk, BUCKET rows) -> dq_b.
-    // every warp must execute the (warp-collective) TMEM loads; only rows < BUCKET are stored
-    const bool live = j < BUCKET;
-    uint32_t r[16];
-    tmem_ld16(t_row + cDQ1 + col0, r);
-    tmem_ld_wait();
-    if (live) {
-      uint4* dst_b = reinterpret_cast<uint4*>(p.dq_b + (out_base + q_slot[kKeyRows + j]) * kBDh + col0);
-#pragma unroll
+    RTTS_BSTAMP(20);
+    // ---- epilogue: warpgroup g handles output columns [16g, 16g+16) of every accumulator row ------------------------------------
+    const int64_t out_base = static_cast<int64_t>(row_bh) * RT;
+    const int64_t my_row = (out_base + q_slot[j]) * kBDh + col0;
+    {
+      uint32_t r[16];
+      tmem_ld16(t_row + cDV + col0, r);
+      tmem_ld_wait();
+      uint4* dst = reinterpret_cast<uint4*>(p.dv + my_row);
+  #pragma unroll
       for (int q = 0; q < 2; ++q)
-        dst_b[q] = make_uint4(pack_bf16(__uint_as_float(r[q * 8]), __uint_as_float(r[q * 8 + 1])), pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3])),
-                              pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5])), pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7])));
+        dst[q] = make_uint4(pack_bf16(__uint_as_float(r[q * 8]), __uint_as_float(r[q * 8 + 1])), pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3])),
+                            pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5])), pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7])));
     }
-  }
+    float g[16], x[16];
+    {
+      uint32_t r[16];
+      tmem_ld16(t_row + cG + col0, r);
+      tmem_ld_wait();
+      float dot = 0.f;
+  #pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint4 u = *reinterpret_cast<const uint4*>(smem + L::kOffX + sw128_offset(j, wg * 2 + c));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  #pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          x[c * 8 + 2 * e] = bf16_lo(w[e]);
+          x[c * 8 + 2 * e + 1] = bf16_hi(w[e]);
+        }
+      }
+  #pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        g[i] = __uint_as_float(r[i]);
+        dot = fmaf(x[i], g[i], dot);
+      }
+      dot_part[wg * kKeyRows + j] = dot;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kBwdWorkers) : "memory");     // workers only: the issuer warp is not part of the epilogue
+    {
+      // key-normalisation Jacobian dx = G - x |k|^-2 <x, G>  (dh == 64: the L2 and the RMS/sqrt(dh) norms share |k|^-2 = inv^2),
+      // plus this slot's query-role gradient from the keys of this CTA (accumulator 0, row j)
+      const float coef = inv * inv * (dot_part[j] + dot_part[kKeyRows + j] + dot_part[2 * kKeyRows + j] + dot_part[3 * kKeyRows + j]);
+      uint32_t r[16];
+      tmem_ld16(t_row + cDQ0 + col0, r);
+      tmem_ld_wait();
+      float o[16];
+  #pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]) + g[i] - x[i] * coef;
+      uint4* dst = reinterpret_cast<uint4*>(p.dqk_main + my_row);
+  #pragma unroll
+      for (int q = 0; q < 2; ++q)
+        dst[q] = make_uint4(pack_bf16(o[q * 8], o[q * 8 + 1]), pack_bf16(o[q * 8 + 2], o[q * 8 + 3]), pack_bf16(o[q * 8 + 4], o[q * 8 + 5]),
+                            pack_bf16(o[q * 8 + 6], o[q * 8 + 7]));
+    }
+    {
+      // accumulator 1 = query rows 128.. (the look-ahead chunk, BUCKET rows) -> dq_b.
+      // every warp must execute the (warp-collective) TMEM loads; only rows < BUCKET are stored
+      const bool live = j < BUCKET;
+      uint32_t r[16];
+      tmem_ld16(t_row + cDQ1 + col0, r);
+      tmem_ld_wait();
+      if (live) {
+        uint4* dst_b = reinterpret_cast<uint4*>(p.dq_b + (out_base + q_slot[kKeyRows + j]) * kBDh + col0);
+  #pragma unroll
+        for (int q = 0; q < 2; ++q)
+          dst_b[q] = make_uint4(pack_bf16(__uint_as_float(r[q * 8]), __uint_as_float(r[q * 8 + 1])), pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3])),
+                                pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5])), pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7])));
+      }
+    }
+  }   // workers
   RTTS_BSTAMP(21);
   tc_fence_before_sync();
   __syncthreads();

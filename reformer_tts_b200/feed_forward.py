@@ -64,3 +64,29 @@ def ln_feed_forward(x, norm, lin1, lin2, cache1, cache2):
         ln_w, ln_b, eps = norm.weight, norm.bias, norm.eps
     return _LNFeedForwardFn.apply(x.float(), ln_w, ln_b, lin1.weight, lin1.bias, lin2.weight, lin2.bias,
                                   cache1.get(lin1.weight), cache2.get(lin2.weight), eps)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """LayerNorm on the row-wise kernels for wrapped layers that cannot take the norm into their own first kernel
+    (the decoder's cross-attention): fp32 in, bf16 out (the consumer runs in bf16), fp32 statistics and gradients."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        y, mean, rstd = ops.layernorm_fwd(x2, weight, bias, eps)
+        ctx.save_for_backward(x2, weight, mean, rstd)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, mean, rstd = ctx.saved_tensors
+        d = x2.shape[-1]
+        g_w = torch.zeros(d, dtype=torch.float32, device=x2.device)
+        g_b = torch.zeros(d, dtype=torch.float32, device=x2.device)
+        dx = ops.layernorm_bwd(dy.reshape(-1, d).float(), x2, weight, mean, rstd, g_w, g_b)
+        return dx.view(dy.shape), g_w, g_b, None
+
+
+def layer_norm_bf16(x, norm):
+    return _LayerNormFn.apply(x.float(), norm.weight, norm.bias, norm.eps)

@@ -27,13 +27,15 @@ class _WeightCache:
     """bf16 copies of fp32 master weights, rebuilt only when a weight's version counter moves.  ``enabled = False`` forces the
     cast on every call (needed while a CUDA graph is captured: the cast must be part of the graph, weights change on replay)."""
     enabled = True
+    epoch = 0       # bumped at the start of every training step: forces one re-cast per step even when version counters cannot be
+                    # observed (a CUDA-graph replay updates the weights without running Python)
 
     def __init__(self):
         self._key = None
         self._val = None
 
     def get(self, *weights: torch.Tensor) -> torch.Tensor:
-        key = tuple((w.data_ptr(), w._version) for w in weights)
+        key = (_WeightCache.epoch,) + tuple((w.data_ptr(), w._version) for w in weights)
         if key != self._key or not _WeightCache.enabled:
             with torch.no_grad():
                 self._val = torch.cat([w.detach() for w in weights], dim=0).to(torch.bfloat16).contiguous()

@@ -14,6 +14,7 @@ from typing import Dict, List, Optional
 import torch
 from torch import nn
 
+from ..feed_forward import layer_norm_bf16
 from ..lsh_attention import HFLSHSelfAttention, LSHSelfAttention
 from .modules import FeedForward
 from .reversible import ReversibleBlock, ReversibleHalfResidual, ReversibleSequence, ReversibleSwap
@@ -95,6 +96,13 @@ class MultiheadAttentionWrapper(nn.Module):
         layer = self.layer
         return (self.training and query.is_cuda and layer._qkv_same_embed_dim and layer.in_proj_bias is not None and layer.bias_k is None
                 and not layer.add_zero_attn and set(extra) <= {"key_padding_mask"})
+
+    def forward_with_norm(self, query, norm, **kwargs):
+        """``WithNorm`` hands over its LayerNorm: in the training fast path it runs on the row-wise kernel (bf16 out)."""
+        extra = {k: v for k, v in kwargs.items() if k not in ("key", "value")}
+        if "key" in kwargs and self._fast_path_ok(query, extra) and query.shape[-1] % 128 == 0:
+            return self._forward_training(layer_norm_bf16(query, norm), kwargs["key"], extra.get("key_padding_mask"))
+        return self.forward(norm(query), **kwargs)
 
     def forward(self, query, **kwargs):
         if "key" not in kwargs:

@@ -44,6 +44,7 @@ class TrainStep:
 
     # ------------------------------------------------------------------------------------------------------------------
     def _eager(self, batch):
+        _WeightCache.epoch += 1       # bf16 weight copies are rebuilt once per step (inside the captured graph too)
         loss = loss_of_batch(self.model, self.loss_fn, batch)
         loss.backward()
         if self.averager is not None:
@@ -69,12 +70,10 @@ class TrainStep:
         graph = torch.cuda.CUDAGraph()
         for g in generators:
             graph.register_generator_state(g)
-        _WeightCache.enabled = False          # the fp32 -> bf16 weight casts must be recorded in the graph
-        try:
-            with torch.cuda.graph(graph):
-                self.static_loss = self._eager(self.static)
-        finally:
-            _WeightCache.enabled = True
+        # the epoch bump inside _eager makes the first use of every weight in the captured step re-cast it, so the fp32 -> bf16
+        # casts are recorded in the graph once per weight and replayed after every optimiser update
+        with torch.cuda.graph(graph):
+            self.static_loss = self._eager(self.static)
         self.graph = graph
 
     # ------------------------------------------------------------------------------------------------------------------
