@@ -17,10 +17,18 @@
 
 namespace rtts {
 
-constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3;
-constexpr int kTileBytes = 128 * kBK * 2;                     // 16 KB per operand per stage
+constexpr int kBM = 128, kBK = 64;
 constexpr int kGemmThreads = 192;
-constexpr int kGemmSmem = kStages * 2 * kTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kATileBytes = kBM * kBK * 2;                    // 16 KB
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kBTileBytes = BN * kBK * 2;            // 16 | 32 KB
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = BN == 128 ? 6 : 4;           // 192 KB of operand ring either way
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t kTmemCols = 2 * BN;               // two accumulators: the epilogue of tile i overlaps the main loop of tile i+1
+};
 
 struct GemmParams {
   void* C;
@@ -31,6 +39,7 @@ struct GemmParams {
   float* colsum;
   int M, N, K;       // K = per-split extent
   int epilogue;
+  int tiles_n, tiles_mn, work;   // work = tiles_mn * split_k
 };
 
 // Sum r[0..32) over the 32 lanes of a warp; lane i ends up owning column i's total.
@@ -48,21 +57,24 @@ __device__ __forceinline__ float warp_column_sums(float* r, int lane) {
   return r[0];
 }
 
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                                                                 const __grid_constant__ CUtensorMap tmap_b,
-                                                                 const GemmParams p) {
+// Persistent: one CTA per SM walks work items w = blockIdx.x, += gridDim.x; w -> (split, m tile, n tile), n fastest so that
+// CTAs running at the same time share A panels in L2.
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                    const __grid_constant__ CUtensorMap tmap_b,
+                                                                    const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t s_base = smem_u32(smem);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * 2 * kTileBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* accum_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + kStages;     // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;
-  const int k_begin = blockIdx.z * p.K;
   const int num_kb = p.K / kBK;
 
   if (warp == 0 && lane == 0) {
@@ -72,10 +84,13 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_kernel(const __grid_co
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full + a, 1);
+      mbar_init(acc_empty + a, 128);
+    }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kBN);
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -83,114 +98,133 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_bf16_kernel(const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        mbar_wait(empty_bar + s, ((kb / kStages) & 1) ^ 1);
-        const uint32_t sa = s_base + s * 2 * kTileBytes, sb = sa + kTileBytes;
-        const int k0 = k_begin + kb * kBK;
-        mbar_arrive_expect_tx(full_bar + s, 2 * kTileBytes);
-        if (A_MN) {
-          tma_load_2d(sa, &tmap_a, full_bar + s, m0, k0);
-          tma_load_2d(sa + kTileBytes / 2, &tmap_a, full_bar + s, m0 + 64, k0);
-        } else {
-          tma_load_2d(sa, &tmap_a, full_bar + s, k0, m0);
-        }
-        if (B_MN) {
-          tma_load_2d(sb, &tmap_b, full_bar + s, n0, k0);
-          tma_load_2d(sb + kTileBytes / 2, &tmap_b, full_bar + s, n0 + 64, k0);
-        } else {
-          tma_load_2d(sb, &tmap_b, full_bar + s, k0, n0);
+      int it = 0;       // running k-block counter across work items: the operand ring never drains between tiles
+      for (int w = blockIdx.x; w < p.work; w += gridDim.x) {
+        const int split = w / p.tiles_mn, tile = w - split * p.tiles_mn;
+        const int m0 = (tile / p.tiles_n) * kBM, n0 = (tile % p.tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(empty_bar + s, ((it / kStages) & 1) ^ 1);
+          const uint32_t sa = s_base + s * Cfg::kStageBytes, sb = sa + kATileBytes;
+          const int k0 = split * p.K + kb * kBK;
+          mbar_arrive_expect_tx(full_bar + s, Cfg::kStageBytes);
+          if (A_MN) {
+            tma_load_2d(sa, &tmap_a, full_bar + s, m0, k0);
+            tma_load_2d(sa + kATileBytes / 2, &tmap_a, full_bar + s, m0 + 64, k0);
+          } else {
+            tma_load_2d(sa, &tmap_a, full_bar + s, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int nb = 0; nb < BN / 64; ++nb) tma_load_2d(sb + nb * (64 * kBK * 2), &tmap_b, full_bar + s, n0 + nb * 64, k0);
+          } else {
+#pragma unroll
+            for (int nb = 0; nb < BN / 128; ++nb) tma_load_2d(sb + nb * (128 * kBK * 2), &tmap_b, full_bar + s, k0, n0 + nb * 128);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, kBN, A_MN, B_MN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        mbar_wait(full_bar + s, (kb / kStages) & 1);
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN, B_MN);
+      int it = 0, t = 0;
+      for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++t) {
+        const int acc = t & 1;
+        mbar_wait(acc_empty + acc, ((t >> 1) & 1) ^ 1);      // epilogue has drained this accumulator (two tiles ago)
         tc_fence_after_sync();
-        const uint32_t sa = s_base + s * 2 * kTileBytes, sb = sa + kTileBytes;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(full_bar + s, (it / kStages) & 1);
+          tc_fence_after_sync();
+          const uint32_t sa = s_base + s * Cfg::kStageBytes, sb = sa + kATileBytes;
+          const uint64_t da0 = A_MN ? umma_desc_sw128(sa, kATileBytes / 2, 1024) : umma_desc_sw128(sa, 16, 1024);
+          const uint64_t db0 = B_MN ? umma_desc_sw128(sb, 64 * kBK * 2, 1024) : umma_desc_sw128(sb, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint64_t da = A_MN ? umma_desc_sw128(sa + k * 2048, kTileBytes / 2, 1024) : umma_desc_sw128(sa + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, kTileBytes / 2, 1024) : umma_desc_sw128(sb + k * 32, 16, 1024);
-          umma_ss(tmem, da, db, idesc, (kb | k) != 0);
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_ss(tmem + acc * BN, da0 + ((A_MN ? k * 2048 : k * 32) >> 4), db0 + ((B_MN ? k * 2048 : k * 32) >> 4), idesc, (kb | k) != 0);
+          umma_commit(empty_bar + s);          // smem slot reusable once these MMAs retire
         }
-        umma_commit(empty_bar + s);          // smem slot reusable once these MMAs retire
+        umma_commit(acc_full + acc);           // accumulator complete
       }
-      umma_commit(accum_bar);                // accumulator complete
     }
   } else {
     // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = output rows m0 + that range ----
     const int quarter = warp & 3;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after_sync();
-    const int row = m0 + quarter * 32 + lane;
     const int epi = p.epilogue;
+    int t = 0;
+    for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++t) {
+      const int split = w / p.tiles_mn, tile = w - split * p.tiles_mn;
+      const int m0 = (tile / p.tiles_n) * kBM, n0 = (tile % p.tiles_n) * BN;
+      const int acc = t & 1;
+      mbar_wait(acc_full + acc, (t >> 1) & 1);
+      tc_fence_after_sync();
+      const int row = m0 + quarter * 32 + lane;
 #pragma unroll 1
-    for (int c0 = 0; c0 < kBN; c0 += 32) {
-      uint32_t raw[32];
-      tmem_ld32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + c0, raw);
-      tmem_ld_wait();
-      float r[32];
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c0, raw);
+        tmem_ld_wait();
+        float r[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(raw[i]);
-      const int col = n0 + c0;
-      if (epi & RTTS_EPI_BIAS) {
+        for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(raw[i]);
+        const int col = n0 + c0;
+        if (epi & RTTS_EPI_BIAS) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
-          r[i] += bv.x; r[i + 1] += bv.y; r[i + 2] += bv.z; r[i + 3] += bv.w;
-        }
-      }
-      if (epi & RTTS_EPI_RELU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = fmaxf(r[i], 0.f);
-      }
-      if (epi & RTTS_EPI_GATE) {
-        const uint4* g = reinterpret_cast<const uint4*>(p.gate + static_cast<int64_t>(row) * p.ldgate + col);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 u = __ldg(g + q);
-          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (!(bf16_lo(w[e]) > 0.f)) r[q * 8 + 2 * e] = 0.f;
-            if (!(bf16_hi(w[e]) > 0.f)) r[q * 8 + 2 * e + 1] = 0.f;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+            r[i] += bv.x; r[i + 1] += bv.y; r[i + 2] += bv.z; r[i + 3] += bv.w;
           }
         }
-      }
-      if (epi & RTTS_EPI_OUT_BF16) {
-        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + col);
+        if (epi & RTTS_EPI_RELU) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16(r[q * 8 + 0], r[q * 8 + 1]); u.y = pack_bf16(r[q * 8 + 2], r[q * 8 + 3]);
-          u.z = pack_bf16(r[q * 8 + 4], r[q * 8 + 5]); u.w = pack_bf16(r[q * 8 + 6], r[q * 8 + 7]);
-          dst[q] = u;
+          for (int i = 0; i < 32; ++i) r[i] = fmaxf(r[i], 0.f);
         }
-      } else if (epi & RTTS_EPI_ATOMIC) {
-        float* dst = static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col;
+        if (epi & RTTS_EPI_GATE) {
+          const uint4* g = reinterpret_cast<const uint4*>(p.gate + static_cast<int64_t>(row) * p.ldgate + col);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)      // 16-byte vector reduction (sm_90+): a quarter of the atomic instructions
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(r[i]), "f"(r[i + 1]), "f"(r[i + 2]), "f"(r[i + 3]) : "memory");
-      } else {
-        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col);
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = __ldg(g + q);
+            const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+            for (int e = 0; e < 4; ++e) {
+              if (!(bf16_lo(wv[e]) > 0.f)) r[q * 8 + 2 * e] = 0.f;
+              if (!(bf16_hi(wv[e]) > 0.f)) r[q * 8 + 2 * e + 1] = 0.f;
+            }
+          }
+        }
+        if (epi & RTTS_EPI_OUT_BF16) {
+          uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + col);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16(r[q * 8 + 0], r[q * 8 + 1]); u.y = pack_bf16(r[q * 8 + 2], r[q * 8 + 3]);
+            u.z = pack_bf16(r[q * 8 + 4], r[q * 8 + 5]); u.w = pack_bf16(r[q * 8 + 6], r[q * 8 + 7]);
+            dst[q] = u;
+          }
+        } else if (epi & RTTS_EPI_ATOMIC) {
+          float* dst = static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)      // 16-byte vector reduction (sm_90+): a quarter of the atomic instructions
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(r[i]), "f"(r[i + 1]), "f"(r[i + 2]), "f"(r[i + 3]) : "memory");
+        } else {
+          float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q] = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+        }
+        if (epi & RTTS_EPI_COLSUM) {
+          const float tot = warp_column_sums(r, lane);
+          atomicAdd(p.colsum + col + lane, tot);
+        }
       }
-      if (epi & RTTS_EPI_COLSUM) {
-        const float tot = warp_column_sums(r, lane);
-        atomicAdd(p.colsum + col + lane, tot);
-      }
+      tc_fence_before_sync();
+      mbar_arrive(acc_empty + acc);            // 128 arrivals: the MMA warp may overwrite this accumulator
     }
-    tc_fence_before_sync();
   }
+  tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem, kBN);
+    tmem_dealloc(tmem, Cfg::kTmemCols);
   }
 }
 
@@ -227,16 +261,36 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_
   return kOk;
 }
 
-template <bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     if (e != cudaSuccess) return fail(kErrCuda, "rtts_gemm_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  gemm_bf16_kernel<A_MN, B_MN><<<grid, kGemmThreads, kGemmSmem, stream>>>(ta, tb, p);
+  const int grid = p.work < kNumSMs ? p.work : kNumSMs;
+  gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(ta, tb, p);
   return check_launch("rtts_gemm_bf16");
+}
+
+template <int BN>
+static int dispatch_gemm(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, GemmParams& p, int K_total, cudaStream_t s) {
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn) rc = make_tmap(&ta, A, p.M, K_total, lda, 64, kBK);
+  else rc = make_tmap(&ta, A, K_total, p.M, lda, kBK, kBM);
+  if (rc) return rc;
+  if (b_mn) rc = make_tmap(&tb, B, p.N, K_total, ldb, 64, kBK);
+  else rc = make_tmap(&tb, B, K_total, p.N, ldb, kBK, 128);
+  if (rc) return rc;
+  p.tiles_n = p.N / BN;
+  p.tiles_mn = (p.M / kBM) * p.tiles_n;
+  if (a_mn && b_mn) return launch_gemm<BN, true, true>(ta, tb, p, s);
+  if (a_mn) return launch_gemm<BN, true, false>(ta, tb, p, s);
+  if (b_mn) return launch_gemm<BN, false, true>(ta, tb, p, s);
+  return launch_gemm<BN, false, false>(ta, tb, p, s);
 }
 
 }  // namespace rtts
@@ -247,7 +301,7 @@ extern "C" int rtts_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
                               int64_t ldc, const float* bias, const void* gate, int64_t ldgate, float* colsum, int M, int N,
                               int K, int epilogue, int split_k, void* stream) {
   RTTS_REQUIRE(A && B && C, "rtts_gemm_bf16: null pointer");
-  RTTS_REQUIRE(M > 0 && N > 0 && K > 0 && M % kBM == 0 && N % kBN == 0, "rtts_gemm_bf16: M=%d, N=%d must be multiples of 128", M, N);
+  RTTS_REQUIRE(M > 0 && N > 0 && K > 0 && M % kBM == 0 && N % 128 == 0, "rtts_gemm_bf16: M=%d, N=%d must be multiples of 128", M, N);
   RTTS_REQUIRE(split_k >= 1 && K % (kBK * split_k) == 0, "rtts_gemm_bf16: K=%d must be a multiple of 64*split_k", K);
   RTTS_REQUIRE(split_k == 1 || (epilogue & RTTS_EPI_ATOMIC), "rtts_gemm_bf16: split_k > 1 needs RTTS_EPI_ATOMIC");
   RTTS_REQUIRE(!((epilogue & RTTS_EPI_ATOMIC) && (epilogue & (RTTS_EPI_OUT_BF16 | RTTS_EPI_BIAS | RTTS_EPI_RELU | RTTS_EPI_GATE | RTTS_EPI_COLSUM))),
@@ -258,21 +312,16 @@ extern "C" int rtts_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   RTTS_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && (ldgate % 8 == 0), "rtts_gemm_bf16: leading dimensions must be multiples of 8");
   RTTS_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) == 0,
                "rtts_gemm_bf16: operands must be 16-byte aligned");
-  CUtensorMap ta, tb;
-  int rc;
-  if (a_mn_major) rc = make_tmap(&ta, A, M, K, lda, 64, kBK);
-  else rc = make_tmap(&ta, A, K, M, lda, kBK, kBM);
-  if (rc) return rc;
-  if (b_mn_major) rc = make_tmap(&tb, B, N, K, ldb, 64, kBK);
-  else rc = make_tmap(&tb, B, K, N, ldb, kBK, kBN);
-  if (rc) return rc;
   GemmParams p;
   p.C = C; p.ldc = ldc; p.bias = bias; p.gate = static_cast<const __nv_bfloat16*>(gate); p.ldgate = ldgate; p.colsum = colsum;
   p.M = M; p.N = N; p.K = K / split_k; p.epilogue = epilogue;
-  dim3 grid(N / kBN, M / kBM, split_k);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a_mn_major && b_mn_major) return launch_gemm<true, true>(ta, tb, p, grid, s);
-  if (a_mn_major) return launch_gemm<true, false>(ta, tb, p, grid, s);
-  if (b_mn_major) return launch_gemm<false, true>(ta, tb, p, grid, s);
-  return launch_gemm<false, false>(ta, tb, p, grid, s);
+  // 128x256 tiles halve the shared-memory traffic per flop; use them when they still give every SM several tiles
+  const int64_t work256 = N % 256 == 0 ? static_cast<int64_t>(M / kBM) * (N / 256) * split_k : 0;
+  if (work256 >= 4 * kNumSMs) {
+    p.work = static_cast<int>(work256);
+    return dispatch_gemm<256>(A, lda, a_mn_major, B, ldb, b_mn_major, p, K, s);
+  }
+  p.work = (M / kBM) * (N / 128) * split_k;
+  return dispatch_gemm<128>(A, lda, a_mn_major, B, ldb, b_mn_major, p, K, s);
 }
