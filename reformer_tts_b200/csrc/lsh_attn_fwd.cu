@@ -349,17 +349,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
         int n_self = 1;
         const int t_in = tile - row_bh * p.tiles_per_row;
         if ((t_in * kQRows) % p.T == 0 && win0 == 0) {       // window starts with the previous round's last chunk
+          // branch-free count first: a duplicate is rare, the scan is not
+          const uint32_t a_pos = smem_u32(key_pos);
+          int n_dup = 0;
 #pragma unroll 4
           for (int c4 = 0; c4 < BUCKET; c4 += 4) {
-            const int4 k4 = *reinterpret_cast<const int4*>(key_pos + c4);
-            const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (kk[i] == q_enc) {
-                set_one(c4 + i);
-                ++n_self;
-              }
-            }
+            const uint4 k4 = lds128(a_pos + c4 * 4);
+            n_dup += (static_cast<int>(k4.x) == q_enc) + (static_cast<int>(k4.y) == q_enc) + (static_cast<int>(k4.z) == q_enc) +
+                     (static_cast<int>(k4.w) == q_enc);
+          }
+          if (n_dup > 0) {
+            for (int c = 0; c < BUCKET; ++c)
+              if (key_pos[c] == q_enc) set_one(c);
+            n_self += n_dup;
           }
         }
         row_sum = static_cast<float>(n_self);

@@ -124,7 +124,21 @@ __global__ void __launch_bounds__(256) cast_bf16_colsum_kernel(const float* __re
   if (c >= cols) return;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
   float4 acc = make_float4(0, 0, 0, 0);
-  for (int r = r0; r < r1; ++r) {
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {       // four independent 16-byte loads in flight per thread
+    float4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(r + i) * cols + c));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint2 o;
+      o.x = pack_bf16(v[i].x, v[i].y);
+      o.y = pack_bf16(v[i].z, v[i].w);
+      *reinterpret_cast<uint2*>(y + static_cast<int64_t>(r + i) * cols + c) = o;
+      acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w;
+    }
+  }
+  for (; r < r1; ++r) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(r) * cols + c));
     uint2 o;
     o.x = pack_bf16(v.x, v.y);
@@ -228,7 +242,7 @@ extern "C" int rtts_cast_bf16_colsum(const float* x, void* y, float* colsum, int
   RTTS_REQUIRE(x && y, "rtts_cast_bf16_colsum: null pointer");
   RTTS_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "rtts_cast_bf16_colsum: cols=%d must be a multiple of 4", cols);
   const int strips = (cols / 4 + 255) / 256;
-  int row_ctas = (4 * kNumSMs + strips - 1) / strips;
+  int row_ctas = (8 * kNumSMs + strips - 1) / strips;
   if (row_ctas > rows) row_ctas = rows;
   const int rows_per_cta = (rows + row_ctas - 1) / row_ctas;
   dim3 grid(strips, (rows + rows_per_cta - 1) / rows_per_cta);
