@@ -26,6 +26,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+NCU_DRAM_BYTES_FWD_DEC_CFG2 = 47_672_576 + 172_148_736      # profiles/r1_attn_fwd_ncu_full.txt (read + write), B=20 T=1024 R=8 bucket 64
 DEFAULT_CONFIG = "bucket-size-64-18-06"       # BASELINE.json configs[1]: the configuration the metric is quoted on
 PHONEMES, FRAMES, N_MELS = 200, 800, 80       # "~200 phonemes -> ~800x80 mel frames" (BASELINE.json configs[0])
 
@@ -254,15 +255,21 @@ def run_ours(args, kwargs, world, rank, local_rank):
         key_fwd, key_bwd = f"lsh_attn_fwd[T={t}]", f"lsh_attn_bwd[T={t}]"
         fwd_ms, bwd_ms = kernel_ms.get(key_fwd, {}).get("avg_ms"), kernel_ms.get(key_bwd, {}).get("avg_ms")
         peak = peaks["bf16_tflops_sustained"]
-        roofline = {"bound": "tensor", "kernel": "lsh_attn_fwd_kernel<64> (decoder shape)", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
+        roofline = {"bound": "tensor", "kernel": f"lsh_attn_fwd_kernel<{bucket}> (decoder shape B={b} T={t} H=8 R={r})", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
                     "traffic": None, "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)"}
         if fwd_ms:
             roofline["achieved"] = flops_fwd / (fwd_ms * 1e-3) / 1e12
             roofline["frac"] = roofline["achieved"] / peak
             roofline["avg_launch_ms"] = fwd_ms
             roofline["launches_timed"] = kernel_ms[key_fwd]["count"]
+            roofline["algorithmic_flop_per_launch"] = flops_fwd
+            # DRAM bytes of one launch from the committed `ncu --set full` capture of this kernel at the benched shape
+            # (profiles/r1_attn_fwd_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum); algorithmic minimum beside it
+            if (b, t, r, bucket) == (20, 1024, 8, 64):
+                roofline["traffic"] = NCU_DRAM_BYTES_FWD_DEC_CFG2
+            roofline["algorithmic_min_bytes"] = 2 * b * t * d * 2 + r * b * t * d * 2 + r * b * 8 * t * 4
         if bwd_ms:
-            roofline["bwd_kernel"] = {"kernel": "lsh_attn_bwd_kernel<64> (decoder shape)", "avg_launch_ms": bwd_ms,
+            roofline["bwd_kernel"] = {"kernel": f"lsh_attn_bwd_kernel<{bucket}> (decoder shape)", "avg_launch_ms": bwd_ms,
                                       "achieved": 2.5 * flops_fwd / (bwd_ms * 1e-3) / 1e12, "frac": 2.5 * flops_fwd / (bwd_ms * 1e-3) / 1e12 / peak}
         roofline["timed_in"] = "eager pass of the same step, CUDA-event pair around each launch (events cannot be recorded inside a CUDA-graph replay)"
         own_total = sum(v["total_ms"] for v in kernel_ms.values()) / 2

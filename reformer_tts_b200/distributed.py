@@ -60,6 +60,9 @@ class GradientAverager:
         if self.overlap:
             self._launch(self._block_params.get(id(block), []))
 
+    def enable_overlap(self):
+        self.overlap = self.world > 1
+
     def disable_overlap(self):
         """One flat all-reduce after backward on the current stream (what a CUDA-graph capture of the step records)."""
         self.overlap = False

@@ -201,6 +201,7 @@ class HFLSHSelfAttention(_LSHBase):
         self.num_buckets = None      # hf:531-533 set lazily on the first call, then kept
         self._wqkv_cache, self._wout_cache = _WeightCache(), _WeightCache()
         self.rot_override = None
+        self._pad_bucket_cached = True
 
     def forward(self, x, attention_mask=None, norm: Optional[nn.LayerNorm] = None, **kwargs):
         b, t, d = x.shape
@@ -216,8 +217,15 @@ class HFLSHSelfAttention(_LSHBase):
         rot = torch.randn((self.heads, d // self.heads, self.n_hashes, nb // 2), dtype=torch.float32, device=x.device)  # hf:717-719
         if self.rot_override is not None:
             rot = self.rot_override.to(device=x.device, dtype=torch.float32)
-        # hf:740-747: extra padding bucket only if some token is actually masked (a host sync in the reference too)
-        pad_bucket = attention_mask is not None and not bool(attention_mask.all())
+        # hf:740-747: extra padding bucket only if some token is actually masked (a host sync in the reference too).  While a
+        # CUDA graph is being captured no host read is possible: the decision of the latest eager call (same batch layout) is kept.
+        if attention_mask is None:
+            pad_bucket = False
+        elif x.is_cuda and torch.cuda.is_current_stream_capturing():
+            pad_bucket = bool(self._pad_bucket_cached)
+        else:
+            pad_bucket = not bool(attention_mask.all())
+            self._pad_bucket_cached = pad_bucket
         cfg = dict(heads=self.heads, n_hashes=self.n_hashes, bucket_size=self.bucket_size, n_buckets=nb, pad_bucket=pad_bucket,
                    spec=LSHSpec.huggingface(d // self.heads, self.causal), eps=1e-5)
         return self._run(x, norm, self.query_key.weight, self.value.weight, None, None, rot, attention_mask, cfg)

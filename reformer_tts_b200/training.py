@@ -34,13 +34,20 @@ class TrainStep:
         self.static_loss = None
         self.graph_error = None
         if use_cuda_graph:
+            rng_before = torch.cuda.get_rng_state(self.device)
             try:
                 self._capture(warmup_steps, seed)
             except Exception as exc:      # capture is an optimisation: report and run eagerly
                 self.graph, self.graph_error = None, f"{type(exc).__name__}: {exc}"
                 print(f"[reformer_tts_b200] CUDA-graph capture failed, running eagerly: {self.graph_error}", file=sys.stderr)
-                _WeightCache.enabled = True
                 torch.cuda.synchronize()
+                # an aborted capture leaves the generators in capture mode: go back to the default record / replay RNG handling
+                for mod in self.model.modules():
+                    if isinstance(mod, Deterministic):
+                        mod._private = None
+                torch.cuda.set_rng_state(rng_before, self.device)
+                if self.averager is not None and hasattr(self.averager, "enable_overlap"):
+                    self.averager.enable_overlap()
 
     # ------------------------------------------------------------------------------------------------------------------
     def _eager(self, batch):
