@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "host_util.h"
 #include "rtts_b200.h"
+#include "tma_host.h"
 
 namespace rtts {
 
@@ -229,36 +230,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
-// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows of `ld` elements; box = box_inner x box_outer.
 static int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, int64_t ld, uint32_t box_inner,
                      uint32_t box_outer) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (fn == nullptr) return fail(kErrCuda, "rtts_gemm_bf16: cuTensorMapEncodeTiled not available from the driver");
-  const cuuint64_t gdim[2] = {inner, outer};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  const cuuint32_t box[2] = {box_inner, box_outer};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(kErrCuda, "rtts_gemm_bf16: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
-  return kOk;
+  return make_tmap_bf16(map, base, inner, outer, ld, box_inner, box_outer);
 }
 
 template <int BN, bool A_MN, bool B_MN>

@@ -1,19 +1,21 @@
 // Fused chunked shared-QK attention, forward (rtts_lsh_attn_fwd) and the round merge
 // (rtts_lsh_merge_fwd).  See include/rtts_b200.h for the contract and DESIGN.md "K9" for the tiling.
 //
-// One CTA (128 threads) owns 128 consecutive SORTED query slots of one (batch, head) row:
-//   bucket 64 : two chunks c0,c1; key tile = slots of chunks [c0-1, c0, c1]      (192 rows)
-//   bucket 128: one chunk c;      key tile = slots of chunks [c-1, c]            (256 rows)
-// and the queries are simply the last 128 rows of the key tile (shared-QK: one gather serves both
-// operands).  Rows are gathered straight from the UNSORTED token-major qk / v arrays through
-// `sticker` with 16-byte cp.async into SWIZZLE_128B shared-memory tiles (a row is 64 bf16 = one
-// 128-byte swizzle row), so the R sorted copies the reference materialises never exist.
-//   S = Q K^T          tcgen05.mma  M=128, N=192|256, K=64   -> TMEM fp32
-//   softmax            one thread per query row reads its 2*bucket-wide window from TMEM, applies the
-//                      per-key 1/|k| scale (keys are normalised AFTER the fp32-accumulated dot), the
-//                      padding / causal / self masks from the position ids, two passes (max, exp)
-//   O = P V            P (bf16) goes to shared memory in K-major SW128 layout, V is the gathered tile
-//                      used MN-major; tcgen05.mma M=128, N=64, K=192|256 -> TMEM (aliases S)
+// A tile is 128 consecutive SORTED query slots of one (batch, head) row: two chunks of bucket 64 or one chunk of
+// bucket 128.  Its keys are the same 128 slots plus the BUCKET slots before them (look-one-back, rp R6), and the
+// queries are simply the main 128 rows (shared-QK: one gather serves both operands).  Rows are gathered straight from
+// the UNSORTED token-major qk / v arrays through `sticker` with 16-byte cp.async into SWIZZLE_128B shared-memory tiles
+// (a row is 64 bf16 = one 128-byte swizzle row), so the R sorted copies the reference materialises never exist.
+//
+// Each CTA walks a CONTIGUOUS run of tiles and keeps the gathered 128-row blocks in a ring, so the look-back rows of
+// tile k are the tail of the block gathered for tile k-1: every row is fetched once per hash round (the gather is what
+// loads the SM's load/store pipe most).
+//   S = Q K^T          tcgen05.mma  M=128, N=BUCKET (look-back block) + N=128 (main block), K=64  -> TMEM fp32
+//   softmax            thread = (query row, half of its 2*bucket window): reads S from TMEM, applies the per-key 1/|k|
+//                      scale (keys are normalised AFTER the fp32-accumulated dot) and the padding / causal / self masks
+//                      from the position ids, single pass (see below), and writes P (bf16 pairs) back into TMEM over
+//                      the S columns it has just consumed
+//   O = P V            tcgen05.mma with A = P from TMEM, B = the gathered V block used MN-major -> TMEM
 //   epilogue           O / rowsum -> bf16, scatter-stored at the UNSORTED slot (r*T + pos); lse too.
 #include <cfloat>
 
@@ -46,419 +48,690 @@ struct AttnFwdParams {
   int key_norm, mask_mode, causal;
 };
 
-// Persistent, warp-specialised pipeline: one CTA per SM walks tiles t = blockIdx.x, += gridDim.x.
-//   warp 12     : TMEM allocation; lane 0 issues every tcgen05.mma  (S(n) as soon as K lands, then PV(n-1) when P(n-1) is ready)
-//   warps 8-11  : loaders - sticker -> position -> qk and V rows by 16-byte cp.async into swizzled tiles, key scale from sumsq;
-//                 they run up to kStages tiles ahead of the consumers
-//   warps 0-3   : softmax group 0 (tiles n even);  warps 4-7: softmax group 1 (tiles n odd); thread = query row = TMEM lane
-// Shared memory: kStages stage sets {K|P tile, V tile, key scale / position / slot arrays}; P aliases the K tile of its stage
-// (K is dead once S(n) has completed, which s_full certifies).  TMEM: one 256-column region per softmax group: S in
-// [0, kKeyRows), O in [192, 256) for bucket 64 (disjoint) or aliased onto S[0, 64) for bucket 128.
-// mbarriers: kv_full[stage] (128 loader arrivals) -> s_full[group] (tcgen05.commit) -> p_full[group] (128 softmax arrivals)
-//            -> o_full[group] + kv_free[stage] (tcgen05.commit after PV) -> o_free[group] (128 arrivals after the epilogue).
+// Persistent, warp-specialised pipeline; CTA c owns tiles [c*N/grid, (c+1)*N/grid) of the (row, tile-in-row) order.
+//   warp 24     : TMEM allocation; one elected lane issues every tcgen05.mma  (S(k) as soon as block k lands, then PV(k-1) when P(k-1) is ready)
+//   warps 16-19 : epilogue - thread = query row: O(k) from TMEM, divide by the row sum the softmax pair left in shared memory, bf16,
+//                 scatter-store at the unsorted slot, lse.  Keeps the softmax pairs off the tensor pipe's latency.
+//   warps 20-23 : loaders - sticker -> position -> qk and V rows by 16-byte cp.async into the ring slot of the tile, key scale
+//                 from sumsq.  Software-pipelined: sticker loads run two tiles ahead, sumsq / mask loads one tile ahead, and a
+//                 tile is announced (cp.async.wait_group 1) after the next one's copies are queued, so no load latency is exposed.
+//   warps 0-7   : softmax pair 0 (tiles k even);  warps 8-15: softmax pair 1 (tiles k odd).  A pair is two warpgroups sharing a
+//                 tile: thread (half, row) owns half of the row's key window (and half of the output columns in the epilogue)
+// Shared memory: kSlots ring slots {K block, V block} of 128 rows + per-row key scale / position.  Tile k lives in slot k % kSlots
+// and reads its look-back rows from the tail of slot (k-1) % kSlots.  The first tile of a CTA and the first tile of a (batch, head)
+// row have no predecessor in the ring ("fresh"): their look-back rows are gathered into the tail of slot (k-1) % kSlots once the
+// tile that lived there is done (a pipeline bubble once per row).
+// TMEM: one 256-column region per softmax pair.  bucket 64: S in [0,192), O in [192,256); P blocks in place at [32q, 32q+16).
+//       bucket 128: S in [0,256); P blocks compacted to [16q,16q+16) (first half) / [128+16(q-4), ...) (second half), O in [64,128).
+// mbarriers: full[slot] (128 loader arrivals) -> s_full[pair] (tcgen05.commit) -> p_full[pair] (256 softmax arrivals)
+//            -> o_full[pair] + free[slot(s)] (tcgen05.commit after PV) -> o_free[pair] (128 epilogue arrivals).
 //
 // Softmax is single-pass: keys are unit vectors after normalisation, so |s_ij| <= |q_i| * score_scale (Cauchy-Schwarz) and
-// m_i = that bound is a valid stabiliser known before any score is read; masked / self entries give exp2() == 0 exactly.  If a
-// row sums to zero (its only visible key is itself - masked to self_value - or, for absurd norms, everything underflowed) the
-// warp re-does that row with the exact two-pass arithmetic of the reference (row max first), so results never depend on the bound.
-constexpr int kFwdThreads = 416;
-constexpr int kLoaderThreads = 128;
+// m_i = that bound is a valid stabiliser known before any score is read; masked / self entries give exp2() == 0 exactly.  A row
+// that sums to zero can only see itself (masked to self_value): its softmax is uniform over the self columns, set analytically.
+// If any query of a tile has a bound >= 60 (norms so large that a visible key could underflow against the bound) the loader
+// flags the tile and the whole pair runs the exact two-pass arithmetic of the reference (row max first) instead.
+constexpr int kSoftmaxThreads = 256;   // two warpgroups per tile: each thread owns half of its row's window
 // Warp roles by index.  The SM's issue arbiter favours higher warp ids, so the producers that everything else waits on get
-// the top ids: warps 0-7 softmax groups, warps 8-11 loaders, warp 12 MMA issuer.
-constexpr int kFirstLoaderWarp = 8;
-constexpr int kMmaWarp = 12;
+// the top ids: warps 0-15 softmax pairs, warps 16-19 epilogue, warps 20-23 loaders, warp 24 MMA issuer.
+constexpr int kFirstEpiWarp = 16;
+constexpr int kEpiThreads = 128;       // thread = query row = TMEM lane
+constexpr int kFirstLoaderWarp = 20;
+constexpr int kLoaderWarps = 4;
+constexpr int kLoaderThreads = kLoaderWarps * 32;
+constexpr int kMmaWarp = kFirstLoaderWarp + kLoaderWarps;
+constexpr int kFwdThreads = (kMmaWarp + 1) * 32;      // 800 threads -> 72 registers each (setmaxnreg rebalancing was tried: the epilogue and
+                                                      // loader warpgroups spill below 64 registers and the spills cost more than the pairs gain)
+constexpr float kExactBound = 60.f;
 
 template <int BUCKET>
 struct AttnFwdSmem {
   static constexpr int kKeyRows = kQRows + BUCKET;
-  static constexpr int kStages = BUCKET == 64 ? 3 : 2;
-  static constexpr int kKeyBytes = kKeyRows * 128;
-  static constexpr int kPBytes = kQRows * kKeyRows * 2;   // P tile, bf16 (>= kKeyBytes): shares its storage with the K tile
-  // per stage (all tile bases 1024-B aligned):  [ K|P tile | V tile | scale | pos | slot ]
-  static constexpr int kOffKP = 0;
-  static constexpr int kOffV = kPBytes;
-  static constexpr int kOffScale = kOffV + kKeyBytes;                // float[kKeyRows]
-  static constexpr int kOffPos = kOffScale + kKeyRows * 4;           // int[kKeyRows]
-  static constexpr int kOffSlot = kOffPos + kKeyRows * 4;            // int[kQRows]  unsorted slot of each query
-  static constexpr int kStageBytes = ((kOffSlot + kQRows * 4 + 1023) / 1024) * 1024;
-  static constexpr int kOffBar = kStages * kStageBytes;              // 2*kStages + 8 mbarriers
-  static constexpr int kOffTmem = kOffBar + (2 * kStages + 8) * 8;
+  static constexpr int kSlots = 6;
+  static constexpr int kTileBytes = kQRows * 128;                    // 16 KB: 128 rows of one head
+  static constexpr int kOffK = 0;                                    // per slot (1024-B aligned): [ K block | V block ]
+  static constexpr int kOffV = kTileBytes;
+  static constexpr int kSlotBytes = 2 * kTileBytes;
+  static constexpr int kOffMeta = kSlots * kSlotBytes;               // per slot: float scale[128], int pos[128], int exact_tag (+pad)
+  static constexpr int kMetaScale = 0, kMetaPos = kQRows * 4, kMetaTag = 2 * kQRows * 4;
+  static constexpr int kMetaGeo = kMetaTag + 16;                     // int4 {row_bh, base_main (round * T), round_start, -}: written by the loader
+  static constexpr int kMetaBytes = 2 * kQRows * 4 + 32;
+  static constexpr int kOffPart = kOffMeta + kSlots * kMetaBytes;    // float[2 pairs][2 halves][128 rows] partial row sums / maxima
+  // per (pair, tile parity): what the epilogue needs from the softmax pair: float sum[128], float max[128], int slot[128], int row_bh (+pad)
+  static constexpr int kOffFin = kOffPart + 2 * 2 * kQRows * 4;
+  static constexpr int kFinSum = 0, kFinMax = kQRows * 4, kFinSlot = 2 * kQRows * 4, kFinRow = 3 * kQRows * 4;
+  static constexpr int kFinBytes = 3 * kQRows * 4 + 16;
+  static constexpr int kOffBar = kOffFin + 4 * kFinBytes;            // 2*kSlots + 8 mbarriers
+  static constexpr int kOffTmem = kOffBar + (2 * kSlots + 8) * 8;
   static constexpr int kTotal = kOffTmem + 8;
   static constexpr int kDynamic = kTotal + 1024;                     // slack for manual 1024-B alignment
 };
 
 #define RTTS_STAMP(role, n, k) do { if (p.trace != nullptr && blockIdx.x == 0 && (n) < 32) p.trace[((role) * 32 + (n)) * 8 + (k)] = clock64(); } while (0)
 
-// One 32-column chunk of the single-pass softmax for one query row: scores r -> e = exp2(s * key_scale - bound), zero where the
-// key is masked (MASK) or is the query itself (SELF), accumulate the row sum, store the bf16 P chunk (4 x 16 B, swizzled).
-// a_pos / a_scale: shared addresses of key_pos / key_scale at this chunk's first column; a_p: shared address of P row m, k-block
-// of this chunk; c16: index of the chunk's first 16-byte column group inside that k-block; m7 = m & 7 (swizzle phase).
-template <bool MASK, bool SELF>
-__device__ __forceinline__ void soft_chunk(const uint32_t* r, uint32_t a_pos, uint32_t a_scale, uint32_t a_p, int c16, int m7, float neg_bound,
-                                           int q_limit, int q_enc, float* sum4) {
+// TMEM column (relative to the pair's region) of the P block of key chunk q (32 keys -> 16 columns of bf16 pairs).
+template <int BUCKET>
+__device__ __forceinline__ constexpr uint32_t p_col(int q) {
+  return BUCKET == 64 ? 32u * q : (q < 4 ? 16u * q : 128u + 16u * (q - 4));
+}
+
+// One 16-column chunk of the softmax for one query row: scores r -> e = exp2(s * key_scale + neg_m), zero where the key is masked
+// (MASK) or is the query itself (SELF); accumulates the row sum and packs the chunk into 8 registers of bf16 pairs.
+// EXACT: neg_m is minus the true row maximum and masked / self entries take the reference's fill values instead of zero.
+// a_pos / a_scale: shared addresses of key_pos / key_scale at this chunk's first column.
+template <bool MASK, bool SELF, bool EXACT>
+__device__ __forceinline__ void soft_chunk(uint32_t* r, uint32_t a_pos, uint32_t a_scale, float neg_m, int q_limit, int q_enc, float mv,
+                                           float sv, float* sum4, uint32_t* pk) {
+  // Written as whole-chunk stages over r[] in place (16 independent elements per stage), so that every stage has 16-way
+  // instruction-level parallelism and no stage waits on the previous element's latency.
+  float* x = reinterpret_cast<float*>(r);
+  {
+    uint4 s[4];
 #pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4) {
-    const uint4 s0 = lds128(a_scale + q4 * 32), s1 = lds128(a_scale + q4 * 32 + 16);
-    const float ks[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
-                         __uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s1.w)};
-    float e[8];
+    for (int q = 0; q < 4; ++q) s[q] = lds128(a_scale + q * 16);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) e[i] = exp2f(fmaf(__uint_as_float(r[q4 * 8 + i]), ks[i], neg_bound));
-    if (MASK || SELF) {
-      const uint4 p0 = lds128(a_pos + q4 * 32), p1 = lds128(a_pos + q4 * 32 + 16);
-      const int kp[8] = {static_cast<int>(p0.x), static_cast<int>(p0.y), static_cast<int>(p0.z), static_cast<int>(p0.w),
-                         static_cast<int>(p1.x), static_cast<int>(p1.y), static_cast<int>(p1.z), static_cast<int>(p1.w)};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (MASK) e[i] = kp[i] > q_limit ? 0.f : e[i];       // exp2(mask_value - m) == 0
-        if (SELF) e[i] = kp[i] == q_enc ? 0.f : e[i];        // exp2(self_value - m) == 0
+    for (int q = 0; q < 4; ++q) {
+      if (EXACT) {
+        x[q * 4 + 0] *= __uint_as_float(s[q].x); x[q * 4 + 1] *= __uint_as_float(s[q].y);
+        x[q * 4 + 2] *= __uint_as_float(s[q].z); x[q * 4 + 3] *= __uint_as_float(s[q].w);
+      } else {
+        x[q * 4 + 0] = fmaf(x[q * 4 + 0], __uint_as_float(s[q].x), neg_m); x[q * 4 + 1] = fmaf(x[q * 4 + 1], __uint_as_float(s[q].y), neg_m);
+        x[q * 4 + 2] = fmaf(x[q * 4 + 2], __uint_as_float(s[q].z), neg_m); x[q * 4 + 3] = fmaf(x[q * 4 + 3], __uint_as_float(s[q].w), neg_m);
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sum4[i & 3] += e[i];
-    uint4 u;
-    u.x = pack_bf16(e[0], e[1]);
-    u.y = pack_bf16(e[2], e[3]);
-    u.z = pack_bf16(e[4], e[5]);
-    u.w = pack_bf16(e[6], e[7]);
-    sts128(a_p + (((c16 + q4) ^ m7) << 4), u);
   }
+  if (EXACT) {
+    uint4 kq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) kq[q] = lds128(a_pos + q * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kp[4] = {static_cast<int>(kq[q].x), static_cast<int>(kq[q].y), static_cast<int>(kq[q].z), static_cast<int>(kq[q].w)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float sc = x[q * 4 + i];
+        sc = kp[i] > q_limit ? mv : sc;
+        sc = kp[i] == q_enc ? sv : sc;
+        x[q * 4 + i] = sc + neg_m;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = exp2f(x[i]);
+  if (!EXACT && (MASK || SELF)) {
+    uint4 kq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) kq[q] = lds128(a_pos + q * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kp[4] = {static_cast<int>(kq[q].x), static_cast<int>(kq[q].y), static_cast<int>(kq[q].z), static_cast<int>(kq[q].w)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (MASK) x[q * 4 + i] = kp[i] > q_limit ? 0.f : x[q * 4 + i];       // exp2(mask_value - m) == 0
+        if (SELF) x[q * 4 + i] = kp[i] == q_enc ? 0.f : x[q * 4 + i];        // exp2(self_value - m) == 0
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sum4[i & 3] += x[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
+}
+
+// Row maximum of one 16-column chunk with the reference's fill values (exact mode, first pass).
+__device__ __forceinline__ float chunk_max(const uint32_t* r, uint32_t a_pos, uint32_t a_scale, int q_limit, int q_enc, float mv, float sv, float mx) {
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const uint4 s0 = lds128(a_scale + q4 * 16), p0 = lds128(a_pos + q4 * 16);
+    const float ks[4] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w)};
+    const int kp[4] = {static_cast<int>(p0.x), static_cast<int>(p0.y), static_cast<int>(p0.z), static_cast<int>(p0.w)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float sc = __uint_as_float(r[q4 * 4 + i]) * ks[i];
+      sc = kp[i] > q_limit ? mv : sc;
+      sc = kp[i] == q_enc ? sv : sc;
+      mx = fmaxf(mx, sc);
+    }
+  }
+  return mx;
 }
 
 template <int BUCKET>
 __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const AttnFwdParams p, const int num_tiles) {
   using L = AttnFwdSmem<BUCKET>;
-  constexpr int kKeyRows = L::kKeyRows, kStages = L::kStages;
-  constexpr int kQOff = BUCKET;           // first query row inside the key tile
+  constexpr int kKeyRows = L::kKeyRows, kSlots = L::kSlots;
   constexpr int kWin = 2 * BUCKET;        // attention window per query
-  constexpr bool kAliasO = BUCKET == 128; // bucket 128: S fills all 256 columns of the region, O reuses S[0, 64)
-  constexpr uint32_t kColO = kAliasO ? 0 : 192;
+  constexpr int kTail = kQRows - BUCKET;  // first look-back row inside the previous block
+  constexpr uint32_t kColO = BUCKET == 64 ? 192 : 64;
+  constexpr bool kAliasO = BUCKET == 128; // bucket 128: S fills all 256 columns of the region, O reuses columns S no longer needs
   constexpr uint32_t kTmemCols = 512;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
-  uint64_t* kv_full = bars;                    // [kStages]
-  uint64_t* kv_free = bars + kStages;          // [kStages]
-  uint64_t* s_full = bars + 2 * kStages;       // [2]
+  uint64_t* full = bars;                       // [kSlots]
+  uint64_t* slot_free = bars + kSlots;         // [kSlots]
+  uint64_t* s_full = bars + 2 * kSlots;        // [2]
   uint64_t* p_full = s_full + 2;               // [2]
   uint64_t* o_full = s_full + 4;               // [2]
   uint64_t* o_free = s_full + 6;               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int RT = p.R * p.T;
+  const long long t_cta0 = clock64();
+  // this CTA's run of tiles
+  const int g0 = static_cast<int>(static_cast<int64_t>(blockIdx.x) * num_tiles / gridDim.x);
+  const int g1 = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * num_tiles / gridDim.x);
+  const int my_tiles = g1 - g0;
+  // position of a tile inside the problem, advanced incrementally (integer divisions only once per CTA)
+  struct Geo {
+    int row_bh, t_in, round, t_round;     // (batch*H + head), tile in row, hash round, tile in round
+  };
+  const int tiles_per_round = p.T / kQRows;
+  auto geo_at = [&](int g) {
+    Geo x;
+    x.row_bh = g / p.tiles_per_row;
+    x.t_in = g - x.row_bh * p.tiles_per_row;
+    x.round = x.t_in / tiles_per_round;
+    x.t_round = x.t_in - x.round * tiles_per_round;
+    return x;
+  };
+  auto geo_next = [&](Geo& x) {
+    ++x.t_in;
+    if (++x.t_round == tiles_per_round) { x.t_round = 0; ++x.round; }
+    if (x.t_in == p.tiles_per_row) { x.t_in = 0; x.round = 0; x.t_round = 0; ++x.row_bh; }
+  };
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(kv_full + s, kLoaderThreads);
-      mbar_init(kv_free + s, 1);
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(full + s, kLoaderThreads);
+      mbar_init(slot_free + s, 1);
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(s_full + g, 1);
-      mbar_init(p_full + g, kQRows);
+      mbar_init(p_full + g, kSoftmaxThreads);
       mbar_init(o_full + g, 1);
-      mbar_init(o_free + g, kQRows);
+      mbar_init(o_free + g, kEpiThreads);
     }
     fence_mbar_init();
   }
+  if (tid < kSlots) *reinterpret_cast<int*>(smem + L::kOffMeta + tid * L::kMetaBytes + L::kMetaTag) = 0;
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
+  // all 512 columns are ours, so the allocation starts at lane 0, column 0: addresses below are compile-time constants
+  if (*tmem_slot != 0) __trap();
+  constexpr uint32_t tmem = 0;
 
   if (warp == kMmaWarp) {
     // ================================================= MMA issuer =================================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKeyRows, false, false);
+    if (elect_one()) {
+      constexpr uint32_t idesc_lb = umma_idesc_bf16(128, BUCKET, false, false);
+      constexpr uint32_t idesc_main = umma_idesc_bf16(128, kQRows, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, kDh, false, true);
-      auto issue_pv = [&](int m) {      // O(m) = P(m) V(m)
-        const int g = m & 1, st = m % kStages;
-        const uint32_t sP = smem_u32(smem + st * L::kStageBytes + L::kOffKP), sV = smem_u32(smem + st * L::kStageBytes + L::kOffV);
-        mbar_wait(p_full + g, (m >> 1) & 1);
-        RTTS_STAMP(0, m, 2);
-        if (!kAliasO) mbar_wait(o_free + g, ((m >> 1) & 1) ^ 1);      // epilogue of tile m-2 has drained O of this group
-        tc_fence_after_sync();
+      constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+      const uint32_t k_lo0 = umma_desc_lo(smem_u32(smem + L::kOffK), 16);     // K-major operand (Q / K rows)
+      const uint32_t v_lo0 = umma_desc_lo(smem_u32(smem + L::kOffV), 0);      // MN-major operand (V rows)
+      constexpr uint32_t kSlotLo = L::kSlotBytes >> 4, kTailLo = (kTail * 128) >> 4;
+      // Issue order: S(0), S(1), PV(0), S(2), PV(1), ... - S(k) runs one tile ahead of PV so that a pair's softmax never waits for
+      // the tensor pipe - except in front of a fresh tile, whose look-back rows can only be gathered after PV(k-1) released the slot.
+      int k = 0, pv = 0;                 // next S / next PV to issue
+      int t_in_s = g0 % p.tiles_per_row; // tile-in-row of tile k (fresh when 0)
+      while (pv < my_tiles) {
+        const bool fresh_k = k == 0 || t_in_s == 0;
+        if (k < my_tiles && (k == pv || (k == pv + 1 && !fresh_k))) {
+          const int g = k & 1, st = k % kSlots, sp = st == 0 ? kSlots - 1 : st - 1;
+          const uint32_t t_reg = tmem + g * 256;
+          RTTS_STAMP(0, k, 4);
+          mbar_wait(full + st, (k / kSlots) & 1);
+          RTTS_STAMP(0, k, 0);
+          if (kAliasO) mbar_wait(o_free + g, ((k >> 1) & 1) ^ 1);       // S(k) overwrites O(k-2): its epilogue must be done
+          tc_fence_after_sync();
+          // S region of pair g is free: PV(k-2) was issued (program order) after p_full(k-2), i.e. after the last read of S(k-2)
+          const uint32_t q_lo = k_lo0 + st * kSlotLo, lb_lo = k_lo0 + sp * kSlotLo + kTailLo;
 #pragma unroll
-        for (int j = 0; j < kKeyRows / 16; ++j)
-          umma_ss(tmem + g * 256 + kColO, umma_desc_sw128(sP + (j >> 2) * (kQRows * 128) + (j & 3) * 32, 16, 1024),
-                  umma_desc_sw128(sV + j * 2048, 0, 1024), idesc_o, j > 0);
-        umma_commit(o_full + g);
-        umma_commit(kv_free + st);
-        RTTS_STAMP(0, m, 3);      // the stage's K|P and V tiles are no longer read
-      };
-      int n = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
-        const int g = n & 1, st = n % kStages;
-        const uint32_t sKP = smem_u32(smem + st * L::kStageBytes + L::kOffKP);
-        mbar_wait(kv_full + st, (n / kStages) & 1);
-        RTTS_STAMP(0, n, 0);
-        if (kAliasO) mbar_wait(o_free + g, ((n >> 1) & 1) ^ 1);       // S(n) overwrites O(n-2): its epilogue must be done
-        tc_fence_after_sync();
-        // S region of group g is free: PV(n-2) was issued (program order) after p_full(n-2), i.e. after the last read of S(n-2)
+          for (int kk = 0; kk < kDh / 16; ++kk) {
+            umma_ss_lo(t_reg, q_lo + kk * 2, lb_lo + kk * 2, hi, idesc_lb, kk > 0);
+            umma_ss_lo(t_reg + BUCKET, q_lo + kk * 2, q_lo + kk * 2, hi, idesc_main, kk > 0);
+          }
+          umma_commit(s_full + g);
+          RTTS_STAMP(0, k, 1);
+          ++k;
+          if (++t_in_s == p.tiles_per_row) t_in_s = 0;
+        } else {
+          const int m = pv;             // O(m) = P(m) V(m)
+          const int g = m & 1, st = m % kSlots, sp = st == 0 ? kSlots - 1 : st - 1;
+          const uint32_t t_reg = tmem + g * 256;
+          mbar_wait(p_full + g, (m >> 1) & 1);
+          RTTS_STAMP(0, m, 2);
+          if (!kAliasO) mbar_wait(o_free + g, ((m >> 1) & 1) ^ 1);      // epilogue of tile m-2 has drained O of this pair
+          RTTS_STAMP(0, m, 5);
+          tc_fence_after_sync();
+          const uint32_t v_lb = v_lo0 + sp * kSlotLo + kTailLo, v_main = v_lo0 + st * kSlotLo;
 #pragma unroll
-        for (int k = 0; k < kDh / 16; ++k)
-          umma_ss(tmem + g * 256, umma_desc_sw128(sKP + kQOff * 128 + k * 32, 16, 1024), umma_desc_sw128(sKP + k * 32, 16, 1024), idesc_s, k > 0);
-        umma_commit(s_full + g);
-        RTTS_STAMP(0, n, 1);
-        if (n > 0) issue_pv(n - 1);
+          for (int j = 0; j < kKeyRows / 16; ++j) {
+            const uint32_t b_lo = (j * 16 < BUCKET) ? v_lb + j * (2048 >> 4) : v_main + (j * 16 - BUCKET) * (128 >> 4);
+            umma_ts_lo(t_reg + kColO, t_reg + p_col<BUCKET>(j >> 1) + (j & 1) * 8, b_lo, hi, idesc_o, j > 0);
+          }
+          RTTS_STAMP(0, m, 6);
+          umma_commit(o_full + g);
+          // the previous block was this tile's look-back; this block is released here only if no tile will look back at it
+          // (k == m + 1 here, so fresh_k describes tile m + 1)
+          umma_commit(slot_free + sp);
+          if (m + 1 >= my_tiles || (k == m + 1 && fresh_k)) umma_commit(slot_free + st);
+          RTTS_STAMP(0, m, 3);
+          ++pv;
+        }
       }
-      if (n > 0) issue_pv(n - 1);
+    }
+  } else if (warp >= kFirstEpiWarp && warp < kFirstLoaderWarp) {
+    // ================================================= epilogue ===================================================
+    const int m = tid - kFirstEpiWarp * 32;         // query row = TMEM lane (warp % 4 selects the lane quarter)
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    for (int k = 0; k < my_tiles; ++k) {
+      const int g = k & 1;
+      const uint32_t ph = (k >> 1) & 1;
+      const uint32_t a_fin = smem_u32(smem + L::kOffFin) + (g * 2 + ph) * L::kFinBytes;
+      mbar_wait(p_full + g, ph);                     // the pair's row sums / slots are in shared memory
+      const float row_sum = __uint_as_float(lds32(a_fin + L::kFinSum + m * 4));
+      const float row_max = __uint_as_float(lds32(a_fin + L::kFinMax + m * 4));
+      const int64_t slot = static_cast<int64_t>(lds32(a_fin + L::kFinRow)) * RT + static_cast<int>(lds32(a_fin + L::kFinSlot + m * 4));
+      const float inv_sum = 1.f / row_sum;
+      uint4* dst = reinterpret_cast<uint4*>(p.o_rounds + slot * kDh);
+      mbar_wait(o_full + g, ph);
+      tc_fence_after_sync();
+      if (m == 0) RTTS_STAMP(3, k, 0);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + g * 256 + kColO + hh * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(r[q4 * 8 + 0]) * inv_sum, __uint_as_float(r[q4 * 8 + 1]) * inv_sum);
+          u.y = pack_bf16(__uint_as_float(r[q4 * 8 + 2]) * inv_sum, __uint_as_float(r[q4 * 8 + 3]) * inv_sum);
+          u.z = pack_bf16(__uint_as_float(r[q4 * 8 + 4]) * inv_sum, __uint_as_float(r[q4 * 8 + 5]) * inv_sum);
+          u.w = pack_bf16(__uint_as_float(r[q4 * 8 + 6]) * inv_sum, __uint_as_float(r[q4 * 8 + 7]) * inv_sum);
+#ifdef RTTS_EXP_NOEPI
+          if (inv_sum == 123.456f) dst[hh * 4 + q4] = u;
+#else
+          dst[hh * 4 + q4] = u;
+#endif
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(o_free + g);      // O columns of this pair may be overwritten
+#ifdef RTTS_EXP_NOEPI
+      if (inv_sum == 123.456f)
+#endif
+      p.lse_rounds[slot] = (row_max + log2f(row_sum)) * kLn2;
+      if (m == 0) RTTS_STAMP(3, k, 1);
     }
   } else if (warp >= kFirstLoaderWarp && warp < kMmaWarp) {
     // ================================================= loaders ====================================================
     // sticker[slot] = round*T + pos and sorted slots keep the rounds contiguous, so pos = sticker - (slot / T) * T with the
     // round taken from the slot index (no integer division on the load's critical path).
-    const int lt = tid - kFirstLoaderWarp * 32;  // 0..127
-    const int grp = lt >> 3, c = lt & 7;         // 16 row groups of 8 lanes; lane c owns 16-byte chunk c of a row
-    constexpr int kPasses = kKeyRows / 16;
-    int n = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
-      const int st_i = n % kStages;
-      uint8_t* stage = smem + st_i * L::kStageBytes;
-      const uint32_t sKP = smem_u32(stage + L::kOffKP), sV = smem_u32(stage + L::kOffV);
-      float* key_scale = reinterpret_cast<float*>(stage + L::kOffScale);
-      int* key_pos = reinterpret_cast<int*>(stage + L::kOffPos);
-      int* q_slot = reinterpret_cast<int*>(stage + L::kOffSlot);
-      const int row_bh = tile / p.tiles_per_row, t_in = tile - row_bh * p.tiles_per_row;
-      const int b = row_bh / p.H, h = row_bh - b * p.H;
-      const int32_t* stk = p.sticker + static_cast<int64_t>(row_bh) * RT;
-      const int first_slot = t_in * kQRows - BUCKET;
-      const int prev_first = first_slot < 0 ? first_slot + RT : first_slot;
-      const int base_prev = (prev_first / p.T) * p.T, base_main = ((t_in * kQRows) / p.T) * p.T;
-      if (lt == 0) RTTS_STAMP(1, n, 0);
-      int st[kPasses];
+    const int lt = tid - kFirstLoaderWarp * 32;
+    const int grp = lt >> 3, c = lt & 7;         // row groups of 8 lanes; lane c owns 16-byte chunk c of a row
+    constexpr int kGroups = kLoaderThreads / 8;  // rows per pass
+    constexpr int kPasses = kQRows / kGroups;    // lane c also owns the metadata of passes c (and c + 8 when there are 16 passes)
+    constexpr int kLbPasses = BUCKET / kGroups;
+    constexpr int kMetaPerLane = (kPasses + 7) / 8, kLbMetaPerLane = (kLbPasses + 7) / 8;
+    auto load_stickers = [&](int k, const Geo& x, int* st) {   // main rows of local tile k
+      if (k >= my_tiles) return;
+      const int32_t* stk = p.sticker + static_cast<int64_t>(x.row_bh) * RT + x.t_in * kQRows + grp;
 #pragma unroll
-      for (int i = 0; i < kPasses; ++i) {
-        const int j = i * 16 + grp;
-        st[i] = __ldg(stk + (j < BUCKET ? prev_first + j : first_slot + j));
-      }
-      float ssq[kPasses];
-      uint8_t valid[kPasses];
-      if (c == 0) {
-        const float* sq = p.sumsq + static_cast<int64_t>(row_bh) * p.T;
+      for (int i = 0; i < kPasses; ++i) st[i] = __ldg(stk + i * kGroups);
+    };
+    auto load_meta = [&](int k, const Geo& x, int b, int pos, float& ssq, uint32_t& valid) {
+      valid = 1u;
+      ssq = 1.f;
+      if (k >= my_tiles) return;
+      ssq = __ldg(p.sumsq + static_cast<int64_t>(x.row_bh) * p.T + pos);
+      if (p.mask != nullptr) valid = __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos);
+    };
+    auto key_scale_of = [&](float ssq) {
+      float inv;
+      if (p.key_norm == RTTS_KEYNORM_L2) inv = 1.f / fmaxf(sqrtf(ssq), 1e-12f);
+      else inv = rsqrtf(ssq * (1.f / kDh) + 1e-6f) * 0.125f;   // 1/sqrt(64)
+      return inv * p.score_scale_log2;
+    };
+    auto select_pass = [&](const int* a, int which) {       // a[which] with a static register index (which = c or c + 8)
+      int x = 0;
 #pragma unroll
-        for (int i = 0; i < kPasses; ++i) {
-          const int pos = st[i] - ((i * 16 + grp) < BUCKET ? base_prev : base_main);
-          ssq[i] = __ldg(sq + pos);
-          valid[i] = p.mask != nullptr ? __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos) : uint8_t(1);
+      for (int i = 0; i < kPasses; ++i) x = (i == which) ? a[i] : x;
+      return x;
+    };
+    int pos_cur[kPasses], st_nxt[kPasses], st_nn[kPasses];
+    float ssq_cur[2] = {1.f, 1.f}, ssq_nxt[2] = {1.f, 1.f};
+    uint32_t valid_cur[2] = {1u, 1u}, valid_nxt[2] = {1u, 1u};
+    Geo x_cur = geo_at(g0), x_nxt = x_cur, x_nn;
+    geo_next(x_nxt);
+    x_nn = x_nxt;
+    geo_next(x_nn);
+    int b_cur = x_cur.row_bh / p.H, b_nxt = x_nxt.row_bh / p.H;      // batch index (mask row) of tiles k and k+1
+    if (my_tiles > 0) {
+      load_stickers(0, x_cur, pos_cur);
+      load_stickers(1, x_nxt, st_nxt);
+      const int base0 = x_cur.round * p.T;
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) pos_cur[i] -= base0;
+#pragma unroll
+      for (int q = 0; q < kMetaPerLane; ++q) load_meta(0, x_cur, b_cur, select_pass(pos_cur, c + 8 * q), ssq_cur[q], valid_cur[q]);
+    }
+    uint32_t free_parity = 0xffffffffu;    // bit s: parity the next wait on slot_free[s] uses (first wait passes on a fresh barrier)
+    int pending = -1;                      // slot whose copies are in flight and not yet announced
+    auto announce = [&](int st_i) {
+      fence_proxy_async_smem();            // cp.async / st.shared data -> visible to the tensor-core (async) proxy
+      mbar_arrive(full + st_i);
+    };
+    auto wait_free = [&](int s) {
+      const uint32_t par = (free_parity >> s) & 1u;
+      if (!mbar_try_wait(slot_free + s, par)) {      // would block:
+        if (pending >= 0) {                          // do not sit on a tile that has already landed
+          cp_async_wait<0>();
+          announce(pending);
+          pending = -1;
         }
+        mbar_wait(slot_free + s, par);
       }
-      if (lt == 0) RTTS_STAMP(1, n, 1);
-      mbar_wait(kv_free + st_i, ((n / kStages) & 1) ^ 1);       // PV of the tile that used this stage has completed
-      if (lt == 0) RTTS_STAMP(1, n, 2);
+      free_parity ^= 1u << s;
+    };
+    for (int k = 0; k < my_tiles; ++k) {
+      const int st_i = k % kSlots, sp_i = (st_i + kSlots - 1) % kSlots;
+      uint8_t* slot = smem + st_i * L::kSlotBytes;
+      const int row_bh = x_cur.row_bh, t_in = x_cur.t_in;
+      const int b = b_cur, h = row_bh - b * p.H;
       const __nv_bfloat16* qk_b = p.qk + static_cast<int64_t>(b) * p.T * p.ld + h * kDh + c * 8;
       const __nv_bfloat16* v_b = p.v + static_cast<int64_t>(b) * p.T * p.ld + h * kDh + c * 8;
+      if (lt == 0) RTTS_STAMP(1, k, 0);
+      load_stickers(k + 2, x_nn, st_nn);
+      if (k + 1 < my_tiles) {
+        const int base1 = x_nxt.round * p.T;
 #pragma unroll
-      for (int i = 0; i < kPasses; ++i) {
-        const int j = i * 16 + grp;
-        const int64_t off = static_cast<int64_t>(st[i] - (j < BUCKET ? base_prev : base_main)) * p.ld;
-        const uint32_t so = sw128_offset(j, c);
-        cp_async16(sKP + so, qk_b + off);
-        cp_async16(sV + so, v_b + off);
+        for (int i = 0; i < kPasses; ++i) st_nxt[i] -= base1;
       }
-      cp_async_commit();
-      if (c == 0) {
 #pragma unroll
-        for (int i = 0; i < kPasses; ++i) {
-          const int j = i * 16 + grp;
-          const int pos = st[i] - (j < BUCKET ? base_prev : base_main);
-          float inv;
-          if (p.key_norm == RTTS_KEYNORM_L2) inv = 1.f / fmaxf(sqrtf(ssq[i]), 1e-12f);
-          else inv = rsqrtf(ssq[i] * (1.f / kDh) + 1e-6f) * 0.125f;   // 1/sqrt(64)
-          key_scale[j] = inv * p.score_scale_log2;
-          key_pos[j] = valid[i] ? pos : (pos | kPadFlag);
-          if (j >= kQOff) q_slot[j - kQOff] = st[i];
+      for (int q = 0; q < kMetaPerLane; ++q) load_meta(k + 1, x_nxt, b_nxt, select_pass(st_nxt, c + 8 * q), ssq_nxt[q], valid_nxt[q]);
+      if (lt == 0) RTTS_STAMP(1, k, 1);
+      if (k == 0 || t_in == 0) {
+        // no predecessor in the ring: gather the look-back rows (the BUCKET sorted slots before this tile, wrapping to the end
+        // of the row) into the tail of the previous slot once the tile that lived there has been consumed
+        wait_free(sp_i);
+        uint8_t* prev = smem + sp_i * L::kSlotBytes;
+        const uint32_t sKp = smem_u32(prev + L::kOffK), sVp = smem_u32(prev + L::kOffV);
+        uint8_t* meta_p = smem + L::kOffMeta + sp_i * L::kMetaBytes;
+        int first = t_in * kQRows - BUCKET;
+        if (first < 0) first += RT;
+        const int base_prev = (first / p.T) * p.T;
+        const int32_t* stk = p.sticker + static_cast<int64_t>(row_bh) * RT + first + grp;
+        int lb[kLbPasses];
+#pragma unroll
+        for (int i = 0; i < kLbPasses; ++i) lb[i] = __ldg(stk + i * kGroups) - base_prev;
+#pragma unroll
+        for (int i = 0; i < kLbPasses; ++i) {
+          const int j = kTail + i * kGroups + grp;
+          const int64_t off = static_cast<int64_t>(lb[i]) * p.ld;
+          const uint32_t so = sw128_offset(j, c);
+          cp_async16(sKp + so, qk_b + off);
+          cp_async16(sVp + so, v_b + off);
+        }
+#pragma unroll
+        for (int q = 0; q < kLbMetaPerLane; ++q) {
+          if (c + 8 * q >= kLbPasses) break;
+          int my_pos = 0;
+#pragma unroll
+          for (int i = 0; i < kLbPasses; ++i) my_pos = (i == c + 8 * q) ? lb[i] : my_pos;
+          float ssq;
+          uint32_t valid;
+          load_meta(k, x_cur, b, my_pos, ssq, valid);
+          const int j = kTail + (c + 8 * q) * kGroups + grp;
+          reinterpret_cast<float*>(meta_p + L::kMetaScale)[j] = key_scale_of(ssq);
+          reinterpret_cast<int*>(meta_p + L::kMetaPos)[j] = valid ? my_pos : (my_pos | kPadFlag);
         }
       }
+      wait_free(st_i);
+      if (lt == 0) RTTS_STAMP(1, k, 2);
+      const uint32_t sK = smem_u32(slot + L::kOffK), sV = smem_u32(slot + L::kOffV);
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) {
+        const int j = i * kGroups + grp;
+        const int64_t off = static_cast<int64_t>(pos_cur[i]) * p.ld;
+        const uint32_t so = sw128_offset(j, c);
+#ifndef RTTS_EXP_NOLOAD
+        cp_async16(sK + so, qk_b + off);
+        cp_async16(sV + so, v_b + off);
+#else
+        if (off == -12345) { cp_async16(sK + so, qk_b + off); cp_async16(sV + so, v_b + off); }
+#endif
+      }
+      cp_async_commit();
+      {
+        uint8_t* meta = smem + L::kOffMeta + st_i * L::kMetaBytes;
+#pragma unroll
+        for (int q = 0; q < kMetaPerLane; ++q) {
+          const int my_pos = select_pass(pos_cur, c + 8 * q), my_row = (c + 8 * q) * kGroups + grp;
+          const float ks = key_scale_of(ssq_cur[q]);
+          reinterpret_cast<float*>(meta + L::kMetaScale)[my_row] = ks;
+          reinterpret_cast<int*>(meta + L::kMetaPos)[my_row] = valid_cur[q] ? my_pos : (my_pos | kPadFlag);
+          // a query whose score bound could push a visible key below the exp2 underflow: the pair runs this tile in exact mode
+          if (p.score_scale_log2 * p.score_scale_log2 / ks * 1.001f >= kExactBound) *reinterpret_cast<volatile int*>(meta + L::kMetaTag) = k + 1;
+        }
+        if (lt == 0) *reinterpret_cast<int4*>(meta + L::kMetaGeo) = make_int4(row_bh, x_cur.round * p.T, x_cur.t_round == 0, 0);
+      }
+      if (pending >= 0) {
+        cp_async_wait<1>();         // everything but the group just committed has landed
+        announce(pending);
+      }
+      pending = st_i;
+      if (lt == 0) RTTS_STAMP(1, k, 3);
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) { pos_cur[i] = st_nxt[i]; st_nxt[i] = st_nn[i]; }
+      ssq_cur[0] = ssq_nxt[0]; ssq_cur[1] = ssq_nxt[1];
+      valid_cur[0] = valid_nxt[0]; valid_cur[1] = valid_nxt[1];
+      x_cur = x_nxt;
+      x_nxt = x_nn;
+      geo_next(x_nn);
+      b_cur = b_nxt;
+      if (x_nxt.t_in == 0) b_nxt = x_nxt.row_bh / p.H;      // a new (batch, head) row starts at tile k + 1
+    }
+    if (pending >= 0) {
       cp_async_wait<0>();
-      fence_proxy_async_smem();     // cp.async / st.shared data -> visible to the tensor-core (async) proxy
-      mbar_arrive(kv_full + st_i);
-      if (lt == 0) RTTS_STAMP(1, n, 3);
+      announce(pending);
     }
   } else {
-    // ================================================= softmax groups =============================================
-    const int wg = warp >> 2;                       // 0 | 1
-    const int m = tid - wg * 128;                   // query row = TMEM lane
+    // ================================================= softmax pairs ==============================================
+    const int wg = warp >> 3;                       // tile pair 0 | 1
+    const int half = (warp >> 2) & 1;               // which half of the row's window / of the output columns
+    const int m = tid & 127;                        // query row = TMEM lane
     const uint32_t t_row = tmem + wg * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const int win0 = (m / BUCKET) * BUCKET;          // first key-tile row of this query's window
+    const uint32_t a_part = smem_u32(smem + L::kOffPart) + wg * 2 * kQRows * 4;      // float [2 halves][128 rows]
+    const int pair_bar = 1 + wg;                    // named barrier of the 256 threads of this pair
+    const int win0 = (m / BUCKET) * BUCKET;          // first key column of this query's window
     const float mv = p.mask_value_log2, sv = p.self_value_log2;
-    int n = wg;
-    for (int tile = blockIdx.x + wg * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, n += 2) {
-      const uint32_t ph = (n >> 1) & 1;
-      const int st_i = n % kStages;
-      uint8_t* stage = smem + st_i * L::kStageBytes;
-      const float* key_scale = reinterpret_cast<const float*>(stage + L::kOffScale);
-      const int* key_pos = reinterpret_cast<const int*>(stage + L::kOffPos);
-      uint8_t* p_row_base = stage + L::kOffKP;
-      const int row_bh = tile / p.tiles_per_row;
-      if (m == 0) RTTS_STAMP(2, n, 0);
-      mbar_wait(kv_full + st_i, (n / kStages) & 1);  // metadata of this stage is visible
-      const int q_enc = key_pos[kQOff + m];
+    const bool need_mask = p.causal || p.mask != nullptr;
+#ifdef RTTS_COUNT_SPINS
+    long long dbg_spins = 0, dbg_wait = 0;
+#endif
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(kSoftmaxThreads) : "memory"); };
+    for (int k = wg; k < my_tiles; k += 2) {
+      const uint32_t ph = (k >> 1) & 1;
+      const int st_i = k % kSlots, sp_i = (st_i + kSlots - 1) % kSlots;
+      const uint8_t* meta = smem + L::kOffMeta + st_i * L::kMetaBytes;
+      const uint8_t* meta_p = smem + L::kOffMeta + sp_i * L::kMetaBytes;
+      // key column j of the tile: j < BUCKET -> look-back row kTail + j of the previous slot, else main row j - BUCKET
+      const uint32_t a_scale_lb = smem_u32(meta_p + L::kMetaScale) + kTail * 4, a_pos_lb = smem_u32(meta_p + L::kMetaPos) + kTail * 4;
+      const uint32_t a_scale_mn = smem_u32(meta + L::kMetaScale) - BUCKET * 4, a_pos_mn = smem_u32(meta + L::kMetaPos) - BUCKET * 4;
+      if (m == 0 && half == 0) RTTS_STAMP(2, k, 0);
+#ifdef RTTS_COUNT_SPINS
+      {
+        long long tw0 = clock64();
+        while (!mbar_try_wait(full + st_i, (k / kSlots) & 1)) { ++dbg_spins; }
+        dbg_wait += clock64() - tw0;
+      }
+#else
+      mbar_wait(full + st_i, (k / kSlots) & 1);      // metadata of this tile (and of its look-back rows) is visible
+#endif
+      if (m == 0 && half == 0) RTTS_STAMP(2, k, 3);
+      const uint32_t a_meta = smem_u32(meta);
+      const uint4 geo = lds128(a_meta + L::kMetaGeo);
+      const int row_bh = static_cast<int>(geo.x), base_main = static_cast<int>(geo.y);
+      const bool round_start = geo.z != 0;
+      const int q_enc = static_cast<int>(lds32(a_meta + L::kMetaPos + m * 4));
       int q_limit = p.causal ? (q_enc & ~kPadFlag) : (kPadFlag - 1);
       if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && (q_enc & kPadFlag)) q_limit = -1;   // padded query: all masked
-      const int my_slot = reinterpret_cast<const int*>(stage + L::kOffSlot)[m];
+      const int my_slot = base_main + (q_enc & ~kPadFlag);        // unsorted slot = round * T + position
+      const bool exact = static_cast<int>(lds32(a_meta + L::kMetaTag)) == k + 1;
       // stabiliser: |q_i| * score_scale * log2(e) = score_scale_log2^2 / key_scale[own row] for both key-norm variants ...
       // (key_scale = score_scale_log2 / |x| up to the norm's epsilon), times (1 + 2^-10) so rounding cannot push a score above it
-      const float row_bound = p.score_scale_log2 * p.score_scale_log2 / key_scale[kQOff + m] * 1.001f;
+      const float row_bound = p.score_scale_log2 * p.score_scale_log2 / __uint_as_float(lds32(a_meta + L::kMetaScale + m * 4)) * 1.001f;
       mbar_wait(s_full + wg, ph);
       tc_fence_after_sync();
-      if (m == 0) RTTS_STAMP(2, n, 1);
+      if (m == 0 && half == 0) RTTS_STAMP(2, k, 1);
 
+      float row_max = row_bound;
+      if (exact) {
+        float mx = -FLT_MAX;
+#pragma unroll 1
+        for (int c0 = half * (kWin / 2); c0 < (half + 1) * (kWin / 2); c0 += 16) {
+          const int col = win0 + c0;
+          uint32_t r[16];
+          tmem_ld16(t_row + col, r);
+          tmem_ld_wait();
+          mx = chunk_max(r, (col < BUCKET ? a_pos_lb : a_pos_mn) + col * 4, (col < BUCKET ? a_scale_lb : a_scale_mn) + col * 4, q_limit, q_enc, mv, sv, mx);
+        }
+        sts32(a_part + (half * kQRows + m) * 4, __float_as_uint(mx));
+        pair_sync();
+        row_max = fmaxf(__uint_as_float(lds32(a_part + m * 4)), __uint_as_float(lds32(a_part + (kQRows + m) * 4)));
+        pair_sync();               // both halves have read the maxima before the slots are reused for the sums
+      }
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       {
         // The query's own column sits in exactly one 32-column chunk per warp (warp-uniform); the same token can appear a second
         // time only in the look-back chunk of the first tile of a hash round.  Only those chunks pay for the self comparison, and
         // the position mask is skipped altogether when nothing can be masked (non-causal, no padding mask).
-        const bool need_mask = p.causal || p.mask != nullptr;
-        const int t_in_s = tile - row_bh * p.tiles_per_row;
-        const bool round_start = (t_in_s * kQRows) % p.T == 0;
-        const int diag_c0 = (kQOff + (m & ~31)) - win0;           // chunk holding columns of rows 32*(m/32) .. +31
-        const uint32_t a_pos0 = smem_u32(key_pos + win0), a_scale0 = smem_u32(key_scale + win0);
-        const uint32_t a_prow = smem_u32(p_row_base) + m * 128;
-        const int m7 = m & 7;
-        const float neg_bound = -row_bound;
+        const int diag_col = BUCKET + (m & ~31);                  // 32 columns holding the own columns of rows 32*(m/32) .. +31
+        const float neg_m = -row_max;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kWin; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + win0 + c0, r);
+#ifdef RTTS_EXP_NOSOFT
+        for (int c0 = half * (kWin / 2); c0 < half * (kWin / 2) + (p.T < 0 ? 64 : 0); c0 += 16) {
+#else
+        for (int c0 = half * (kWin / 2); c0 < (half + 1) * (kWin / 2); c0 += 16) {
+#endif
           const int col = win0 + c0;
-          const uint32_t a_p = a_prow + (col >> 6) * (kQRows * 128);
-          const int c16 = (col & 63) >> 3;
-          const bool self_chunk = c0 == diag_c0 || (round_start && col < BUCKET);
+          uint32_t r[16], pk[8];
+#ifdef RTTS_TIME_LD
+          const long long t_a = clock64();
+#endif
+          tmem_ld16(t_row + col, r);
+          const uint32_t a_pos = (col < BUCKET ? a_pos_lb : a_pos_mn) + col * 4, a_scale = (col < BUCKET ? a_scale_lb : a_scale_mn) + col * 4;
+          const bool self_chunk = (col & ~31) == diag_col || (round_start && col < BUCKET);
           tmem_ld_wait();
-          if (self_chunk) soft_chunk<true, true>(r, a_pos0 + c0 * 4, a_scale0 + c0 * 4, a_p, c16, m7, neg_bound, q_limit, q_enc, sum4);
-          else if (need_mask) soft_chunk<true, false>(r, a_pos0 + c0 * 4, a_scale0 + c0 * 4, a_p, c16, m7, neg_bound, q_limit, q_enc, sum4);
-          else soft_chunk<false, false>(r, a_pos0 + c0 * 4, a_scale0 + c0 * 4, a_p, c16, m7, neg_bound, q_limit, q_enc, sum4);
+#ifdef RTTS_TIME_LD
+          if (p.trace != nullptr && blockIdx.x == 0 && k < 32 && m == 0 && half == 0) p.trace[(2 * 32 + k) * 8 + 6] += clock64() - t_a;
+#endif
+          if (exact) soft_chunk<true, true, true>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+          else if (self_chunk) soft_chunk<true, true, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+          else if (need_mask) soft_chunk<true, false, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+          else soft_chunk<false, false, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+#ifdef RTTS_TIME_LD
+          const long long t_b = clock64();
+#endif
+          tmem_st8(t_row + p_col<BUCKET>(col >> 5) + ((col >> 4) & 1) * 8, pk);      // P over S columns this thread has already consumed
+#ifdef RTTS_TIME_LD
+          if (p.trace != nullptr && blockIdx.x == 0 && k < 32 && (tid & 31) == 0 && (warp == 0 || warp == 12)) {
+            p.trace[(2 * 32 + k) * 8 + (warp == 0 ? 4 : 7)] += t_b - t_a;      // ld + wait + compute
+          }
+#endif
         }
       }
-      float row_sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      if (m == 0) RTTS_STAMP(2, n, 5);
-      float row_max = row_bound;
-      bool redo = !(row_sum > 1e-30f);
-      if (redo && row_bound < 60.f) {
-        // Every term was exactly zero.  With bound < 60 a visible key cannot underflow (s - bound >= -2*bound > -126), so no key
-        // is visible: only the query itself (masked to self_value) remains and the softmax is uniform over the self columns
+      if (BUCKET == 64) {
+        // the 64 keys outside this query's window contribute nothing: zero their P blocks (one per half)
+        const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const int dead_q = (m < 64 ? 4 : 0) + half;
+        tmem_st16(t_row + p_col<BUCKET>(dead_q), z);
+      }
+      sts32(a_part + (half * kQRows + m) * 4, __float_as_uint((sum4[0] + sum4[1]) + (sum4[2] + sum4[3])));
+      pair_sync();                 // both halves of every row are summed and stored
+      float row_sum = __uint_as_float(lds32(a_part + m * 4)) + __uint_as_float(lds32(a_part + (kQRows + m) * 4));
+      if (m == 0 && half == 0) RTTS_STAMP(2, k, 5);
+      const bool lonely = !exact && !(row_sum > 0.f);
+      if (__any_sync(0xffffffffu, lonely)) {
+        // Every term of a lonely row was exactly zero: with bound < 60 a visible key cannot underflow (s - bound >= -2*bound > -126),
+        // so no key is visible: only the query itself (masked to self_value) remains and the softmax is uniform over the self columns
         // (rp R8 "except when no other targets are available").  The query's own column is known; the same token can appear a
         // second time only when the look-back chunk comes from the previous hash round (first tile of a round).
-        auto set_one = [&](int kc) {
-          *reinterpret_cast<uint16_t*>(p_row_base + (kc >> 6) * (kQRows * 128) + sw128_offset(m, (kc & 63) >> 3) + (kc & 7) * 2) = 0x3F80;
-        };
-        set_one(kQOff + m);
         int n_self = 1;
-        const int t_in = tile - row_bh * p.tiles_per_row;
-        if ((t_in * kQRows) % p.T == 0 && win0 == 0) {       // window starts with the previous round's last chunk
+        const bool dup_possible = round_start && win0 == 0;
+        if (half == 1) {           // the own column lies in the second half of the window: column BUCKET + m
+          uint32_t blk[16];
+          const uint32_t t_blk = t_row + p_col<BUCKET>((BUCKET + (m & ~31)) >> 5);
+          tmem_ld16(t_blk, blk);
+          tmem_ld_wait();
+          if (lonely) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) blk[i] = (i == ((m & 31) >> 1)) ? ((m & 1) ? 0x3F800000u : 0x00003F80u) : 0u;
+          }
+          tmem_st16(t_blk, blk);
+        }
+        if (dup_possible && lonely) {
           // branch-free count first: a duplicate is rare, the scan is not
-          const uint32_t a_pos = smem_u32(key_pos);
           int n_dup = 0;
 #pragma unroll 4
           for (int c4 = 0; c4 < BUCKET; c4 += 4) {
-            const uint4 k4 = lds128(a_pos + c4 * 4);
+            const uint4 k4 = lds128(a_pos_lb + c4 * 4);
             n_dup += (static_cast<int>(k4.x) == q_enc) + (static_cast<int>(k4.y) == q_enc) + (static_cast<int>(k4.z) == q_enc) +
                      (static_cast<int>(k4.w) == q_enc);
           }
-          if (n_dup > 0) {
-            for (int c = 0; c < BUCKET; ++c)
-              if (key_pos[c] == q_enc) set_one(c);
-            n_self += n_dup;
-          }
+          n_self += n_dup;
         }
-        row_sum = static_cast<float>(n_self);
-        row_max = sv;
-        redo = false;
-      }
-      if (__any_sync(0xffffffffu, redo)) {
-        // exact two-pass arithmetic for the rows that need it; the TMEM loads are warp-collective, so every lane walks the loop
-        float mx = -FLT_MAX;
+        if (half == 0 && __any_sync(0xffffffffu, lonely && n_self > 1)) {
+          // the duplicates live in the look-back columns [0, BUCKET): first half of the window of rows with win0 == 0
 #pragma unroll 1
-        for (int c0 = 0; c0 < kWin; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + win0 + c0, r);
-          tmem_ld_wait();
-          if (redo) {
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-              const int kpi = key_pos[win0 + c0 + i];
-              float sc = __uint_as_float(r[i]) * key_scale[win0 + c0 + i];
-              sc = kpi > q_limit ? mv : sc;
-              sc = kpi == q_enc ? sv : sc;
-              mx = fmaxf(mx, sc);
-            }
-          }
-        }
-        float sm = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kWin; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + win0 + c0, r);
-          tmem_ld_wait();
-          if (redo) {
-#pragma unroll 1
-            for (int q8 = 0; q8 < 4; ++q8) {
-              float e8[8];
+          for (int c0 = 0; c0 < BUCKET; c0 += 32) {
+            uint32_t blk[16];
+            const uint32_t t_blk = t_row + p_col<BUCKET>(c0 >> 5);
+            tmem_ld16(t_blk, blk);
+            tmem_ld_wait();
+            if (lonely && n_self > 1) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int col = win0 + c0 + q8 * 8 + i;
-                const int kpi = key_pos[col];
-                float sc = __uint_as_float(r[q8 * 8 + i]) * key_scale[col];
-                sc = kpi > q_limit ? mv : sc;
-                sc = kpi == q_enc ? sv : sc;
-                e8[i] = exp2f(sc - mx);
-                sm += e8[i];
+              for (int i = 0; i < 16; ++i) {
+                const int k0 = static_cast<int>(lds32(a_pos_lb + (c0 + 2 * i) * 4));
+                const int k1 = static_cast<int>(lds32(a_pos_lb + (c0 + 2 * i + 1) * 4));
+                blk[i] = (k0 == q_enc ? 0x00003F80u : 0u) | (k1 == q_enc ? 0x3F800000u : 0u);
               }
-              const int col = win0 + c0 + q8 * 8;
-              uint4 u;
-              u.x = pack_bf16(e8[0], e8[1]); u.y = pack_bf16(e8[2], e8[3]);
-              u.z = pack_bf16(e8[4], e8[5]); u.w = pack_bf16(e8[6], e8[7]);
-              *reinterpret_cast<uint4*>(p_row_base + (col >> 6) * (kQRows * 128) + sw128_offset(m, (col & 63) >> 3)) = u;
             }
+            tmem_st16(t_blk, blk);
           }
         }
-        if (redo) { row_max = mx; row_sum = sm; }
+        if (lonely) {
+          row_sum = static_cast<float>(n_self);
+          row_max = sv;
+        }
       }
-      if (BUCKET == 64) {
-        // the 64 key rows outside this query's window contribute nothing: zero that k-block of P
-        const int dead_block = (m < 64) ? 2 : 0;
-        const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(p_row_base + dead_block * (kQRows * 128) + sw128_offset(m, c)) = z;
+      if (half == 0) {
+        // what the epilogue warps need for this row (double-buffered by tile parity: tile k+4 of this pair writes the same buffer, and
+        // its S is issued only after PV(k+2) has waited for epilogue(k))
+        const uint32_t a_fin = smem_u32(smem + L::kOffFin) + (wg * 2 + ph) * L::kFinBytes;
+        sts32(a_fin + L::kFinSum + m * 4, __float_as_uint(row_sum));
+        sts32(a_fin + L::kFinMax + m * 4, __float_as_uint(row_max));
+        sts32(a_fin + L::kFinSlot + m * 4, static_cast<uint32_t>(my_slot));
+        if (m == 0) sts32(a_fin + L::kFinRow, static_cast<uint32_t>(row_bh));
       }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();       // this thread's TMEM reads of S precede the MMAs that overwrite the region
+      tmem_st_wait();
+      tc_fence_before_sync();       // this thread's TMEM reads of S / writes of P precede the MMAs that consume / overwrite the region
       mbar_arrive(p_full + wg);
-      if (m == 0) RTTS_STAMP(2, n, 2);
-
-      mbar_wait(o_full + wg, ph);
-      tc_fence_after_sync();
-      if (m == 0) RTTS_STAMP(2, n, 3);
-      {
-        const float inv_sum = 1.f / row_sum;
-        const int64_t slot = static_cast<int64_t>(row_bh) * RT + my_slot;
-        uint4* dst = reinterpret_cast<uint4*>(p.o_rounds + slot * kDh);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld32(t_row + kColO + half * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 u;
-            u.x = pack_bf16(__uint_as_float(r[q4 * 8 + 0]) * inv_sum, __uint_as_float(r[q4 * 8 + 1]) * inv_sum);
-            u.y = pack_bf16(__uint_as_float(r[q4 * 8 + 2]) * inv_sum, __uint_as_float(r[q4 * 8 + 3]) * inv_sum);
-            u.z = pack_bf16(__uint_as_float(r[q4 * 8 + 4]) * inv_sum, __uint_as_float(r[q4 * 8 + 5]) * inv_sum);
-            u.w = pack_bf16(__uint_as_float(r[q4 * 8 + 6]) * inv_sum, __uint_as_float(r[q4 * 8 + 7]) * inv_sum);
-            dst[half * 4 + q4] = u;
-          }
-        }
-        p.lse_rounds[slot] = (row_max + log2f(row_sum)) * kLn2;
-      }
-      tc_fence_before_sync();
-      mbar_arrive(o_free + wg);     // O columns of this group may be overwritten
-      if (m == 0) RTTS_STAMP(2, n, 4);
+      if (m == 0 && half == 0) RTTS_STAMP(2, k, 2);
     }
+#ifdef RTTS_COUNT_SPINS
+    if (p.trace != nullptr && (tid & 31) == 0) { p.trace[4 * 32 * 8 + 148 * 32 + blockIdx.x * 32 + warp] = dbg_spins; p.trace[4 * 32 * 8 + 2 * 148 * 32 + blockIdx.x * 32 + warp] = dbg_wait; }
+#endif
   }
+  // debug: per-CTA time until each role is done (trace buffer rows after the 4*32*8 stamps)
+  if (p.trace != nullptr && (tid & 31) == 0) p.trace[4 * 32 * 8 + blockIdx.x * 32 + warp] = clock64() - t_cta0;
   tc_fence_before_sync();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
@@ -566,5 +839,5 @@ extern "C" int rtts_lsh_merge_fwd(const void* o_rounds, const float* lse_rounds,
   return check_launch("rtts_lsh_merge_fwd");
 }
 
-// Debug hook (not part of the product ABI): device buffer of 3*32*8 int64 receiving clock64 stamps of CTA 0.
+// Debug hook (not part of the product ABI): device buffer of 4*32*8 int64 receiving clock64 stamps of CTA 0.
 extern "C" void rtts_debug_set_fwd_trace(void* device_buffer) { g_fwd_trace = static_cast<long long*>(device_buffer); }
