@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
   if (tid == 0) {
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 1, 1);
-    mbar_init(bar_blk, kBwdWorkers);
-    mbar_init(bar_blk + 1, kBwdWorkers);
+    mbar_init(bar_blk, kBwdWorkers / 32);        // one arrival per worker warp
+    mbar_init(bar_blk + 1, kBwdWorkers / 32);
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
   };
   if (warp == kBwdWorkers / 32) {
     // ================================================= MMA issuer =================================================
-    if ((tid & 31) == 0) {
+    if (elect_one()) {      // elect.sync: the compiler then emits the tcgen05.mma sequence straight-line (no per-instruction uniformity loop)
       issue_scores(0);
       issue_scores(1);
       constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, false, true);   // A K-major, B MN-major
@@ -279,24 +279,31 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(bar_blk + (qb & 1));
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(bar_blk + (qb & 1));
     }
     mbar_wait(bar_acc, 0);
     tc_fence_after_sync();
 
     RTTS_BSTAMP(20);
-    // ---- epilogue: warpgroup g handles output columns [16g, 16g+16) of every accumulator row ------------------------------------
+    // ---- epilogue: warpgroup g handles output columns [16g, 16g+16) of every accumulator row.  The bf16 results go through
+    // shared-memory staging tiles (the Pt blocks, dead now) so that the scattered global stores are whole 128-byte rows.
     const int64_t out_base = static_cast<int64_t>(row_bh) * RT;
-    const int64_t my_row = (out_base + q_slot[j]) * kBDh + col0;
+    const uint32_t stage_dv = sPT, stage_dx = sPT + kBlk, stage_dqb = sPT + 2 * kBlk;
+    auto stage16 = [&](uint32_t tile, const float* o) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        sts128(tile + sw128_offset(j, wg * 2 + q), make_uint4(pack_bf16(o[q * 8], o[q * 8 + 1]), pack_bf16(o[q * 8 + 2], o[q * 8 + 3]),
+                                                              pack_bf16(o[q * 8 + 4], o[q * 8 + 5]), pack_bf16(o[q * 8 + 6], o[q * 8 + 7])));
+    };
     {
       uint32_t r[16];
       tmem_ld16(t_row + cDV + col0, r);
       tmem_ld_wait();
-      uint4* dst = reinterpret_cast<uint4*>(p.dv + my_row);
-  #pragma unroll
-      for (int q = 0; q < 2; ++q)
-        dst[q] = make_uint4(pack_bf16(__uint_as_float(r[q * 8]), __uint_as_float(r[q * 8 + 1])), pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3])),
-                            pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5])), pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7])));
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]);
+      stage16(stage_dv, o);
     }
     float g[16], x[16];
     {
@@ -306,7 +313,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
       float dot = 0.f;
   #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const uint4 u = *reinterpret_cast<const uint4*>(smem + L::kOffX + sw128_offset(j, wg * 2 + c));
+        const uint4 u = lds128(sX + sw128_offset(j, wg * 2 + c));
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
   #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -321,6 +328,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
       }
       dot_part[wg * kKeyRows + j] = dot;
     }
+    {
+      // accumulator 1 = query rows 128.. (the look-ahead chunk, BUCKET rows) -> dq_b (rows >= BUCKET are never stored)
+      uint32_t r[16];
+      tmem_ld16(t_row + cDQ1 + col0, r);
+      tmem_ld_wait();
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]);
+      stage16(stage_dqb, o);
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(kBwdWorkers) : "memory");     // workers only: the issuer warp is not part of the epilogue
     {
       // key-normalisation Jacobian dx = G - x |k|^-2 <x, G>  (dh == 64: the L2 and the RMS/sqrt(dh) norms share |k|^-2 = inv^2),
@@ -332,25 +349,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
       float o[16];
   #pragma unroll
       for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]) + g[i] - x[i] * coef;
-      uint4* dst = reinterpret_cast<uint4*>(p.dqk_main + my_row);
-  #pragma unroll
-      for (int q = 0; q < 2; ++q)
-        dst[q] = make_uint4(pack_bf16(o[q * 8], o[q * 8 + 1]), pack_bf16(o[q * 8 + 2], o[q * 8 + 3]), pack_bf16(o[q * 8 + 4], o[q * 8 + 5]),
-                            pack_bf16(o[q * 8 + 6], o[q * 8 + 7]));
+      stage16(stage_dx, o);
     }
+    asm volatile("bar.sync 1, %0;" ::"n"(kBwdWorkers) : "memory");     // staging tiles complete
     {
-      // accumulator 1 = query rows 128.. (the look-ahead chunk, BUCKET rows) -> dq_b.
-      // every warp must execute the (warp-collective) TMEM loads; only rows < BUCKET are stored
-      const bool live = j < BUCKET;
-      uint32_t r[16];
-      tmem_ld16(t_row + cDQ1 + col0, r);
-      tmem_ld_wait();
-      if (live) {
-        uint4* dst_b = reinterpret_cast<uint4*>(p.dq_b + (out_base + q_slot[kKeyRows + j]) * kBDh + col0);
-  #pragma unroll
-        for (int q = 0; q < 2; ++q)
-          dst_b[q] = make_uint4(pack_bf16(__uint_as_float(r[q * 8]), __uint_as_float(r[q * 8 + 1])), pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3])),
-                                pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5])), pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7])));
+      // warp w stores rows [8w, 8w+8) of each output: 8 lanes per 128-byte row, four rows per instruction
+      const int lane = tid & 31, ch = lane & 7;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int row = warp * 8 + it * 4 + (lane >> 3);
+        const int64_t dst_row = (out_base + q_slot[row]) * kBDh;
+        const uint32_t so = sw128_offset(row, ch);
+        reinterpret_cast<uint4*>(p.dv + dst_row)[ch] = lds128(stage_dv + so);
+        reinterpret_cast<uint4*>(p.dqk_main + dst_row)[ch] = lds128(stage_dx + so);
+        if (row < BUCKET) reinterpret_cast<uint4*>(p.dq_b + (out_base + q_slot[kKeyRows + row]) * kBDh)[ch] = lds128(stage_dqb + so);
       }
     }
   }   // workers
