@@ -19,6 +19,7 @@
 // A key's dV / dx are complete inside one CTA; a query chunk's dQ is split between the CTA that owns it as
 // a key chunk (dq_a) and the previous one where it is the look-back chunk (dq_b).
 #include <cfloat>
+#include <type_traits>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -53,324 +54,405 @@ struct AttnBwdParams {
   int key_norm, mask_mode, causal;
 };
 
-#define RTTS_BSTAMP(k) do { if (p.trace != nullptr && blockIdx.x == 0 && tid == 0) p.trace[(k)] = clock64(); } while (0)
-constexpr int kBwdWorkers = 512;     // 4 warpgroups; warpgroup g owns 16 of the 64 query columns of every block / 16 of the 64 output columns
-constexpr int kBwdThreads = kBwdWorkers + 32;   // + one warp whose lane 0 issues every tcgen05.mma (the workers never wait on the issue itself)
+#define RTTS_BSTAMP(k) do { if (p.trace != nullptr && blockIdx.x == 0 && tid == 0 && n == 1) p.trace[(k)] = clock64(); } while (0)
+// Persistent: one CTA per SM walks tiles blockIdx.x, += gridDim.x.
+//   warps 0-15 : workers - 4 warpgroups; warpgroup g owns 16 of the 64 query columns of every block / 16 of the 64 output columns
+//   warp 16    : one elected lane issues every tcgen05.mma
+//   warps 17-18: loaders - gather the next tile's qk / v / dout rows and per-row statistics into the other input stage while
+//                the current tile is being processed (bucket 128 has room for one stage only: no overlap, but no CTA relaunch either)
+constexpr int kBwdWorkers = 512;
+constexpr int kBwdMmaWarp = kBwdWorkers / 32;
+constexpr int kBwdLoaderThreads = 64;
+constexpr int kBwdThreads = kBwdWorkers + 32 + kBwdLoaderThreads;
 
 template <int BUCKET>
 struct AttnBwdSmem {
   static constexpr int kQRows = kKeyRows + BUCKET;      // 192 | 256
   static constexpr int kQBlocks = kQRows / 64;          // 3 | 4
+  static constexpr int kStages = BUCKET == 64 ? 2 : 1;
+  // per input stage (tile bases 1024-B aligned):
   static constexpr int kOffX = 0;                        // qk rows of all query slots (first 128 = keys)
   static constexpr int kOffV = kOffX + kQRows * 128;     // v rows of the key slots
   static constexpr int kOffDO = kOffV + kKeyRows * 128;  // dout rows of the query slots
-  static constexpr int kOffPT = kOffDO + kQRows * 128;   // Pt  tile: kQBlocks blocks of [128 x 64] bf16
-  static constexpr int kOffDS = kOffPT + kQBlocks * kBlk;  // dSt tile: always 4 blocks (pair reads need block 3)
-  static constexpr int kOffQMeta = kOffDS + 4 * kBlk;      // int2[kQRows]  (enc, limit)
-  static constexpr int kOffQStat = kOffQMeta + kQRows * 8; // float2[kQRows] (L*log2e, delta)
+  static constexpr int kOffQEnc = kOffDO + kQRows * 128;   // int[kQRows] position | pad flag (self test)
+  static constexpr int kOffQLim = kOffQEnc + kQRows * 4;   // int[kQRows] largest key position this query may see (mask test)
+  static constexpr int kOffQStat = kOffQLim + kQRows * 4;  // float2[kQRows] (L*log2e, delta)
   static constexpr int kOffQSlot = kOffQStat + kQRows * 8; // int[kQRows] unsorted slot
   static constexpr int kOffKInv = kOffQSlot + kQRows * 4;  // float[kKeyRows] 1/|k|
-  static constexpr int kOffDot = kOffKInv + kKeyRows * 4;  // float[4][kKeyRows] partial <x, G>
-  static constexpr int kOffBar = kOffDot + 4 * kKeyRows * 4;   // 2 mbarriers (S/dP buffers) + 2 (block consumed) + 1 (accumulators)
-  static constexpr int kOffTmem = kOffBar + 5 * 8;
+  static constexpr int kStageBytes = ((kOffKInv + kKeyRows * 4 + 1023) / 1024) * 1024;
+  // shared by all tiles:
+  static constexpr int kOffDS = kStages * kStageBytes;     // dSt tile: always 4 blocks of [128 x 64] bf16 (pair reads need block 3); staging in the epilogue
+  static constexpr int kOffDot = kOffDS + 4 * kBlk;        // float[4][kKeyRows] partial <x, G>
+  static constexpr int kOffBar = kOffDot + 4 * kKeyRows * 4;   // in_full[2], in_free[2], S/dP buffers [2], block written [2], accumulators [1]
+  static constexpr int kOffTmem = kOffBar + 9 * 8;
   static constexpr int kTotal = kOffTmem + 8;
   static constexpr int kDynamic = kTotal + 1024;
 };
 
 template <int BUCKET>
-__global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const AttnBwdParams p) {
+__global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const AttnBwdParams p, const int num_tiles) {
   using L = AttnBwdSmem<BUCKET>;
-  constexpr int kQRows = L::kQRows, kQBlocks = L::kQBlocks;
+  constexpr int kQRows = L::kQRows, kQBlocks = L::kQBlocks, kStages = L::kStages;
   constexpr uint32_t kTmemCols = 512;
-  // TMEM columns: two (St, dPt) buffers so the tensor core works on block qb+1 while block qb is consumed
+  // TMEM columns: two (St, dPt) buffers so the tensor core works on block qb+1 while block qb is consumed.  Pt (bf16 pairs) is
+  // written back over the St columns its thread has consumed and read from there as the A operand of dV += Pt dO.
   constexpr uint32_t cS0 = 0, cDP0 = 64, cS1 = 128, cDP1 = 192, cDV = 256, cG = 320, cDQ0 = 384, cDQ1 = 448;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t sX = smem_u32(smem + L::kOffX), sV = smem_u32(smem + L::kOffV), sDO = smem_u32(smem + L::kOffDO);
-  const uint32_t sPT = smem_u32(smem + L::kOffPT), sDS = smem_u32(smem + L::kOffDS);
-  int2* q_meta = reinterpret_cast<int2*>(smem + L::kOffQMeta);
-  float2* q_stat = reinterpret_cast<float2*>(smem + L::kOffQStat);
-  int* q_slot = reinterpret_cast<int*>(smem + L::kOffQSlot);
-  float* k_inv = reinterpret_cast<float*>(smem + L::kOffKInv);
+  const uint32_t sDS = smem_u32(smem + L::kOffDS);
   float* dot_part = reinterpret_cast<float*>(smem + L::kOffDot);
-  uint64_t* bar_s = reinterpret_cast<uint64_t*>(smem + L::kOffBar);     // [2]
-  uint64_t* bar_blk = bar_s + 2;                                        // [2] 512 worker arrivals: Pt / dSt of a block written
-  uint64_t* bar_acc = bar_s + 4;
+  uint64_t* in_full = reinterpret_cast<uint64_t*>(smem + L::kOffBar);   // [2] loader -> everyone
+  uint64_t* in_free = in_full + 2;                                      // [2] 16 worker-warp arrivals: stage may be refilled
+  uint64_t* bar_s = in_full + 4;                                        // [2] tcgen05.commit: (St, dPt) of a block ready
+  uint64_t* bar_blk = in_full + 6;                                      // [2] 16 worker-warp arrivals: Pt / dSt of a block written
+  uint64_t* bar_acc = in_full + 8;                                      // tcgen05.commit: accumulators of the tile complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int wg = tid >> 7;            // column group 0..3
-  const int j = tid & 127;            // key row = TMEM lane
-  const int row_bh = blockIdx.x / p.tiles_per_row;
-  const int tile = blockIdx.x - row_bh * p.tiles_per_row;
-  const int b = row_bh / p.H, h = row_bh - b * p.H;
   const int RT = p.R * p.T;
-  const int32_t* stk = p.sticker + static_cast<int64_t>(row_bh) * RT;
-  const int first_slot = tile * kKeyRows;      // sorted slot of row 0; rows >= RT wrap to the start
 
-  RTTS_BSTAMP(0);
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   if (tid == 0) {
-    mbar_init(bar_s, 1);
-    mbar_init(bar_s + 1, 1);
-    mbar_init(bar_blk, kBwdWorkers / 32);        // one arrival per worker warp
-    mbar_init(bar_blk + 1, kBwdWorkers / 32);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(in_full + i, kBwdLoaderThreads / 32);
+      mbar_init(in_free + i, kBwdWorkers / 32);
+      mbar_init(bar_s + i, 1);
+      mbar_init(bar_blk + i, kBwdWorkers / 32);        // one arrival per worker warp
+    }
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
-
-  // ---- gather qk / dout rows of the query slots, v rows of the key slots ---------------------------------
-  // pos = sticker - round*T with the round taken from the slot index (see the forward kernel).
-  if (tid < kBwdWorkers) {
-    const int g = tid >> 3, c = tid & 7;          // 64 row groups of 8 lanes
-    constexpr int kPasses = kQRows / 64;
-    const int ahead_first = first_slot + kKeyRows >= RT ? first_slot + kKeyRows - RT : first_slot + kKeyRows;   // look-ahead chunk
-    const int base_main = (first_slot / p.T) * p.T, base_ahead = (ahead_first / p.T) * p.T;
-    int st[kPasses], pos[kPasses];
-#pragma unroll
-    for (int i = 0; i < kPasses; ++i) {
-      const int r = i * 64 + g;
-      st[i] = __ldg(stk + (r < kKeyRows ? first_slot + r : ahead_first + (r - kKeyRows)));
-    }
-    const int64_t head_off = static_cast<int64_t>(h) * kBDh + c * 8;
-#pragma unroll
-    for (int i = 0; i < kPasses; ++i) {
-      const int r = i * 64 + g;
-      pos[i] = st[i] - (r < kKeyRows ? base_main : base_ahead);
-      const int64_t tok = static_cast<int64_t>(b) * p.T + pos[i];
-      const uint32_t so = sw128_offset(r, c);
-      cp_async16(sX + so, p.qk + tok * p.ld + head_off);
-      cp_async16(sDO + so, p.dout + tok * p.ld_do + head_off);
-      if (r < kKeyRows) cp_async16(sV + so, p.v + tok * p.ld + head_off);
-    }
-    cp_async_commit();
-    RTTS_BSTAMP(1);
-    if (c == 0) {
-#pragma unroll
-      for (int i = 0; i < kPasses; ++i) {
-        const int r = i * 64 + g;
-        const int64_t sidx = static_cast<int64_t>(row_bh) * p.T + pos[i];
-        const float lse_v = __ldg(p.lse + sidx), delta_v = __ldg(p.delta + sidx);
-        const bool valid = p.mask == nullptr || __ldg(p.mask + static_cast<int64_t>(b) * p.T + pos[i]) != 0;
-        const int enc = valid ? pos[i] : (pos[i] | kBPadFlag);
-        int limit = p.causal ? pos[i] : (kBPadFlag - 1);
-        if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && !valid) limit = -1;
-        q_meta[r] = make_int2(enc, limit);
-        q_stat[r] = make_float2(lse_v * kBLog2e, delta_v);
-        q_slot[r] = st[i];
-        if (r < kKeyRows) {
-          const float ss = __ldg(p.sumsq + sidx);
-          k_inv[r] = p.key_norm == RTTS_KEYNORM_L2 ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : rsqrtf(ss * (1.f / kBDh) + 1e-6f) * 0.125f;
-        }
-      }
-    }
-    RTTS_BSTAMP(2);
-    cp_async_wait<0>();
-  }
-  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  RTTS_BSTAMP(3);
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  if (*tmem_slot != 0) __trap();      // all 512 columns are ours: the allocation starts at lane 0, column 0
+  constexpr uint32_t tmem = 0;
 
-  // descriptor bases (K-major: lbo 16; MN-major: lbo 0 or one block); a k-step / block offset is an add on the address field
-  const uint64_t dX_k = umma_desc_sw128(sX, 16, 1024), dV_k = umma_desc_sw128(sV, 16, 1024), dDO_k = umma_desc_sw128(sDO, 16, 1024);
-  const uint64_t dPT_k = umma_desc_sw128(sPT, 16, 1024), dDS_k = umma_desc_sw128(sDS, 16, 1024);
-  const uint64_t dDO_n = umma_desc_sw128(sDO, 0, 1024), dX_n = umma_desc_sw128(sX, 0, 1024), dDS_n = umma_desc_sw128(sDS, kBlk, 1024);
-  // issue St / dPt of query block qb into TMEM buffer qb & 1 (one thread)
-  auto issue_scores = [&](int qb) {
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, false, false);
-    const uint32_t cs_ = (qb & 1) ? cS1 : cS0, cdp_ = (qb & 1) ? cDP1 : cDP0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_ss(tmem + cs_, dX_k + (k * 32 >> 4), dX_k + ((qb * 8192 + k * 32) >> 4), idesc, k > 0);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_ss(tmem + cdp_, dV_k + (k * 32 >> 4), dDO_k + ((qb * 8192 + k * 32) >> 4), idesc, k > 0);
-    umma_commit(bar_s + (qb & 1));
-  };
-  if (warp == kBwdWorkers / 32) {
-    // ================================================= MMA issuer =================================================
-    if (elect_one()) {      // elect.sync: the compiler then emits the tcgen05.mma sequence straight-line (no per-instruction uniformity loop)
-      issue_scores(0);
-      issue_scores(1);
-      constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, false, true);   // A K-major, B MN-major
-      constexpr uint32_t idesc_nn = umma_idesc_bf16(128, 64, true, true);
+  if (warp > kBwdMmaWarp) {
+    // ================================================= loaders ====================================================
+    // pos = sticker - round*T with the round taken from the slot index (see the forward kernel).
+    const int lt = tid - (kBwdMmaWarp + 1) * 32;   // 0..63
+    const int g = lt >> 3, c = lt & 7;             // 8 row groups of 8 lanes; lane c owns 16-byte chunk c of a row and the statistics of pass c of every 8
+    int n = 0;
+    for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, ++n) {
+      const int st = n % kStages;
+      uint8_t* stage = smem + st * L::kStageBytes;
+      const uint32_t sX = smem_u32(stage + L::kOffX), sV = smem_u32(stage + L::kOffV), sDO = smem_u32(stage + L::kOffDO);
+      int* q_enc = reinterpret_cast<int*>(stage + L::kOffQEnc);
+      int* q_lim = reinterpret_cast<int*>(stage + L::kOffQLim);
+      float2* q_stat = reinterpret_cast<float2*>(stage + L::kOffQStat);
+      int* q_slot = reinterpret_cast<int*>(stage + L::kOffQSlot);
+      float* k_inv = reinterpret_cast<float*>(stage + L::kOffKInv);
+      const int row_bh = tile_id / p.tiles_per_row, tile = tile_id - row_bh * p.tiles_per_row;
+      const int b = row_bh / p.H, h = row_bh - b * p.H;
+      const int32_t* stk = p.sticker + static_cast<int64_t>(row_bh) * RT;
+      const int first_slot = tile * kKeyRows;      // sorted slot of row 0; rows >= RT wrap to the start
+      const int ahead_first = first_slot + kKeyRows >= RT ? first_slot + kKeyRows - RT : first_slot + kKeyRows;   // look-ahead chunk
+      const int base_main = (first_slot / p.T) * p.T, base_ahead = (ahead_first / p.T) * p.T;
+      const int64_t head_off = static_cast<int64_t>(h) * kBDh + c * 8;
+      mbar_wait(in_free + st, ((n / kStages) & 1) ^ 1);      // the tile that used this stage is completely done
 #pragma unroll 1
-      for (int qb = 0; qb < kQBlocks; ++qb) {
-        mbar_wait(bar_blk + (qb & 1), (qb >> 1) & 1);      // Pt / dSt of block qb written, its (St, dPt) buffer fully consumed
-        tc_fence_after_sync();
+      for (int r0 = 0; r0 < kQRows; r0 += 64) {            // 8 passes of 8 rows
+        int stv[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem + cDV, dPT_k + ((qb * kBlk + k * 32) >> 4), dDO_n + ((qb * 8192 + k * 2048) >> 4), idesc_kn, (qb | k) != 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem + cG, dDS_k + ((qb * kBlk + k * 32) >> 4), dX_n + ((qb * 8192 + k * 2048) >> 4), idesc_kn, (qb | k) != 0);
-        if ((qb & 1) || qb == kQBlocks - 1) {
-          // dQ for query rows [pair*128, +128): A = dSt blocks (pair*2, pair*2+1) read MN-major (M = queries)
-          const int pair = qb >> 1;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_ss(tmem + (pair ? cDQ1 : cDQ0), dDS_n + ((pair * 2 * kBlk + k * 2048) >> 4), dX_n + (k * 2048 >> 4), idesc_nn, k > 0);
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + i * 8 + g;
+          stv[i] = __ldg(stk + (r < kKeyRows ? first_slot + r : ahead_first + (r - kKeyRows)));
         }
-        if (qb + 2 < kQBlocks) issue_scores(qb + 2);     // refill the buffer that was just consumed
+        int my_pos = 0, my_st = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + i * 8 + g;
+          const int pos = stv[i] - (r < kKeyRows ? base_main : base_ahead);
+          const int64_t tok = static_cast<int64_t>(b) * p.T + pos;
+          const uint32_t so = sw128_offset(r, c);
+          cp_async16(sX + so, p.qk + tok * p.ld + head_off);
+          cp_async16(sDO + so, p.dout + tok * p.ld_do + head_off);
+          if (r0 < kKeyRows) cp_async16(sV + so, p.v + tok * p.ld + head_off);
+          if (i == c) { my_pos = pos; my_st = stv[i]; }
+        }
+        {
+          // statistics of row r0 + c*8 + g
+          const int r = r0 + c * 8 + g;
+          const int64_t sidx = static_cast<int64_t>(row_bh) * p.T + my_pos;
+          const float lse_v = __ldg(p.lse + sidx), delta_v = __ldg(p.delta + sidx);
+          const bool valid = p.mask == nullptr || __ldg(p.mask + static_cast<int64_t>(b) * p.T + my_pos) != 0;
+          const int enc = valid ? my_pos : (my_pos | kBPadFlag);
+          int limit = p.causal ? my_pos : (kBPadFlag - 1);
+          if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && !valid) limit = -1;
+          q_enc[r] = enc;
+          q_lim[r] = limit;
+          q_stat[r] = make_float2(lse_v * kBLog2e, delta_v);
+          q_slot[r] = my_st;
+          if (r0 < kKeyRows) {
+            const float ss = __ldg(p.sumsq + sidx);
+            k_inv[r] = p.key_norm == RTTS_KEYNORM_L2 ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : rsqrtf(ss * (1.f / kBDh) + 1e-6f) * 0.125f;
+          }
+        }
       }
-      umma_commit(bar_acc);
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(in_full + st);
+    }
+  } else if (warp == kBwdMmaWarp) {
+    // ================================================= MMA issuer =================================================
+    if (elect_one()) {      // elect.sync: the compiler then emits the tcgen05.mma sequences straight-line (no per-instruction uniformity loop)
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, false, false);
+      constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, false, true);   // A K-major (or TMEM), B MN-major
+      constexpr uint32_t idesc_nn = umma_idesc_bf16(128, 64, true, true);
+      constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+      const uint32_t dDS_k = umma_desc_lo(sDS, 16), dDS_n = umma_desc_lo(sDS, kBlk);
+      uint32_t n_blk[2] = {0, 0};      // completed uses of bar_blk[i]
+      int n = 0;
+      for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, ++n) {
+        const int st = n % kStages;
+        const uint32_t sX = smem_u32(smem + st * L::kStageBytes + L::kOffX), sV = smem_u32(smem + st * L::kStageBytes + L::kOffV),
+                       sDO = smem_u32(smem + st * L::kStageBytes + L::kOffDO);
+        // descriptor bases (K-major: lbo 16; MN-major: lbo 0); a k-step / block offset is an add on the address field
+        const uint32_t dX_k = umma_desc_lo(sX, 16), dV_k = umma_desc_lo(sV, 16), dDO_k = umma_desc_lo(sDO, 16);
+        const uint32_t dDO_n = umma_desc_lo(sDO, 0), dX_n = umma_desc_lo(sX, 0);
+        auto issue_scores = [&](int qb) {      // St / dPt of query block qb into TMEM buffer qb & 1
+          const uint32_t cs_ = (qb & 1) ? cS1 : cS0, cdp_ = (qb & 1) ? cDP1 : cDP0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss_lo(tmem + cs_, dX_k + (k * 32 >> 4), dX_k + ((qb * 8192 + k * 32) >> 4), hi, idesc, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss_lo(tmem + cdp_, dV_k + (k * 32 >> 4), dDO_k + ((qb * 8192 + k * 32) >> 4), hi, idesc, k > 0);
+          umma_commit(bar_s + (qb & 1));
+        };
+        mbar_wait(in_full + st, (n / kStages) & 1);
+        tc_fence_after_sync();
+        // the (St, dPt) buffers are free: every block of the previous tile was consumed before its accumulate MMAs were issued
+        issue_scores(0);
+        issue_scores(1);
+#pragma unroll 1
+        for (int qb = 0; qb < kQBlocks; ++qb) {
+          // Pt / dSt of block qb written, its dPt buffer consumed.  For qb == 0 this also certifies that every worker has finished
+          // the previous tile's epilogue (program order), i.e. the accumulators may be overwritten.
+          mbar_wait(bar_blk + (qb & 1), n_blk[qb & 1] & 1);
+          ++n_blk[qb & 1];
+          tc_fence_after_sync();
+          const uint32_t cs_ = (qb & 1) ? cS1 : cS0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)      // dV += Pt dO: A = Pt from TMEM (16 queries = 8 columns of bf16 pairs per k-step)
+            umma_ts_lo(tmem + cDV, tmem + cs_ + 16 * k, dDO_n + ((qb * 8192 + k * 2048) >> 4), hi, idesc_kn, (qb | k) != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss_lo(tmem + cG, dDS_k + ((qb * kBlk + k * 32) >> 4), dX_n + ((qb * 8192 + k * 2048) >> 4), hi, idesc_kn, (qb | k) != 0);
+          if ((qb & 1) || qb == kQBlocks - 1) {
+            // dQ for query rows [pair*128, +128): A = dSt blocks (pair*2, pair*2+1) read MN-major (M = queries)
+            const int pair = qb >> 1;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_ss_lo(tmem + (pair ? cDQ1 : cDQ0), dDS_n + ((pair * 2 * kBlk + k * 2048) >> 4), dX_n + (k * 2048 >> 4), hi, idesc_nn, k > 0);
+          }
+          if (qb + 2 < kQBlocks) issue_scores(qb + 2);     // refill the buffer that was just consumed
+        }
+        umma_commit(bar_acc);
+      }
     }
   } else {
     // ================================================= workers ====================================================
-    // this thread's key row
-    const float inv = k_inv[j];
-    const float cs = inv * p.score_scale * kBLog2e;   // score scale in log2 units
-    const float gs = inv * p.score_scale;             // folded into dSt so one tile serves dQ and G
-    const int k_enc = q_meta[j].x;
-    const int k_chunk = j / BUCKET;                   // 0|1 for bucket 64, 0 for bucket 128
+    const int wg = tid >> 7;            // column group 0..3
+    const int j = tid & 127;            // key row = TMEM lane
+    const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const float mv = p.mask_value_log2, sv = p.self_value_log2;
     const int col0 = wg * 16;                         // this thread's 16 query columns inside a block
+    const int k_chunk = j / BUCKET;                   // 0|1 for bucket 64, 0 for bucket 128
+    uint32_t n_s[2] = {0, 0};            // completed uses of bar_s[i]
+    int n = 0;
+    for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, ++n) {
+      const int st = n % kStages;
+      uint8_t* stage = smem + st * L::kStageBytes;
+      const uint32_t sX = smem_u32(stage + L::kOffX);
+      const uint32_t a_enc = smem_u32(stage + L::kOffQEnc), a_lim = smem_u32(stage + L::kOffQLim), a_stat = smem_u32(stage + L::kOffQStat);
+      const int* q_slot = reinterpret_cast<const int*>(stage + L::kOffQSlot);
+      const float* k_inv = reinterpret_cast<const float*>(stage + L::kOffKInv);
+      const int row_bh = tile_id / p.tiles_per_row, tile = tile_id - row_bh * p.tiles_per_row;
+      // the look-ahead chunk starts a new hash round (or wraps to round 0): only then can a key's token show up a second time
+      const int ahead_first = tile * kKeyRows + kKeyRows >= RT ? 0 : tile * kKeyRows + kKeyRows;
+      const bool ahead_crosses = ahead_first % p.T == 0;
+      RTTS_BSTAMP(0);
+      mbar_wait(in_full + st, (n / kStages) & 1);
+      RTTS_BSTAMP(3);
+      // this thread's key row
+      const float inv = k_inv[j];
+      const float cs = inv * p.score_scale * kBLog2e;   // score scale in log2 units
+      const float gs = inv * p.score_scale;             // folded into dSt so one tile serves dQ and G
+      const int k_enc = static_cast<int>(lds32(a_enc + j * 4));
 
 #pragma unroll 1
-    for (int qb = 0; qb < kQBlocks; ++qb) {
-      mbar_wait(bar_s + (qb & 1), (qb >> 1) & 1);
+      for (int qb = 0; qb < kQBlocks; ++qb) {
+        mbar_wait(bar_s + (qb & 1), n_s[qb & 1] & 1);
+        ++n_s[qb & 1];
+        tc_fence_after_sync();
+        const uint32_t cs_ = (qb & 1) ? cS1 : cS0, cdp_ = (qb & 1) ? cDP1 : cDP0;
+        // which query chunk is this block, and does it see this warp's key chunk?  (warp-uniform: a dead block costs nothing)
+        const int q_chunk = (qb * 64) / BUCKET;
+        const bool pair_live = (q_chunk == k_chunk) || (q_chunk == k_chunk + 1);
+        // Self entries (key slot == query slot: the key's own column, block j / 64) and second occurrences of its token (only in
+        // look-ahead blocks that belong to another hash round) need the reference's self_value; everything else is a plain
+        // masked softmax term.  The test is kept warp-uniform: the warp's 32 own columns lie in one 32-column half of a block.
+        const bool self_block = (qb == (j >> 6) && (((j & 63) >> 5) == (wg >> 1))) || (qb * 64 >= kKeyRows && ahead_crosses);
+        uint32_t pk[8];
+        uint4 w[2];
+        if (pair_live) {
+          uint32_t rs[16], rp[16];
+          tmem_ld16(t_row + cs_ + col0, rs);
+          tmem_ld16(t_row + cdp_ + col0, rp);
+          const uint32_t a_col = (qb * 64 + col0) * 4;
+          float pe[16], de[16];
+          auto body = [&](auto mask_tag, auto self_tag) {
+            constexpr bool MASK = decltype(mask_tag)::value, SELF = decltype(self_tag)::value;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint4 s0 = lds128(a_stat + a_col * 2 + q4 * 32), s1 = lds128(a_stat + a_col * 2 + q4 * 32 + 16);
+              const float Lv[4] = {__uint_as_float(s0.x), __uint_as_float(s0.z), __uint_as_float(s1.x), __uint_as_float(s1.z)};
+              const float dv_[4] = {__uint_as_float(s0.y), __uint_as_float(s0.w), __uint_as_float(s1.y), __uint_as_float(s1.w)};
+              uint4 lim = make_uint4(0, 0, 0, 0), enc = make_uint4(0, 0, 0, 0);
+              if (MASK) lim = lds128(a_lim + a_col + q4 * 16);
+              if (SELF) enc = lds128(a_enc + a_col + q4 * 16);
+              const int lv[4] = {static_cast<int>(lim.x), static_cast<int>(lim.y), static_cast<int>(lim.z), static_cast<int>(lim.w)};
+              const int ev[4] = {static_cast<int>(enc.x), static_cast<int>(enc.y), static_cast<int>(enc.z), static_cast<int>(enc.w)};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = q4 * 4 + e;
+                float pr = exp2f(fmaf(__uint_as_float(rs[i]), cs, -Lv[e]));
+                if (MASK) pr = k_enc > lv[e] ? 0.f : pr;               // exp2(mask_value - L) == 0
+                float ds = pr * ((__uint_as_float(rp[i]) - dv_[e]) * gs);
+                if (SELF) {
+                  const bool self = k_enc == ev[e];
+                  pr = self ? exp2f(sv - Lv[e]) : pr;                    // self_value overrides the mask; non-zero only for lonely rows
+                  ds = self ? 0.f : ds;                                  // a constant was written: no gradient
+                }
+                pe[i] = pr;
+                de[i] = ds;
+              }
+            }
+          };
+          tmem_ld_wait();
+          const bool need_mask = p.causal || p.mask != nullptr;
+          if (self_block) body(std::true_type{}, std::true_type{});
+          else if (need_mask) body(std::true_type{}, std::false_type{});
+          else body(std::false_type{}, std::false_type{});
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pe[2 * i], pe[2 * i + 1]);
+#pragma unroll
+          for (int q2 = 0; q2 < 2; ++q2) {
+            w[q2].x = pack_bf16(de[q2 * 8 + 0], de[q2 * 8 + 1]); w[q2].y = pack_bf16(de[q2 * 8 + 2], de[q2 * 8 + 3]);
+            w[q2].z = pack_bf16(de[q2 * 8 + 4], de[q2 * 8 + 5]); w[q2].w = pack_bf16(de[q2 * 8 + 6], de[q2 * 8 + 7]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = 0u;
+          w[0] = make_uint4(0, 0, 0, 0);
+          w[1] = make_uint4(0, 0, 0, 0);
+        }
+        tmem_st8(t_row + cs_ + col0, pk);          // Pt over the St columns this thread has consumed
+        sts128(sDS + qb * kBlk + sw128_offset(j, wg * 2), w[0]);
+        sts128(sDS + qb * kBlk + sw128_offset(j, wg * 2 + 1), w[1]);
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(bar_blk + (qb & 1));
+      }
+      mbar_wait(bar_acc, n & 1);
       tc_fence_after_sync();
-      const uint32_t cs_ = (qb & 1) ? cS1 : cS0, cdp_ = (qb & 1) ? cDP1 : cDP0;
-      // which query chunk is this block, and does it see this thread's key chunk?
-      const int q_chunk = (qb * 64) / BUCKET;
-      const bool pair_live = (q_chunk == k_chunk) || (q_chunk == k_chunk + 1);
-      uint32_t rs[16], rp[16];
-      tmem_ld16(t_row + cs_ + col0, rs);
-      tmem_ld16(t_row + cdp_ + col0, rp);
-      int2 qmv[16];
-      float2 qsv[16];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {     // 16-byte broadcast loads of two columns' metadata at a time
-        *reinterpret_cast<int4*>(qmv + 2 * i) = *reinterpret_cast<const int4*>(q_meta + qb * 64 + col0 + 2 * i);
-        *reinterpret_cast<float4*>(qsv + 2 * i) = *reinterpret_cast<const float4*>(q_stat + qb * 64 + col0 + 2 * i);
-      }
-      tmem_ld_wait();
-      float pe[16], de[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int2 qm = qmv[i];
-        const float2 qs = qsv[i];
-        const bool masked = k_enc > qm.y;
-        const bool self = k_enc == qm.x;
-        float sc = __uint_as_float(rs[i]) * cs;
-        sc = masked ? mv : sc;
-        sc = self ? sv : sc;
-        const float pr = pair_live ? exp2f(sc - qs.x) : 0.f;
-        pe[i] = pr;
-        de[i] = (masked || self) ? 0.f : pr * (__uint_as_float(rp[i]) - qs.y) * gs;
-      }
-      uint8_t* pt_row = smem + L::kOffPT + qb * kBlk;
-      uint8_t* ds_row = smem + L::kOffDS + qb * kBlk;
-#pragma unroll
-      for (int q2 = 0; q2 < 2; ++q2) {
-        uint4 u, w;
-        u.x = pack_bf16(pe[q2 * 8 + 0], pe[q2 * 8 + 1]); u.y = pack_bf16(pe[q2 * 8 + 2], pe[q2 * 8 + 3]);
-        u.z = pack_bf16(pe[q2 * 8 + 4], pe[q2 * 8 + 5]); u.w = pack_bf16(pe[q2 * 8 + 6], pe[q2 * 8 + 7]);
-        w.x = pack_bf16(de[q2 * 8 + 0], de[q2 * 8 + 1]); w.y = pack_bf16(de[q2 * 8 + 2], de[q2 * 8 + 3]);
-        w.z = pack_bf16(de[q2 * 8 + 4], de[q2 * 8 + 5]); w.w = pack_bf16(de[q2 * 8 + 6], de[q2 * 8 + 7]);
-        const uint32_t off = sw128_offset(j, wg * 2 + q2);
-        *reinterpret_cast<uint4*>(pt_row + off) = u;
-        *reinterpret_cast<uint4*>(ds_row + off) = w;
-      }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(bar_blk + (qb & 1));
-    }
-    mbar_wait(bar_acc, 0);
-    tc_fence_after_sync();
 
-    RTTS_BSTAMP(20);
-    // ---- epilogue: warpgroup g handles output columns [16g, 16g+16) of every accumulator row.  The bf16 results go through
-    // shared-memory staging tiles (the Pt blocks, dead now) so that the scattered global stores are whole 128-byte rows.
-    const int64_t out_base = static_cast<int64_t>(row_bh) * RT;
-    const uint32_t stage_dv = sPT, stage_dx = sPT + kBlk, stage_dqb = sPT + 2 * kBlk;
-    auto stage16 = [&](uint32_t tile, const float* o) {
+      RTTS_BSTAMP(20);
+      // ---- epilogue: warpgroup g handles output columns [16g, 16g+16) of every accumulator row.  The bf16 results go through
+      // shared-memory staging tiles (the dSt blocks, dead now) so that the scattered global stores are whole 128-byte rows.
+      const int64_t out_base = static_cast<int64_t>(row_bh) * RT;
+      const uint32_t stage_dv = sDS, stage_dx = sDS + kBlk, stage_dqb = sDS + 2 * kBlk;
+      auto stage16 = [&](uint32_t tile, const float* o) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q)
-        sts128(tile + sw128_offset(j, wg * 2 + q), make_uint4(pack_bf16(o[q * 8], o[q * 8 + 1]), pack_bf16(o[q * 8 + 2], o[q * 8 + 3]),
-                                                              pack_bf16(o[q * 8 + 4], o[q * 8 + 5]), pack_bf16(o[q * 8 + 6], o[q * 8 + 7])));
-    };
-    {
-      uint32_t r[16];
-      tmem_ld16(t_row + cDV + col0, r);
-      tmem_ld_wait();
-      float o[16];
+        for (int q = 0; q < 2; ++q)
+          sts128(tile + sw128_offset(j, wg * 2 + q), make_uint4(pack_bf16(o[q * 8], o[q * 8 + 1]), pack_bf16(o[q * 8 + 2], o[q * 8 + 3]),
+                                                                pack_bf16(o[q * 8 + 4], o[q * 8 + 5]), pack_bf16(o[q * 8 + 6], o[q * 8 + 7])));
+      };
+      {
+        uint32_t r[16];
+        tmem_ld16(t_row + cDV + col0, r);
+        tmem_ld_wait();
+        float o[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]);
-      stage16(stage_dv, o);
-    }
-    float g[16], x[16];
-    {
-      uint32_t r[16];
-      tmem_ld16(t_row + cG + col0, r);
-      tmem_ld_wait();
-      float dot = 0.f;
-  #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint4 u = lds128(sX + sw128_offset(j, wg * 2 + c));
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-  #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          x[c * 8 + 2 * e] = bf16_lo(w[e]);
-          x[c * 8 + 2 * e + 1] = bf16_hi(w[e]);
+        for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]);
+        stage16(stage_dv, o);
+      }
+      float g[16], x[16];
+      {
+        uint32_t r[16];
+        tmem_ld16(t_row + cG + col0, r);
+        tmem_ld_wait();
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint4 u = lds128(sX + sw128_offset(j, wg * 2 + c));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            x[c * 8 + 2 * e] = bf16_lo(w[e]);
+            x[c * 8 + 2 * e + 1] = bf16_hi(w[e]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          g[i] = __uint_as_float(r[i]);
+          dot = fmaf(x[i], g[i], dot);
+        }
+        dot_part[wg * kKeyRows + j] = dot;
+      }
+      {
+        // accumulator 1 = query rows 128.. (the look-ahead chunk, BUCKET rows) -> dq_b (rows >= BUCKET are never stored)
+        uint32_t r[16];
+        tmem_ld16(t_row + cDQ1 + col0, r);
+        tmem_ld_wait();
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]);
+        stage16(stage_dqb, o);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kBwdWorkers) : "memory");     // workers only: partial dots complete
+      {
+        // key-normalisation Jacobian dx = G - x |k|^-2 <x, G>  (dh == 64: the L2 and the RMS/sqrt(dh) norms share |k|^-2 = inv^2),
+        // plus this slot's query-role gradient from the keys of this CTA (accumulator 0, row j)
+        const float coef = inv * inv * (dot_part[j] + dot_part[kKeyRows + j] + dot_part[2 * kKeyRows + j] + dot_part[3 * kKeyRows + j]);
+        uint32_t r[16];
+        tmem_ld16(t_row + cDQ0 + col0, r);
+        tmem_ld_wait();
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]) + g[i] - x[i] * coef;
+        stage16(stage_dx, o);
+      }
+      tc_fence_before_sync();       // this thread's reads of the accumulators precede the next tile's MMAs (ordered through bar_blk)
+      asm volatile("bar.sync 1, %0;" ::"n"(kBwdWorkers) : "memory");     // staging tiles complete
+      {
+        // warp w stores rows [8w, 8w+8) of each output: 8 lanes per 128-byte row, four rows per instruction
+        const int lane = tid & 31, ch = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int row = warp * 8 + it * 4 + (lane >> 3);
+          const int64_t dst_row = (out_base + q_slot[row]) * kBDh;
+          const uint32_t so = sw128_offset(row, ch);
+          reinterpret_cast<uint4*>(p.dv + dst_row)[ch] = lds128(stage_dv + so);
+          reinterpret_cast<uint4*>(p.dqk_main + dst_row)[ch] = lds128(stage_dx + so);
+          if (row < BUCKET) reinterpret_cast<uint4*>(p.dq_b + (out_base + q_slot[kKeyRows + row]) * kBDh)[ch] = lds128(stage_dqb + so);
         }
       }
-  #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        g[i] = __uint_as_float(r[i]);
-        dot = fmaf(x[i], g[i], dot);
-      }
-      dot_part[wg * kKeyRows + j] = dot;
+      RTTS_BSTAMP(21);
+      // the input stage (x rows, slots) and the staging tiles have been read by this warp; the next tile's dSt writes wait for all
+      asm volatile("bar.sync 1, %0;" ::"n"(kBwdWorkers) : "memory");
+      if ((tid & 31) == 0) mbar_arrive(in_free + st);
+      RTTS_BSTAMP(22);
     }
-    {
-      // accumulator 1 = query rows 128.. (the look-ahead chunk, BUCKET rows) -> dq_b (rows >= BUCKET are never stored)
-      uint32_t r[16];
-      tmem_ld16(t_row + cDQ1 + col0, r);
-      tmem_ld_wait();
-      float o[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]);
-      stage16(stage_dqb, o);
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kBwdWorkers) : "memory");     // workers only: the issuer warp is not part of the epilogue
-    {
-      // key-normalisation Jacobian dx = G - x |k|^-2 <x, G>  (dh == 64: the L2 and the RMS/sqrt(dh) norms share |k|^-2 = inv^2),
-      // plus this slot's query-role gradient from the keys of this CTA (accumulator 0, row j)
-      const float coef = inv * inv * (dot_part[j] + dot_part[kKeyRows + j] + dot_part[2 * kKeyRows + j] + dot_part[3 * kKeyRows + j]);
-      uint32_t r[16];
-      tmem_ld16(t_row + cDQ0 + col0, r);
-      tmem_ld_wait();
-      float o[16];
-  #pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]) + g[i] - x[i] * coef;
-      stage16(stage_dx, o);
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kBwdWorkers) : "memory");     // staging tiles complete
-    {
-      // warp w stores rows [8w, 8w+8) of each output: 8 lanes per 128-byte row, four rows per instruction
-      const int lane = tid & 31, ch = lane & 7;
-#pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int row = warp * 8 + it * 4 + (lane >> 3);
-        const int64_t dst_row = (out_base + q_slot[row]) * kBDh;
-        const uint32_t so = sw128_offset(row, ch);
-        reinterpret_cast<uint4*>(p.dv + dst_row)[ch] = lds128(stage_dv + so);
-        reinterpret_cast<uint4*>(p.dqk_main + dst_row)[ch] = lds128(stage_dx + so);
-        if (row < BUCKET) reinterpret_cast<uint4*>(p.dq_b + (out_base + q_slot[kKeyRows + row]) * kBDh)[ch] = lds128(stage_dqb + so);
-      }
-    }
-  }   // workers
-  RTTS_BSTAMP(21);
+  }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
-  RTTS_BSTAMP(22);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -418,7 +500,8 @@ int launch_attn_bwd(const AttnBwdParams& p, int ctas, cudaStream_t stream) {
     if (e != cudaSuccess) return fail(kErrCuda, "rtts_lsh_attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  lsh_attn_bwd_kernel<BUCKET><<<ctas, kBwdThreads, L::kDynamic, stream>>>(p);
+  const int grid = ctas < kNumSMs ? ctas : kNumSMs;     // persistent: one CTA per SM
+  lsh_attn_bwd_kernel<BUCKET><<<grid, kBwdThreads, L::kDynamic, stream>>>(p, ctas);
   return check_launch("rtts_lsh_attn_bwd");
 }
 
