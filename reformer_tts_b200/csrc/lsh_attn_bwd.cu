@@ -89,6 +89,82 @@ struct AttnBwdSmem {
   static constexpr int kDynamic = kTotal + 1024;
 };
 
+  // Gather one tile's qk / dout rows of the query slots, v rows of the key slots and the per-row statistics into an input stage.
+  // Executed by `nthr` threads (lt = 0..nthr-1): groups of 8 lanes copy a row (lane c = 16-byte chunk c); lane c also owns the
+  // statistics of pass c of every 8 passes.  pos = sticker - round*T with the round taken from the slot index (see the forward kernel).
+template <int BUCKET, int NTHR>
+__device__ __forceinline__ void bwd_gather_tile(const AttnBwdParams& p, uint8_t* smem, uint64_t* in_full, int tile_id, int st, int lt) {
+  using L = AttnBwdSmem<BUCKET>;
+  constexpr int kQRows = L::kQRows;
+  constexpr int G = NTHR >> 3;                       // rows per pass
+  constexpr int kPasses = (kQRows + G - 1) / G;      // 24 | 32 passes of 8 rows (loader warps), 3 | 4 of 64 rows (workers)
+  constexpr int kStatRounds = (kPasses + 7) / 8;     // lane c owns the statistics of passes c, c + 8, ...
+  const int RT = p.R * p.T;
+  const int g = lt >> 3, c = lt & 7;
+  uint8_t* stage = smem + st * L::kStageBytes;
+  const uint32_t sX = smem_u32(stage + L::kOffX), sV = smem_u32(stage + L::kOffV), sDO = smem_u32(stage + L::kOffDO);
+  int* q_enc = reinterpret_cast<int*>(stage + L::kOffQEnc);
+  int* q_lim = reinterpret_cast<int*>(stage + L::kOffQLim);
+  float2* q_stat = reinterpret_cast<float2*>(stage + L::kOffQStat);
+  int* q_slot = reinterpret_cast<int*>(stage + L::kOffQSlot);
+  float* k_inv = reinterpret_cast<float*>(stage + L::kOffKInv);
+  const int row_bh = tile_id / p.tiles_per_row, tile = tile_id - row_bh * p.tiles_per_row;
+  const int b = row_bh / p.H, h = row_bh - b * p.H;
+  const int32_t* stk = p.sticker + static_cast<int64_t>(row_bh) * RT;
+  const int first_slot = tile * kKeyRows;      // sorted slot of row 0; rows >= RT wrap to the start
+  const int ahead_first = first_slot + kKeyRows >= RT ? first_slot + kKeyRows - RT : first_slot + kKeyRows;   // look-ahead chunk
+  const int base_main = (first_slot / p.T) * p.T, base_ahead = (ahead_first / p.T) * p.T;
+  const int64_t head_off = static_cast<int64_t>(h) * kBDh + c * 8;
+  // all sticker loads first (one exposed latency per tile), then every row copy, then the statistics while the copies fly
+  int stv[kPasses];
+#pragma unroll
+  for (int i = 0; i < kPasses; ++i) {
+    const int r = i * G + g;
+    stv[i] = r < kQRows ? __ldg(stk + (r < kKeyRows ? first_slot + r : ahead_first + (r - kKeyRows))) : 0;
+  }
+#pragma unroll
+  for (int i = 0; i < kPasses; ++i) {
+    const int r = i * G + g;
+    if (r < kQRows) {
+      const int pos = stv[i] - (r < kKeyRows ? base_main : base_ahead);
+      const int64_t tok = static_cast<int64_t>(b) * p.T + pos;
+      const uint32_t so = sw128_offset(r, c);
+      cp_async16(sX + so, p.qk + tok * p.ld + head_off);
+      cp_async16(sDO + so, p.dout + tok * p.ld_do + head_off);
+      if (r < kKeyRows) cp_async16(sV + so, p.v + tok * p.ld + head_off);
+    }
+  }
+  cp_async_commit();
+#pragma unroll
+  for (int q = 0; q < kStatRounds; ++q) {
+    int my_st = 0;
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i) my_st = (i == q * 8 + c) ? stv[i] : my_st;
+    const int r = (q * 8 + c) * G + g;
+    if (q * 8 + c < kPasses && r < kQRows) {
+      const int my_pos = my_st - (r < kKeyRows ? base_main : base_ahead);
+      const int64_t sidx = static_cast<int64_t>(row_bh) * p.T + my_pos;
+      const float lse_v = __ldg(p.lse + sidx), delta_v = __ldg(p.delta + sidx);
+      const bool valid = p.mask == nullptr || __ldg(p.mask + static_cast<int64_t>(b) * p.T + my_pos) != 0;
+      const int enc = valid ? my_pos : (my_pos | kBPadFlag);
+      int limit = p.causal ? my_pos : (kBPadFlag - 1);
+      if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && !valid) limit = -1;
+      q_enc[r] = enc;
+      q_lim[r] = limit;
+      q_stat[r] = make_float2(lse_v * kBLog2e, delta_v);
+      q_slot[r] = my_st;
+      if (r < kKeyRows) {
+        const float ss = __ldg(p.sumsq + sidx);
+        k_inv[r] = p.key_norm == RTTS_KEYNORM_L2 ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : rsqrtf(ss * (1.f / kBDh) + 1e-6f) * 0.125f;
+      }
+    }
+  }
+  cp_async_wait<0>();
+  fence_proxy_async_smem();
+  __syncwarp();
+  if ((lt & 31) == 0) mbar_arrive(in_full + st);
+}
+
 template <int BUCKET>
 __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const AttnBwdParams p, const int num_tiles) {
   using L = AttnBwdSmem<BUCKET>;
@@ -115,7 +191,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(in_full + i, kBwdLoaderThreads / 32);
+      mbar_init(in_full + i, (kStages == 2 ? kBwdLoaderThreads : kBwdWorkers) / 32);
       mbar_init(in_free + i, kBwdWorkers / 32);
       mbar_init(bar_s + i, 1);
       mbar_init(bar_blk + i, kBwdWorkers / 32);        // one arrival per worker warp
@@ -129,73 +205,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
   if (*tmem_slot != 0) __trap();      // all 512 columns are ours: the allocation starts at lane 0, column 0
   constexpr uint32_t tmem = 0;
 
+  constexpr bool kPrefetch = kStages == 2;       // one stage only (bucket 128): nothing to overlap, so the workers gather themselves
+
   if (warp > kBwdMmaWarp) {
     // ================================================= loaders ====================================================
-    // pos = sticker - round*T with the round taken from the slot index (see the forward kernel).
-    const int lt = tid - (kBwdMmaWarp + 1) * 32;   // 0..63
-    const int g = lt >> 3, c = lt & 7;             // 8 row groups of 8 lanes; lane c owns 16-byte chunk c of a row and the statistics of pass c of every 8
-    int n = 0;
-    for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, ++n) {
-      const int st = n % kStages;
-      uint8_t* stage = smem + st * L::kStageBytes;
-      const uint32_t sX = smem_u32(stage + L::kOffX), sV = smem_u32(stage + L::kOffV), sDO = smem_u32(stage + L::kOffDO);
-      int* q_enc = reinterpret_cast<int*>(stage + L::kOffQEnc);
-      int* q_lim = reinterpret_cast<int*>(stage + L::kOffQLim);
-      float2* q_stat = reinterpret_cast<float2*>(stage + L::kOffQStat);
-      int* q_slot = reinterpret_cast<int*>(stage + L::kOffQSlot);
-      float* k_inv = reinterpret_cast<float*>(stage + L::kOffKInv);
-      const int row_bh = tile_id / p.tiles_per_row, tile = tile_id - row_bh * p.tiles_per_row;
-      const int b = row_bh / p.H, h = row_bh - b * p.H;
-      const int32_t* stk = p.sticker + static_cast<int64_t>(row_bh) * RT;
-      const int first_slot = tile * kKeyRows;      // sorted slot of row 0; rows >= RT wrap to the start
-      const int ahead_first = first_slot + kKeyRows >= RT ? first_slot + kKeyRows - RT : first_slot + kKeyRows;   // look-ahead chunk
-      const int base_main = (first_slot / p.T) * p.T, base_ahead = (ahead_first / p.T) * p.T;
-      const int64_t head_off = static_cast<int64_t>(h) * kBDh + c * 8;
-      mbar_wait(in_free + st, ((n / kStages) & 1) ^ 1);      // the tile that used this stage is completely done
-#pragma unroll 1
-      for (int r0 = 0; r0 < kQRows; r0 += 64) {            // 8 passes of 8 rows
-        int stv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + i * 8 + g;
-          stv[i] = __ldg(stk + (r < kKeyRows ? first_slot + r : ahead_first + (r - kKeyRows)));
-        }
-        int my_pos = 0, my_st = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + i * 8 + g;
-          const int pos = stv[i] - (r < kKeyRows ? base_main : base_ahead);
-          const int64_t tok = static_cast<int64_t>(b) * p.T + pos;
-          const uint32_t so = sw128_offset(r, c);
-          cp_async16(sX + so, p.qk + tok * p.ld + head_off);
-          cp_async16(sDO + so, p.dout + tok * p.ld_do + head_off);
-          if (r0 < kKeyRows) cp_async16(sV + so, p.v + tok * p.ld + head_off);
-          if (i == c) { my_pos = pos; my_st = stv[i]; }
-        }
-        {
-          // statistics of row r0 + c*8 + g
-          const int r = r0 + c * 8 + g;
-          const int64_t sidx = static_cast<int64_t>(row_bh) * p.T + my_pos;
-          const float lse_v = __ldg(p.lse + sidx), delta_v = __ldg(p.delta + sidx);
-          const bool valid = p.mask == nullptr || __ldg(p.mask + static_cast<int64_t>(b) * p.T + my_pos) != 0;
-          const int enc = valid ? my_pos : (my_pos | kBPadFlag);
-          int limit = p.causal ? my_pos : (kBPadFlag - 1);
-          if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && !valid) limit = -1;
-          q_enc[r] = enc;
-          q_lim[r] = limit;
-          q_stat[r] = make_float2(lse_v * kBLog2e, delta_v);
-          q_slot[r] = my_st;
-          if (r0 < kKeyRows) {
-            const float ss = __ldg(p.sumsq + sidx);
-            k_inv[r] = p.key_norm == RTTS_KEYNORM_L2 ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : rsqrtf(ss * (1.f / kBDh) + 1e-6f) * 0.125f;
-          }
-        }
+    if (kPrefetch) {
+      const int lt = tid - (kBwdMmaWarp + 1) * 32;   // 0..63
+      int n = 0;
+      for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, ++n) {
+        const int st = n % kStages;
+        mbar_wait(in_free + st, ((n / kStages) & 1) ^ 1);      // the tile that used this stage is completely done
+        bwd_gather_tile<BUCKET, kBwdLoaderThreads>(p, smem, in_full, tile_id, st, lt);
       }
-      cp_async_commit();
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(in_full + st);
     }
   } else if (warp == kBwdMmaWarp) {
     // ================================================= MMA issuer =================================================
@@ -275,6 +296,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
       const int ahead_first = tile * kKeyRows + kKeyRows >= RT ? 0 : tile * kKeyRows + kKeyRows;
       const bool ahead_crosses = ahead_first % p.T == 0;
       RTTS_BSTAMP(0);
+      if (!kPrefetch) bwd_gather_tile<BUCKET, kBwdWorkers>(p, smem, in_full, tile_id, st, tid);      // (the previous tile ended with a barrier of all workers)
       mbar_wait(in_full + st, (n / kStages) & 1);
       RTTS_BSTAMP(3);
       // this thread's key row
