@@ -26,7 +26,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NCU_DRAM_BYTES_FWD_DEC_CFG2 = 47_672_576 + 172_148_736      # profiles/r1_attn_fwd_ncu_full.txt (read + write), B=20 T=1024 R=8 bucket 64
+NCU_DRAM_BYTES_FWD_DEC_CFG2 = 61_466_880 + 120_846_848      # profiles/r1_attn_v2_ncu_full.txt (read + write), B=20 T=1024 R=8 bucket 64
 DEFAULT_CONFIG = "bucket-size-64-18-06"       # BASELINE.json configs[1]: the configuration the metric is quoted on
 PHONEMES, FRAMES, N_MELS = 200, 800, 80       # "~200 phonemes -> ~800x80 mel frames" (BASELINE.json configs[0])
 
@@ -264,7 +264,7 @@ def run_ours(args, kwargs, world, rank, local_rank):
             roofline["launches_timed"] = kernel_ms[key_fwd]["count"]
             roofline["algorithmic_flop_per_launch"] = flops_fwd
             # DRAM bytes of one launch from the committed `ncu --set full` capture of this kernel at the benched shape
-            # (profiles/r1_attn_fwd_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum); algorithmic minimum beside it
+            # (profiles/r1_attn_v2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum); algorithmic minimum beside it
             if (b, t, r, bucket) == (20, 1024, 8, 64):
                 roofline["traffic"] = NCU_DRAM_BYTES_FWD_DEC_CFG2
             roofline["algorithmic_min_bytes"] = 2 * b * t * d * 2 + r * b * t * d * 2 + r * b * 8 * t * 4
@@ -292,7 +292,13 @@ def run_ours(args, kwargs, world, rank, local_rank):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroying a communicator whose collectives were captured into a CUDA graph hung the
+        # workers after the result line had been printed (2 GPUs, torch 2.11 / NCCL 2.28).  Everyone syncs, flushes and exits.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
