@@ -27,7 +27,8 @@ struct GemmCfg {
   static constexpr int kBTileBytes = BN * kBK * 2;            // 16 | 32 KB
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStages = BN == 128 ? 6 : 4;           // 192 KB of operand ring either way
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kOffStaging = kStages * kStageBytes + 256;                 // after the barriers: 4 epilogue warps x (output tile + gate tile) x 32 rows x 128 B
+  static constexpr int kSmem = kOffStaging + 4 * 8192 + 1024 /*align*/;
   static constexpr uint32_t kTmemCols = 2 * BN;               // two accumulators: the epilogue of tile i overlaps the main loop of tile i+1
 };
 
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;       // running k-block counter across work items: the operand ring never drains between tiles
       for (int w = blockIdx.x; w < p.work; w += gridDim.x) {
         const int split = w / p.tiles_mn, tile = w - split * p.tiles_mn;
@@ -126,8 +127,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {      // elect.sync: straight-line tcgen05.mma issue (a plain lane test makes the compiler wrap every MMA in a uniformity loop)
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN, B_MN);
+      constexpr uint32_t hi = umma_desc_hi_sw128(1024);
       int it = 0, t = 0;
       for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++t) {
         const int acc = t & 1;
@@ -138,11 +140,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           mbar_wait(full_bar + s, (it / kStages) & 1);
           tc_fence_after_sync();
           const uint32_t sa = s_base + s * Cfg::kStageBytes, sb = sa + kATileBytes;
-          const uint64_t da0 = A_MN ? umma_desc_sw128(sa, kATileBytes / 2, 1024) : umma_desc_sw128(sa, 16, 1024);
-          const uint64_t db0 = B_MN ? umma_desc_sw128(sb, 64 * kBK * 2, 1024) : umma_desc_sw128(sb, 16, 1024);
+          const uint32_t da0 = A_MN ? umma_desc_lo(sa, kATileBytes / 2) : umma_desc_lo(sa, 16);
+          const uint32_t db0 = B_MN ? umma_desc_lo(sb, 64 * kBK * 2) : umma_desc_lo(sb, 16);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            umma_ss(tmem + acc * BN, da0 + ((A_MN ? k * 2048 : k * 32) >> 4), db0 + ((B_MN ? k * 2048 : k * 32) >> 4), idesc, (kb | k) != 0);
+            umma_ss_lo(tmem + acc * BN, da0 + ((A_MN ? k * 2048 : k * 32) >> 4), db0 + ((B_MN ? k * 2048 : k * 32) >> 4), hi, idesc, (kb | k) != 0);
           umma_commit(empty_bar + s);          // smem slot reusable once these MMAs retire
         }
         umma_commit(acc_full + acc);           // accumulator complete
@@ -152,6 +154,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = output rows m0 + that range ----
     const int quarter = warp & 3;
     const int epi = p.epilogue;
+    // Staging tile of this warp (32 rows x 128 B, 16-byte chunks XOR-swizzled by the row): the thread-per-row register layout that
+    // tcgen05.ld produces is transposed through it so that global accesses are whole 128-byte row segments (four rows per warp
+    // instruction) instead of 32 rows x 16 B.
+    const uint32_t stage = s_base + Cfg::kOffStaging + quarter * 8192, gstage = stage + 4096;      // output rows | gate rows
+    const int srow = lane >> 3, sch = lane & 7;      // coalesced phase: lane -> (row within a group of four, 16-byte chunk)
     int t = 0;
     for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++t) {
       const int split = w / p.tiles_mn, tile = w - split * p.tiles_mn;
@@ -181,10 +188,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           for (int i = 0; i < 32; ++i) r[i] = fmaxf(r[i], 0.f);
         }
         if (epi & RTTS_EPI_GATE) {
-          const uint4* g = reinterpret_cast<const uint4*>(p.gate + static_cast<int64_t>(row) * p.ldgate + col);
+          // gate rows [32 x 64 B] -> staging (coalesced: 4 lanes per row, 8 rows per instruction) -> this thread's row
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int gr = it * 8 + (lane >> 2), gc = lane & 3;
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.gate + static_cast<int64_t>(m0 + quarter * 32 + gr) * p.ldgate + col) + gc);
+            sts128(gstage + gr * 128 + ((gc ^ (gr & 7)) << 4), u);
+          }
+          __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 u = __ldg(g + q);
+            const uint4 u = lds128(gstage + lane * 128 + ((q ^ (lane & 7)) << 4));
             const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -193,14 +207,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
             }
           }
         }
+        if (epi & RTTS_EPI_GATE) __syncwarp();       // every lane has read its gate row: the staging tile is free again
         if (epi & RTTS_EPI_OUT_BF16) {
-          uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + col);
+          // two 32-column chunks make one 128-byte row segment
+          const int half = (c0 >> 5) & 1;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 u;
             u.x = pack_bf16(r[q * 8 + 0], r[q * 8 + 1]); u.y = pack_bf16(r[q * 8 + 2], r[q * 8 + 3]);
             u.z = pack_bf16(r[q * 8 + 4], r[q * 8 + 5]); u.w = pack_bf16(r[q * 8 + 6], r[q * 8 + 7]);
-            dst[q] = u;
+            sts128(stage + lane * 128 + (((half * 4 + q) ^ (lane & 7)) << 4), u);
+          }
+          if (half == 1) {
+            __syncwarp();
+            __nv_bfloat16* base = static_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(m0 + quarter * 32) * p.ldc + (col - 32);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + srow;
+              reinterpret_cast<uint4*>(base + static_cast<int64_t>(rr) * p.ldc)[sch] = lds128(stage + rr * 128 + ((sch ^ (rr & 7)) << 4));
+            }
+            __syncwarp();
           }
         } else if (epi & RTTS_EPI_ATOMIC) {
           float* dst = static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col;
@@ -208,9 +234,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           for (int i = 0; i < 32; i += 4)      // 16-byte vector reduction (sm_90+): a quarter of the atomic instructions
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(r[i]), "f"(r[i + 1]), "f"(r[i + 2]), "f"(r[i + 3]) : "memory");
         } else {
-          float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col);
+          // 32 fp32 columns = one 128-byte row segment
 #pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+          for (int q = 0; q < 8; ++q)
+            sts128(stage + lane * 128 + ((q ^ (lane & 7)) << 4),
+                   make_uint4(__float_as_uint(r[q * 4]), __float_as_uint(r[q * 4 + 1]), __float_as_uint(r[q * 4 + 2]), __float_as_uint(r[q * 4 + 3])));
+          __syncwarp();
+          float* base = static_cast<float*>(p.C) + static_cast<int64_t>(m0 + quarter * 32) * p.ldc + col;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + srow;
+            reinterpret_cast<uint4*>(base + static_cast<int64_t>(rr) * p.ldc)[sch] = lds128(stage + rr * 128 + ((sch ^ (rr & 7)) << 4));
+          }
+          __syncwarp();
         }
         if (epi & RTTS_EPI_COLSUM) {
           const float tot = warp_column_sums(r, lane);

@@ -116,37 +116,50 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const float*
   }
 }
 
-// y = bf16(x); colsum[c] += sum_rows x[r,c]  (colsum may be NULL).  CTA = 256 threads x 4 columns = 1024-column
-// panel strip; each CTA walks `rows_per_cta` rows so the column sums need one atomic per column per CTA.
+// y = bf16(x); colsum[c] += sum_rows x[r,c]  (colsum may be NULL).  A CTA (256 threads) owns a strip of up to 1024 columns:
+// `tpr` threads (float4 each) cover one row of the strip and 256 / tpr rows are in flight per pass, eight passes of loads are
+// issued before any is consumed.  Column sums: registers -> shared-memory reduction over the row lanes -> ONE atomic per column
+// per CTA, and the grid is only ~4 CTAs per SM, so an address sees a few hundred atomics instead of thousands.
 __global__ void __launch_bounds__(256) cast_bf16_colsum_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                                               float* __restrict__ colsum, int rows, int cols, int rows_per_cta) {
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
-  if (c >= cols) return;
+                                                               float* __restrict__ colsum, int rows, int cols, int rows_per_cta, int tpr) {
+  __shared__ float4 red[256];
+  const int lane_row = threadIdx.x / tpr, lanes = 256 / tpr;
+  const int c = (blockIdx.x * tpr + threadIdx.x % tpr) * 4;
+  const bool live = c < cols;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
   float4 acc = make_float4(0, 0, 0, 0);
-  int r = r0;
-  for (; r + 4 <= r1; r += 4) {       // four independent 16-byte loads in flight per thread
-    float4 v[4];
+  if (live) {
+    int r = r0 + lane_row;
+    for (; r + 7 * lanes < r1; r += 8 * lanes) {       // eight independent 16-byte loads in flight per thread
+      float4 v[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(r + i) * cols + c));
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(r + i * lanes) * cols + c));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
+        uint2 o;
+        o.x = pack_bf16(v[i].x, v[i].y);
+        o.y = pack_bf16(v[i].z, v[i].w);
+        *reinterpret_cast<uint2*>(y + static_cast<int64_t>(r + i * lanes) * cols + c) = o;
+        acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w;
+      }
+    }
+    for (; r < r1; r += lanes) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(r) * cols + c));
       uint2 o;
-      o.x = pack_bf16(v[i].x, v[i].y);
-      o.y = pack_bf16(v[i].z, v[i].w);
-      *reinterpret_cast<uint2*>(y + static_cast<int64_t>(r + i) * cols + c) = o;
-      acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w;
+      o.x = pack_bf16(v.x, v.y);
+      o.y = pack_bf16(v.z, v.w);
+      *reinterpret_cast<uint2*>(y + static_cast<int64_t>(r) * cols + c) = o;
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
-  for (; r < r1; ++r) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(r) * cols + c));
-    uint2 o;
-    o.x = pack_bf16(v.x, v.y);
-    o.y = pack_bf16(v.z, v.w);
-    *reinterpret_cast<uint2*>(y + static_cast<int64_t>(r) * cols + c) = o;
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-  }
-  if (colsum) {
+  if (colsum == nullptr) return;
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (lane_row == 0 && live) {
+    for (int l = 1; l < lanes; ++l) {
+      const float4 o = red[l * tpr + threadIdx.x];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
     atomicAdd(colsum + c, acc.x); atomicAdd(colsum + c + 1, acc.y);
     atomicAdd(colsum + c + 2, acc.z); atomicAdd(colsum + c + 3, acc.w);
   }
@@ -241,13 +254,15 @@ extern "C" int rtts_layernorm_bwd(const float* dy, const float* x, const float* 
 extern "C" int rtts_cast_bf16_colsum(const float* x, void* y, float* colsum, int rows, int cols, void* stream) {
   RTTS_REQUIRE(x && y, "rtts_cast_bf16_colsum: null pointer");
   RTTS_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "rtts_cast_bf16_colsum: cols=%d must be a multiple of 4", cols);
-  const int strips = (cols / 4 + 255) / 256;
-  int row_ctas = (8 * kNumSMs + strips - 1) / strips;
+  int tpr = 256;                                  // threads per row of a strip: a power of two covering min(cols, 1024) columns
+  while (tpr > 1 && (tpr / 2) * 4 >= cols) tpr /= 2;
+  const int strips = (cols / 4 + tpr - 1) / tpr;
+  int row_ctas = (4 * kNumSMs + strips - 1) / strips;
   if (row_ctas > rows) row_ctas = rows;
   const int rows_per_cta = (rows + row_ctas - 1) / row_ctas;
   dim3 grid(strips, (rows + rows_per_cta - 1) / rows_per_cta);
   cast_bf16_colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y), colsum, rows, cols,
-                                                                              rows_per_cta);
+                                                                              rows_per_cta, tpr);
   return check_launch("rtts_cast_bf16_colsum");
 }
 
