@@ -1,0 +1,104 @@
+"""Decoder-to-encoder attention block (ref:reformer_tts/model/reformer.py:161-186 under ``WithNorm``), training path.
+
+SURVEY.md 8(f) rank 1: the first caller outside the LSH / FFN hot path that shares its reversible loop.  The block is one
+autograd.Function with a hand-written backward: LayerNorm and every projection (forward, dgrad, wgrad, bias gradients) run on
+the library's own kernels (row-wise LayerNorm, tcgen05 GEMMs with fused bias / bf16 epilogues); only the dense softmax(QK^T)V
+core over the <= 256 encoder positions stays on the vendor flash kernel (``scaled_dot_product_attention``), whose backward is
+reached through a small inner autograd graph kept on the context (no recompute of the core).  Same parameters and state-dict
+keys as ``nn.MultiheadAttention`` (``in_proj_weight``, ``in_proj_bias``, ``out_proj.{weight,bias}``)."""
+from __future__ import annotations
+
+import torch
+from torch.nn import functional as F
+
+from . import ops
+from .lsh_attention import _split_k
+
+
+class _CrossAttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, memory, w_in, b_in, w_out, b_out, wq_bf16, wkv_bf16, wo_bf16, keep_mask, cfg):
+        b, t, d = x.shape
+        s = memory.shape[1]
+        h, eps, p_drop = cfg["heads"], cfg["eps"], cfg["dropout"]
+        dh = d // h
+        x2 = x.reshape(b * t, d)
+        if ln_w is not None:
+            xn, mean, rstd = ops.layernorm_fwd(x2, ln_w, ln_b, eps)
+        else:
+            xn, mean, rstd = ops.cast_bf16_colsum(x2), None, None
+        memb = ops.cast_bf16_colsum(memory.reshape(b * s, d))
+        q = ops.gemm(xn, wq_bf16, bias=b_in[:d], out_dtype=torch.bfloat16)                 # [B*T, D]
+        kv = ops.gemm(memb, wkv_bf16, bias=b_in[d:], out_dtype=torch.bfloat16)             # [B*S, 2D]
+        kv5 = kv.view(b, s, 2, h, dh)
+        need_grad = any(ctx.needs_input_grad)       # False in the reversible forward (no_grad): no inner graph to keep then
+        with torch.set_grad_enabled(need_grad):
+            ql = q.view(b, t, h, dh).transpose(1, 2).detach().requires_grad_(need_grad)
+            kl = kv5[:, :, 0].transpose(1, 2).detach().requires_grad_(need_grad)
+            vl = kv5[:, :, 1].transpose(1, 2).detach().requires_grad_(need_grad)
+            o = F.scaled_dot_product_attention(ql, kl, vl, attn_mask=keep_mask, dropout_p=p_drop)
+        o2 = o.detach().transpose(1, 2).reshape(b * t, d)
+        if not o2.is_contiguous():
+            o2 = o2.contiguous()
+        y = ops.gemm(o2, wo_bf16, bias=b_out).view(b, t, d)
+        ctx.inner = (ql, kl, vl, o) if need_grad else None
+        ctx.has_ln = ln_w is not None
+        ctx.dims = (b, t, s, d, h)
+        ctx.save_for_backward(x2, ln_w, mean, rstd, xn, memb, o2, wq_bf16, wkv_bf16, wo_bf16)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, ln_w, mean, rstd, xn, memb, o2, wq_bf16, wkv_bf16, wo_bf16 = ctx.saved_tensors
+        ql, kl, vl, o = ctx.inner
+        ctx.inner = None
+        b, t, s, d, h = ctx.dims
+        dh = d // h
+        dev = x2.device
+        rows_q, rows_kv = b * t, b * s
+        tiles = (d // 128) ** 2
+        # output projection
+        g_bo = torch.zeros(d, dtype=torch.float32, device=dev)
+        dyb = ops.cast_bf16_colsum(dy.reshape(rows_q, d), g_bo)
+        g_wo = torch.zeros((d, d), dtype=torch.float32, device=dev)
+        ops.gemm(dyb, o2, a_mn_major=True, b_mn_major=True, out=g_wo, accumulate=True, split_k=_split_k(rows_q, tiles))
+        do = ops.gemm(dyb, wo_bf16, b_mn_major=True, out_dtype=torch.bfloat16)            # [B*T, D]
+        # attention core (vendor kernel, saved inner graph)
+        dq4, dk4, dv4 = torch.autograd.grad(o, (ql, kl, vl), do.view(b, t, h, dh).transpose(1, 2))
+        dq = dq4.transpose(1, 2).reshape(rows_q, d)
+        if not dq.is_contiguous():
+            dq = dq.contiguous()
+        dkv = torch.stack((dk4.transpose(1, 2), dv4.transpose(1, 2)), dim=2).reshape(rows_kv, 2 * d)
+        # input projections: weights [3D, D] = [Wq; Wk; Wv]
+        g_win = torch.zeros((3 * d, d), dtype=torch.float32, device=dev)
+        g_bin = torch.empty(3 * d, dtype=torch.float32, device=dev)
+        torch.sum(dq, dim=0, dtype=torch.float32, out=g_bin[:d])
+        torch.sum(dkv, dim=0, dtype=torch.float32, out=g_bin[d:])
+        ops.gemm(dq, xn, a_mn_major=True, b_mn_major=True, out=g_win[:d], accumulate=True, split_k=_split_k(rows_q, tiles))
+        ops.gemm(dkv, memb, a_mn_major=True, b_mn_major=True, out=g_win[d:], accumulate=True, split_k=_split_k(rows_kv, 2 * tiles))
+        dxn = ops.gemm(dq, wq_bf16, b_mn_major=True)                                        # fp32 [B*T, D]
+        dmem = ops.gemm(dkv, wkv_bf16, b_mn_major=True).view(b, s, d)                       # fp32 [B, S, D]
+        g_lnw = g_lnb = None
+        if ctx.has_ln:
+            g_lnw = torch.zeros(d, dtype=torch.float32, device=dev)
+            g_lnb = torch.zeros(d, dtype=torch.float32, device=dev)
+            dx = ops.layernorm_bwd(dxn, x2, ln_w, mean, rstd, g_lnw, g_lnb)
+        else:
+            dx = dxn
+        return dx.view(b, t, d), g_lnw, g_lnb, dmem, g_win, g_bin, g_wo, g_bo, None, None, None, None, None
+
+
+def cross_attention(x, norm, memory, layer, caches, key_padding_mask):
+    """x fp32 [B,T,D] (un-normalised query), memory fp32 [B,S,D]; ``layer`` = the wrapped nn.MultiheadAttention."""
+    if not x.is_cuda:
+        raise RuntimeError("reformer_tts_b200 cross-attention training path runs on sm_100a CUDA only")
+    d = x.shape[-1]
+    w_in, b_in = layer.in_proj_weight, layer.in_proj_bias
+    ln_w = ln_b = None
+    eps = 1e-5
+    if norm is not None:
+        ln_w, ln_b, eps = norm.weight, norm.bias, norm.eps
+    keep = None if key_padding_mask is None else ~key_padding_mask[:, None, None, :]
+    cfg = dict(heads=layer.num_heads, eps=eps, dropout=layer.dropout if layer.training else 0.0)
+    return _CrossAttentionFn.apply(x.float(), ln_w, ln_b, memory.float(), w_in, b_in, layer.out_proj.weight, layer.out_proj.bias,
+                                   caches[0].get(w_in[:d]), caches[1].get(w_in[d:]), caches[2].get(layer.out_proj.weight), keep, cfg)

@@ -14,7 +14,9 @@ from typing import Dict, List, Optional
 import torch
 from torch import nn
 
+from ..cross_attention import cross_attention
 from ..feed_forward import layer_norm_bf16
+from ..lsh_attention import _WeightCache
 from ..lsh_attention import HFLSHSelfAttention, LSHSelfAttention
 from .modules import FeedForward
 from .reversible import ReversibleBlock, ReversibleHalfResidual, ReversibleSequence, ReversibleSwap
@@ -91,6 +93,7 @@ class MultiheadAttentionWrapper(nn.Module):
         super().__init__()
         self.layer = nn.MultiheadAttention(dim, **kwargs)
         self.attention_matrices_ = attention_matrices
+        self._caches = (_WeightCache(), _WeightCache(), _WeightCache())      # bf16 copies of Wq, Wkv, Wo
 
     def _fast_path_ok(self, query, extra) -> bool:
         layer = self.layer
@@ -101,8 +104,17 @@ class MultiheadAttentionWrapper(nn.Module):
         """``WithNorm`` hands over its LayerNorm: in the training fast path it runs on the row-wise kernel (bf16 out)."""
         extra = {k: v for k, v in kwargs.items() if k not in ("key", "value")}
         if "key" in kwargs and self._fast_path_ok(query, extra) and query.shape[-1] % 128 == 0:
-            return self._forward_training(layer_norm_bf16(query, norm), kwargs["key"], extra.get("key_padding_mask"))
+            memory = kwargs["key"]
+            if self._kernel_path_ok(query, memory):
+                return cross_attention(query, norm, memory, self.layer, self._caches, extra.get("key_padding_mask"))
+            return self._forward_training(layer_norm_bf16(query, norm), memory, extra.get("key_padding_mask"))
         return self.forward(norm(query), **kwargs)
+
+    def _kernel_path_ok(self, query, memory) -> bool:
+        """Shapes the tcgen05 GEMMs take (rows in multiples of 128, head size 64); anything else stays on the library path."""
+        b, t, d = query.shape
+        return (memory.dim() == 3 and (b * t) % 128 == 0 and (b * memory.shape[1]) % 128 == 0 and d // self.layer.num_heads == 64
+                and memory.shape[-1] == d)
 
     def forward(self, query, **kwargs):
         if "key" not in kwargs:

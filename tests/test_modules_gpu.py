@@ -160,6 +160,49 @@ def test_feed_forward_with_norm_equals_chunked_reference():
         assert rel_l2(g_ours[k], g_ref[k]) <= 6e-2, k
 
 
+@pytest.mark.parametrize("pad", [False, True])
+def test_cross_attention_block_equals_multihead_attention(pad):
+    """WithNorm(LayerNorm, MultiheadAttentionWrapper) (ref:reformer_tts/model/reformer.py:161-186 as built at :122-125) on the
+    kernel path (row-wise LayerNorm + tcgen05 projections, hand-written backward) against LayerNorm + stock ``nn.MultiheadAttention``
+    in fp32 on the CPU: output, input / memory gradients and every parameter gradient.  bf16 hops: LN out, q|kv, P, o, and the same
+    number on the way back, so the layer tolerance (1e-2) applies."""
+    from reformer_tts_b200.model.reformer import MultiheadAttentionWrapper, WithNorm
+    torch.manual_seed(3)
+    dim, heads, B, T, S = 128, 2, 2, 256, 128
+    ours = WithNorm(nn.LayerNorm, dim, MultiheadAttentionWrapper(dim, num_heads=heads)).to(DEV).train()
+    _round_weights_to_bf16(ours)
+    with torch.no_grad():
+        ours.norm.weight.uniform_(0.5, 1.5)
+        ours.norm.bias.normal_(0, 0.1)
+        ours.fn.layer.in_proj_bias.normal_(0, 0.1)
+        ours.fn.layer.out_proj.bias.normal_(0, 0.1)
+    ref_norm, ref_mha = nn.LayerNorm(dim), nn.MultiheadAttention(dim, num_heads=heads)
+    ref_norm.load_state_dict(ours.norm.state_dict())
+    ref_mha.load_state_dict(ours.fn.layer.state_dict())
+    x, mem, dy = torch.randn(B, T, dim), torch.randn(B, S, dim), torch.randn(B, T, dim)
+    kpm = None
+    if pad:
+        kpm = torch.zeros(B, S, dtype=torch.bool)
+        kpm[0, 100:] = True
+        kpm[1, 77:] = True
+    xg, mg = x.to(DEV).requires_grad_(True), mem.to(DEV).requires_grad_(True)
+    assert ours.fn._kernel_path_ok(xg, mg)
+    y = ours(xg, key=mg, value=mg, key_padding_mask=None if kpm is None else kpm.to(DEV))
+    y.backward(dy.to(DEV))
+    xr, mr = x.clone().requires_grad_(True), mem.clone().requires_grad_(True)
+    yr, _ = ref_mha(ref_norm(xr).transpose(0, 1), mr.transpose(0, 1), mr.transpose(0, 1), key_padding_mask=kpm)
+    yr = yr.transpose(0, 1)
+    yr.backward(dy)
+    assert rel_l2(y, yr) <= TOL_LAYER
+    assert rel_l2(xg.grad, xr.grad) <= TOL_LAYER and rel_l2(mg.grad, mr.grad) <= TOL_LAYER
+    g_ours = _grads(ours)
+    g_ref = {"norm." + k: v for k, v in _grads(ref_norm).items()}
+    g_ref.update({"fn.layer." + k: v for k, v in _grads(ref_mha).items()})
+    assert set(g_ours) == set(g_ref)
+    for k in g_ref:
+        assert rel_l2(g_ours[k], g_ref[k]) <= TOL_LAYER, k
+
+
 def _small_kwargs(impl="reformer_pytorch", depth=2):
     from reformer_tts_b200.model import config as C
     kw = C.model_kwargs({"num_mel_coeffs": 80, "dict_size": 76, "embedding_dim": 128, "pad_base": 128, "scp_encoding_dropout": 0.,
