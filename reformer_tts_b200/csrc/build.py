@@ -13,6 +13,7 @@ SOURCES = ["api.cu", "lsh_bucket.cu", "lsh_attn_fwd.cu", "lsh_attn_bwd.cu", "gem
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",
          "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"), "-I", str(HERE)]
+FLAGS += os.environ.get("RTTS_DEFS", "").split()      # experiment builds only (e.g. RTTS_DEFS="-DRTTS_TIME_LD"), use with -f
 
 
 def _stale(obj: Path, src: Path) -> bool:

@@ -11,7 +11,7 @@
 // tile k are the tail of the block gathered for tile k-1: every row is fetched once per hash round (the gather is what
 // loads the SM's load/store pipe most).
 //   S = Q K^T          tcgen05.mma  M=128, N=BUCKET (look-back block) + N=128 (main block), K=64  -> TMEM fp32
-//   softmax            thread = (query row, half of its 2*bucket window): reads S from TMEM, applies the per-key 1/|k|
+//   softmax            thread = (query row, quarter of its 2*bucket window): reads S from TMEM, applies the per-key 1/|k|
 //                      scale (keys are normalised AFTER the fp32-accumulated dot) and the padding / causal / self masks
 //                      from the position ids, single pass (see below), and writes P (bf16 pairs) back into TMEM over
 //                      the S columns it has just consumed
@@ -23,9 +23,6 @@
 #include "host_util.h"
 #include "rtts_b200.h"
 
-#ifndef RTTS_HALVES
-#define RTTS_HALVES 2
-#endif
 namespace rtts {
 
 constexpr int kDh = 64;
@@ -59,7 +56,7 @@ struct AttnFwdParams {
 //                 from sumsq.  Software-pipelined: sticker loads run two tiles ahead, sumsq / mask loads one tile ahead, and a
 //                 tile is announced (cp.async.wait_group 1) after the next one's copies are queued, so no load latency is exposed.
 //   warps 0-7   : softmax pair 0 (tiles k even);  warps 8-15: softmax pair 1 (tiles k odd).  A pair is two warpgroups sharing a
-//                 tile: thread (half, row) owns half of the row's key window (and half of the output columns in the epilogue)
+//                 tile: thread (part, row) owns a quarter of the row's key window
 // Shared memory: kSlots ring slots {K block, V block} of 128 rows + per-row key scale / position.  Tile k lives in slot k % kSlots
 // and reads its look-back rows from the tail of slot (k-1) % kSlots.  The first tile of a CTA and the first tile of a (batch, head)
 // row have no predecessor in the ring ("fresh"): their look-back rows are gathered into the tail of slot (k-1) % kSlots once the
@@ -74,14 +71,20 @@ struct AttnFwdParams {
 // that sums to zero can only see itself (masked to self_value): its softmax is uniform over the self columns, set analytically.
 // If any query of a tile has a bound >= 60 (norms so large that a visible key could underflow against the bound) the loader
 // flags the tile and the whole pair runs the exact two-pass arithmetic of the reference (row max first) instead.
-constexpr int kHalves = RTTS_HALVES;             // threads per query row in a softmax group (2: each thread owns half of the row's key window)
-constexpr int kSoftmaxThreads = 128 * kHalves;   // threads of one softmax group (one tile)
+// 16 softmax warps.  bucket 64: ONE group, thread = (query row, quarter of its window), works on every tile and alternates between
+// the two TMEM regions.  bucket 128: two groups (thread = (row, half of the window)), one per region / tile parity - its compacted P
+// layout (which makes room for O inside the S columns) lets a thread write only behind the S columns of its own half.
+#ifndef RTTS_SOFTMAX_WARPS
+#define RTTS_SOFTMAX_WARPS 16
+#endif
+constexpr int kSoftmaxWarps = RTTS_SOFTMAX_WARPS;
+constexpr int kMaxParts = 4;
 // Warp roles by index.  The SM's issue arbiter favours higher warp ids, so the producers that everything else waits on get
 // the top ids: warps 0-7 softmax groups, warps 8-11 epilogue, warps 12-19 loaders, warp 20 MMA issuer.
-constexpr int kFirstEpiWarp = 8 * kHalves;
+constexpr int kFirstEpiWarp = kSoftmaxWarps;
 constexpr int kEpiThreads = 128;       // thread = query row = TMEM lane
 constexpr int kFirstLoaderWarp = kFirstEpiWarp + 4;
-constexpr int kLoaderWarps = kHalves == 2 ? 4 : 8;
+constexpr int kLoaderWarps = 4;
 #ifndef RTTS_LOADER_GROUPS
 #define RTTS_LOADER_GROUPS 1
 #endif
@@ -104,9 +107,9 @@ struct AttnFwdSmem {
   static constexpr int kMetaScale = 0, kMetaPos = kQRows * 4, kMetaTag = 2 * kQRows * 4;
   static constexpr int kMetaGeo = kMetaTag + 16;                     // int4 {row_bh, base_main (round * T), round_start, -}: written by the loader
   static constexpr int kMetaBytes = 2 * kQRows * 4 + 32;
-  static constexpr int kOffPart = kOffMeta + kSlots * kMetaBytes;    // float[2 pairs][2 halves][128 rows] partial row sums / maxima
+  static constexpr int kOffPart = kOffMeta + kSlots * kMetaBytes;    // float[2 tile parities][kParts][128 rows] partial row sums / maxima
   // per (pair, tile parity): what the epilogue needs from the softmax pair: float sum[128], float max[128], int slot[128], int row_bh (+pad)
-  static constexpr int kOffFin = kOffPart + 2 * 2 * kQRows * 4;
+  static constexpr int kOffFin = kOffPart + 2 * kMaxParts * kQRows * 4;
   static constexpr int kFinSum = 0, kFinMax = kQRows * 4, kFinSlot = 2 * kQRows * 4, kFinRow = 3 * kQRows * 4;
   static constexpr int kFinBytes = 3 * kQRows * 4 + 16;
   static constexpr int kOffStage = kOffFin + 4 * kFinBytes;          // epilogue staging: 4 warps x 32 rows x 128 B (swizzled) for coalesced stores
@@ -116,7 +119,11 @@ struct AttnFwdSmem {
   static constexpr int kDynamic = kTotal + 1024;                     // slack for manual 1024-B alignment
 };
 
+#ifdef RTTS_TRACE      // timeline build (tools/trace_fwd.py): RTTS_DEFS=-DRTTS_TRACE python reformer_tts_b200/csrc/build.py -f
 #define RTTS_STAMP(role, n, k) do { if (p.trace != nullptr && blockIdx.x == 0 && (n) < 32) p.trace[((role) * 32 + (n)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define RTTS_STAMP(role, n, k) do { } while (0)
+#endif
 
 // TMEM column (relative to the pair's region) of the P block of key chunk q (32 keys -> 16 columns of bf16 pairs).
 template <int BUCKET>
@@ -214,6 +221,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
   constexpr uint32_t kColO = BUCKET == 64 ? 192 : 64;
   constexpr bool kAliasO = BUCKET == 128; // bucket 128: S fills all 256 columns of the region, O reuses columns S no longer needs
   constexpr uint32_t kTmemCols = 512;
+#ifndef RTTS_PARTS64
+#define RTTS_PARTS64 4
+#endif
+  constexpr int kParts = BUCKET == 64 ? RTTS_PARTS64 : 2;       // threads per query row in a softmax group
+  constexpr int kGroups = kSoftmaxWarps / (4 * kParts);         // softmax groups: group w takes tiles k = w (mod kGroups)
+  constexpr int kSoftmaxThreads = 128 * kParts;                 // threads working on one tile
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -228,7 +241,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int RT = p.R * p.T;
+#ifdef RTTS_TRACE
   const long long t_cta0 = clock64();
+#endif
   // this CTA's run of tiles
   const int g0 = static_cast<int>(static_cast<int64_t>(blockIdx.x) * num_tiles / gridDim.x);
   const int g1 = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * num_tiles / gridDim.x);
@@ -348,12 +363,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const int g = k & 1;
       const uint32_t ph = (k >> 1) & 1;
       const uint32_t a_fin = smem_u32(smem + L::kOffFin) + (g * 2 + ph) * L::kFinBytes;
-      mbar_wait(p_full + g, ph);                     // the group's row sums / slots are in shared memory
+      mbar_wait_relaxed(p_full + g, ph, 100);        // the group's row sums / slots are in shared memory
       const float row_sum = __uint_as_float(lds32(a_fin + L::kFinSum + m * 4));
       const float row_max = __uint_as_float(lds32(a_fin + L::kFinMax + m * 4));
       const int64_t row_base = static_cast<int64_t>(lds32(a_fin + L::kFinRow)) * RT;
       const float inv_sum = 1.f / row_sum;
-      mbar_wait(o_full + g, ph);
+      mbar_wait_relaxed(o_full + g, ph, 40);
       tc_fence_after_sync();
       if (m == 0) RTTS_STAMP(3, k, 0);
       // O row / row sum -> bf16 -> this warp's staging tile (row = lane, 16-byte chunks swizzled by the row)
@@ -377,7 +392,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       if (lane == 0) mbar_arrive(o_free + g);      // O columns of this group may be overwritten
       // scatter-store at the UNSORTED slot, one full 128-byte row per 8 lanes (four rows per instruction)
       const int64_t my_slot = row_base + static_cast<int>(lds32(a_fin + L::kFinSlot + m * 4));
-#ifndef RTTS_EXP_NOEPI
       p.lse_rounds[my_slot] = (row_max + log2f(row_sum)) * kLn2;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -386,9 +400,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
         const int64_t slot = row_base + static_cast<int>(lds32(a_fin + L::kFinSlot + ((warp & 3) * 32 + row) * 4));
         reinterpret_cast<uint4*>(p.o_rounds + slot * kDh)[ch] = u;
       }
-#else
-      if (inv_sum == 123.456f) p.lse_rounds[my_slot] = row_max;
-#endif
       __syncwarp();                 // the staging tile is free again
       if (m == 0) RTTS_STAMP(3, k, 1);
     }
@@ -469,7 +480,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           announce(pending);
           pending = -1;
         }
-        mbar_wait(slot_free + s, par);
+        mbar_wait_relaxed(slot_free + s, par, 100);
       }
       free_parity ^= 1u << s;
     };
@@ -544,12 +555,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
         const int j = i * kGroups + grp;
         const int64_t off = static_cast<int64_t>(pos_cur[i]) * p.ld;
         const uint32_t so = sw128_offset(j, c);
-#ifndef RTTS_EXP_NOLOAD
         cp_async16(sK + so, qk_b + off);
         cp_async16(sV + so, v_b + off);
-#else
-        if (off == -12345) { cp_async16(sK + so, qk_b + off); cp_async16(sV + so, v_b + off); }
-#endif
       }
       cp_async_commit();
       {
@@ -593,38 +600,36 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
     }
   } else {
     // ================================================= softmax pairs ==============================================
-    const int wg = warp / (4 * kHalves);            // softmax group 0 | 1 (tiles k even | odd)
-    const int half = kHalves == 2 ? (warp >> 2) & 1 : 0;      // which part of the row's window
+    // All 16 warps work on the SAME tile (thread = (query row, quarter of its window)) and alternate between the two TMEM
+    // regions: while they are in tile k (region k & 1), the tensor pipe runs PV(k-1) and S(k+1) on the other region, so that
+    // chain hides under the softmax.  (Two groups owning one region each run their softmax phases in lockstep - they share the
+    // issue slots equally and finish together - and then both idle through their PV -> S chains: 2100 of 6500 cycles per tile pair.)
+    const int grp_id = warp / (4 * kParts);         // softmax group (bucket 128 only: 0 | 1)
+    const int part = (warp >> 2) % kParts;          // which part of the row's window
     const int m = tid & 127;                        // query row = TMEM lane
-    const uint32_t t_row = tmem + wg * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const uint32_t a_part = smem_u32(smem + L::kOffPart) + wg * 2 * kQRows * 4;      // float [2 halves][128 rows]
-    const int pair_bar = 1 + wg;                    // named barrier of the 256 threads of this pair
+    const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    constexpr int kPartCols = kWin / kParts;        // 32 (bucket 64) or 64 (bucket 128) key columns per thread
     const int win0 = (m / BUCKET) * BUCKET;          // first key column of this query's window
     const float mv = p.mask_value_log2, sv = p.self_value_log2;
     const bool need_mask = p.causal || p.mask != nullptr;
-#ifdef RTTS_COUNT_SPINS
-    long long dbg_spins = 0, dbg_wait = 0;
-#endif
-    auto pair_sync = [&]() { if (kHalves == 2) asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(kSoftmaxThreads) : "memory"); };
-    for (int k = wg; k < my_tiles; k += 2) {
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp_id), "n"(kSoftmaxThreads) : "memory"); };
+    // the block of 32 key columns holding this warp's own columns (rows 32*(m/32) .. +31) and the quarter that owns it (warp-uniform)
+    const int diag_col = BUCKET + (m & ~31);
+    const int part_own = (diag_col - win0) / kPartCols;
+    for (int k = grp_id; k < my_tiles; k += kGroups) {
+      const int wg = k & 1;                         // TMEM region / barrier set of this tile
       const uint32_t ph = (k >> 1) & 1;
+      const uint32_t t_row = t_lane + wg * 256;
+      const uint32_t a_part = smem_u32(smem + L::kOffPart) + wg * kMaxParts * kQRows * 4;      // float [kParts][128 rows], double-buffered by tile parity
       const int st_i = k % kSlots, sp_i = (st_i + kSlots - 1) % kSlots;
       const uint8_t* meta = smem + L::kOffMeta + st_i * L::kMetaBytes;
       const uint8_t* meta_p = smem + L::kOffMeta + sp_i * L::kMetaBytes;
       // key column j of the tile: j < BUCKET -> look-back row kTail + j of the previous slot, else main row j - BUCKET
       const uint32_t a_scale_lb = smem_u32(meta_p + L::kMetaScale) + kTail * 4, a_pos_lb = smem_u32(meta_p + L::kMetaPos) + kTail * 4;
       const uint32_t a_scale_mn = smem_u32(meta + L::kMetaScale) - BUCKET * 4, a_pos_mn = smem_u32(meta + L::kMetaPos) - BUCKET * 4;
-      if (m == 0 && half == 0) RTTS_STAMP(2, k, 0);
-#ifdef RTTS_COUNT_SPINS
-      {
-        long long tw0 = clock64();
-        while (!mbar_try_wait(full + st_i, (k / kSlots) & 1)) { ++dbg_spins; }
-        dbg_wait += clock64() - tw0;
-      }
-#else
+      if (m == 0 && part == 0) RTTS_STAMP(2, k, 0);
       mbar_wait(full + st_i, (k / kSlots) & 1);      // metadata of this tile (and of its look-back rows) is visible
-#endif
-      if (m == 0 && half == 0) RTTS_STAMP(2, k, 3);
+      if (m == 0 && part == 0) RTTS_STAMP(2, k, 3);
       const uint32_t a_meta = smem_u32(meta);
       const uint4 geo = lds128(a_meta + L::kMetaGeo);
       const int row_bh = static_cast<int>(geo.x), base_main = static_cast<int>(geo.y);
@@ -639,13 +644,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const float row_bound = p.score_scale_log2 * p.score_scale_log2 / __uint_as_float(lds32(a_meta + L::kMetaScale + m * 4)) * 1.001f;
       mbar_wait(s_full + wg, ph);
       tc_fence_after_sync();
-      if (m == 0 && half == 0) RTTS_STAMP(2, k, 1);
+      if (m == 0 && part == 0) RTTS_STAMP(2, k, 1);
 
       float row_max = row_bound;
       if (exact) {
         float mx = -FLT_MAX;
 #pragma unroll 1
-        for (int c0 = half * (kWin / kHalves); c0 < (half + 1) * (kWin / kHalves); c0 += 16) {
+        for (int c0 = part * kPartCols; c0 < (part + 1) * kPartCols; c0 += 16) {
           const int col = win0 + c0;
           uint32_t r[16];
           tmem_ld16(t_row + col, r);
@@ -653,82 +658,92 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           mx = chunk_max(r, (col < BUCKET ? a_pos_lb : a_pos_mn) + col * 4, (col < BUCKET ? a_scale_lb : a_scale_mn) + col * 4, q_limit, q_enc, mv, sv, mx);
         }
         row_max = mx;
-        if (kHalves == 2) {
-          sts32(a_part + (half * kQRows + m) * 4, __float_as_uint(mx));
-          pair_sync();
-          row_max = fmaxf(__uint_as_float(lds32(a_part + m * 4)), __uint_as_float(lds32(a_part + (kQRows + m) * 4)));
-          pair_sync();             // both halves have read the maxima before the slots are reused for the sums
-        }
+        sts32(a_part + (part * kQRows + m) * 4, __float_as_uint(mx));
+        pair_sync();
+#pragma unroll
+        for (int q = 0; q < kParts; ++q) row_max = q == 0 ? __uint_as_float(lds32(a_part + m * 4)) : fmaxf(row_max, __uint_as_float(lds32(a_part + (q * kQRows + m) * 4)));
+        pair_sync();               // every part has read the maxima before the slots are reused for the sums
       }
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       {
         // The query's own column sits in exactly one 32-column chunk per warp (warp-uniform); the same token can appear a second
         // time only in the look-back chunk of the first tile of a hash round.  Only those chunks pay for the self comparison, and
         // the position mask is skipped altogether when nothing can be masked (non-causal, no padding mask).
-        const int diag_col = BUCKET + (m & ~31);                  // 32 columns holding the own columns of rows 32*(m/32) .. +31
         const float neg_m = -row_max;
-#pragma unroll 1
-#ifdef RTTS_EXP_NOSOFT
-        for (int c0 = half * (kWin / kHalves); c0 < half * (kWin / kHalves) + (p.T < 0 ? 64 : 0); c0 += 16) {
-#else
-        for (int c0 = half * (kWin / kHalves); c0 < (half + 1) * (kWin / kHalves); c0 += 16) {
-#endif
-          const int col = win0 + c0;
-          uint32_t r[16], pk[8];
-#ifdef RTTS_TIME_LD
-          const long long t_a = clock64();
-#endif
-#ifdef RTTS_EXP_NOLDTM
-#pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(1e-3f * static_cast<float>(col + i + m));
-#else
-          tmem_ld16(t_row + col, r);
-#endif
+        if (kParts == 4) {
+          // 32 columns per thread = one P block: both TMEM loads are issued before anything is computed, and both chunks share
+          // one variant (a 32-column block lies entirely in the look-back or the main part and holds the own column or not)
+          const int col = win0 + part * kPartCols;
+          uint32_t r0[16], r1[16], pk[8];
+          tmem_ld16(t_row + col, r0);
+          tmem_ld16(t_row + col + 16, r1);
           const uint32_t a_pos = (col < BUCKET ? a_pos_lb : a_pos_mn) + col * 4, a_scale = (col < BUCKET ? a_scale_lb : a_scale_mn) + col * 4;
-          const bool self_chunk = (col & ~31) == diag_col || (round_start && col < BUCKET);
+          const bool self_chunk = col == diag_col || (round_start && col < BUCKET);
+          const uint32_t t_p = t_row + p_col<BUCKET>(col >> 5);
           tmem_ld_wait();
-#ifdef RTTS_TIME_LD
-          if (p.trace != nullptr && blockIdx.x == 0 && k < 32 && m == 0 && half == 0) p.trace[(2 * 32 + k) * 8 + 6] += clock64() - t_a;
-#endif
-          if (exact) soft_chunk<true, true, true>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
-          else if (self_chunk) soft_chunk<true, true, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
-          else if (need_mask) soft_chunk<true, false, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
-          else soft_chunk<false, false, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
-#ifdef RTTS_TIME_LD
-          const long long t_b = clock64();
-#endif
-#ifdef RTTS_EXP_NOSTTM
-          if (pk[0] == 0x12345678u)
-#endif
-          tmem_st8(t_row + p_col<BUCKET>(col >> 5) + ((col >> 4) & 1) * 8, pk);      // P over S columns this thread has already consumed
-#ifdef RTTS_TIME_LD
-          if (p.trace != nullptr && blockIdx.x == 0 && k < 32 && (tid & 31) == 0 && (warp == 0 || warp == 12)) {
-            p.trace[(2 * 32 + k) * 8 + (warp == 0 ? 4 : 7)] += t_b - t_a;      // ld + wait + compute
+          if (exact) {
+            soft_chunk<true, true, true>(r0, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+            tmem_st8(t_p, pk);
+            soft_chunk<true, true, true>(r1, a_pos + 64, a_scale + 64, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+          } else if (self_chunk) {
+            soft_chunk<true, true, false>(r0, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+            tmem_st8(t_p, pk);
+            soft_chunk<true, true, false>(r1, a_pos + 64, a_scale + 64, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+          } else if (need_mask) {
+            soft_chunk<true, false, false>(r0, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+            tmem_st8(t_p, pk);
+            soft_chunk<true, false, false>(r1, a_pos + 64, a_scale + 64, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+          } else {
+            soft_chunk<false, false, false>(r0, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+            tmem_st8(t_p, pk);
+            soft_chunk<false, false, false>(r1, a_pos + 64, a_scale + 64, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
           }
+          tmem_st8(t_p + 8, pk);        // P over S columns this thread has already consumed
+        } else {
+#pragma unroll 1
+          for (int c0 = part * kPartCols; c0 < (part + 1) * kPartCols; c0 += 16) {
+            const int col = win0 + c0;
+            uint32_t r[16], pk[8];
+#ifdef RTTS_TRACE
+            const long long t_a = clock64();
 #endif
+            tmem_ld16(t_row + col, r);
+            const uint32_t a_pos = (col < BUCKET ? a_pos_lb : a_pos_mn) + col * 4, a_scale = (col < BUCKET ? a_scale_lb : a_scale_mn) + col * 4;
+            const bool self_chunk = (col & ~31) == diag_col || (round_start && col < BUCKET);
+            tmem_ld_wait();
+#ifdef RTTS_TRACE
+            const long long t_b = clock64();
+#endif
+            if (exact) soft_chunk<true, true, true>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+            else if (self_chunk) soft_chunk<true, true, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+            else if (need_mask) soft_chunk<true, false, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+            else soft_chunk<false, false, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+#ifdef RTTS_TRACE
+            const long long t_c = clock64();
+#endif
+            tmem_st8(t_row + p_col<BUCKET>(col >> 5) + ((col >> 4) & 1) * 8, pk);      // P over S columns this thread has already consumed
+#ifdef RTTS_TRACE
+            if (p.trace != nullptr && blockIdx.x == 0 && k < 32 && m == 0 && part == 0) {
+              p.trace[(2 * 32 + k) * 8 + 6] += t_b - t_a;               // TMEM load + wait
+              p.trace[(2 * 32 + k) * 8 + 4] += t_c - t_b;               // chunk arithmetic
+              p.trace[(2 * 32 + k) * 8 + 7] += clock64() - t_c;         // TMEM store issue
+            }
+#endif
+          }
         }
       }
       if (BUCKET == 64) {
         // the 64 keys outside this query's window contribute nothing: zero their two P blocks
         const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         const int dead_q = m < 64 ? 4 : 0;
-        if (kHalves == 2) {
-          tmem_st16(t_row + p_col<BUCKET>(dead_q + half), z);
-        } else {
-          tmem_st16(t_row + p_col<BUCKET>(dead_q), z);
-          tmem_st16(t_row + p_col<BUCKET>(dead_q + 1), z);
-        }
+        if (part < 2) tmem_st16(t_row + p_col<BUCKET>(dead_q + part), z);      // parts 0 / 1: the same blocks they own in the duplicate scan below
       }
       float row_sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-#ifdef RTTS_EXP_NOSOFT
-      row_sum = 1.f;
-#endif
-      if (kHalves == 2) {
-        sts32(a_part + (half * kQRows + m) * 4, __float_as_uint(row_sum));
-        pair_sync();               // both halves of every row are summed and stored
-        row_sum = __uint_as_float(lds32(a_part + m * 4)) + __uint_as_float(lds32(a_part + (kQRows + m) * 4));
-      }
-      if (m == 0 && half == 0) RTTS_STAMP(2, k, 5);
+      sts32(a_part + (part * kQRows + m) * 4, __float_as_uint(row_sum));
+      pair_sync();                 // all parts of every row are summed and stored
+      row_sum = __uint_as_float(lds32(a_part + m * 4)) + __uint_as_float(lds32(a_part + (kQRows + m) * 4));
+      if (kParts == 4) row_sum += __uint_as_float(lds32(a_part + (2 * kQRows + m) * 4)) + __uint_as_float(lds32(a_part + (3 * kQRows + m) * 4));
+      if (m == 0 && part == 0) RTTS_STAMP(2, k, 5);
       const bool lonely = !exact && !(row_sum > 0.f);
       if (__any_sync(0xffffffffu, lonely)) {
         // Every term of a lonely row was exactly zero: with bound < 60 a visible key cannot underflow (s - bound >= -2*bound > -126),
@@ -737,9 +752,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
         // second time only when the look-back chunk comes from the previous hash round (first tile of a round).
         int n_self = 1;
         const bool dup_possible = round_start && win0 == 0;
-        if (half == kHalves - 1) { // the own column lies in the second half of the window: column BUCKET + m
+        if (part == part_own) {    // the thread that wrote the P block holding the own column (BUCKET + m) rewrites it
           uint32_t blk[16];
-          const uint32_t t_blk = t_row + p_col<BUCKET>((BUCKET + (m & ~31)) >> 5);
+          const uint32_t t_blk = t_row + p_col<BUCKET>(diag_col >> 5);
           tmem_ld16(t_blk, blk);
           tmem_ld_wait();
           if (lonely) {
@@ -759,10 +774,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           }
           n_self += n_dup;
         }
-        if (half == 0 && __any_sync(0xffffffffu, lonely && n_self > 1)) {
-          // the duplicates live in the look-back columns [0, BUCKET): first half of the window of rows with win0 == 0
+        if (part * kPartCols < BUCKET && __any_sync(0xffffffffu, lonely && n_self > 1)) {
+          // the duplicates live in the look-back columns [0, BUCKET) of rows with win0 == 0: each part rewrites the blocks it wrote
 #pragma unroll 1
-          for (int c0 = 0; c0 < BUCKET; c0 += 32) {
+          for (int c0 = part * kPartCols; c0 < (part + 1) * kPartCols; c0 += 32) {
             uint32_t blk[16];
             const uint32_t t_blk = t_row + p_col<BUCKET>(c0 >> 5);
             tmem_ld16(t_blk, blk);
@@ -783,7 +798,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           row_max = sv;
         }
       }
-      if (half == 0) {
+      if (part == 0) {
         // what the epilogue warps need for this row (double-buffered by tile parity: tile k+4 of this pair writes the same buffer, and
         // its S is issued only after PV(k+2) has waited for epilogue(k))
         const uint32_t a_fin = smem_u32(smem + L::kOffFin) + (wg * 2 + ph) * L::kFinBytes;
@@ -796,14 +811,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       tc_fence_before_sync();       // this thread's TMEM reads of S / writes of P precede the MMAs that consume / overwrite the region
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(p_full + wg);
-      if (m == 0 && half == 0) RTTS_STAMP(2, k, 2);
+      if (m == 0 && part == 0) RTTS_STAMP(2, k, 2);
     }
-#ifdef RTTS_COUNT_SPINS
-    if (p.trace != nullptr && (tid & 31) == 0) { p.trace[4 * 32 * 8 + 148 * 32 + blockIdx.x * 32 + warp] = dbg_spins; p.trace[4 * 32 * 8 + 2 * 148 * 32 + blockIdx.x * 32 + warp] = dbg_wait; }
-#endif
   }
   // debug: per-CTA time until each role is done (trace buffer rows after the 4*32*8 stamps)
+#ifdef RTTS_TRACE
   if (p.trace != nullptr && (tid & 31) == 0) p.trace[4 * 32 * 8 + blockIdx.x * 32 + warp] = clock64() - t_cta0;
+#endif
   tc_fence_before_sync();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
