@@ -107,16 +107,16 @@ struct AttnFwdSmem {
   static constexpr int kMetaScale = 0, kMetaPos = kQRows * 4, kMetaTag = 2 * kQRows * 4;
   static constexpr int kMetaGeo = kMetaTag + 16;                     // int4 {row_bh, base_main (round * T), round_start, -}: written by the loader
   static constexpr int kMetaBytes = 2 * kQRows * 4 + 32;
-  static constexpr int kOffPart = kOffMeta + kSlots * kMetaBytes;    // float[2 tile parities][kParts][128 rows] partial row sums / maxima
-  // per (pair, tile parity): what the epilogue needs from the softmax pair: float sum[128], float max[128], int slot[128], int row_bh (+pad)
-  static constexpr int kOffFin = kOffPart + 2 * kMaxParts * kQRows * 4;
-  static constexpr int kFinSum = 0, kFinMax = kQRows * 4, kFinSlot = 2 * kQRows * 4, kFinRow = 3 * kQRows * 4;
-  static constexpr int kFinBytes = 3 * kQRows * 4 + 16;
+  static constexpr int kOffPart = kOffMeta + kSlots * kMetaBytes;    // float[2 tile parities][2 phases][kParts][128 rows] partial row sums (bit 31: duplicate seen) / maxima
+  // per (tile parity, phase): what the epilogue needs besides the partial sums: float max[128], int slot[128], int row_bh (+pad)
+  static constexpr int kOffFin = kOffPart + 4 * kMaxParts * kQRows * 4;
+  static constexpr int kFinMax = 0, kFinSlot = kQRows * 4, kFinRow = 2 * kQRows * 4;
+  static constexpr int kFinBytes = 2 * kQRows * 4 + 16;
   static constexpr int kOffStage = kOffFin + 4 * kFinBytes;          // epilogue staging: 4 warps x 32 rows x 128 B (swizzled) for coalesced stores
   static constexpr int kOffBar = kOffStage + 4 * 4096;               // 2*kSlots + 8 mbarriers
   static constexpr int kOffTmem = kOffBar + (2 * kSlots + 8) * 8;
   static constexpr int kTotal = kOffTmem + 8;
-  static constexpr int kDynamic = kTotal + 1024;                     // slack for manual 1024-B alignment
+  static constexpr int kDynamic = kTotal;                            // no static shared memory in the kernel: the dynamic segment starts 1024-B aligned (checked)
 };
 
 #ifdef RTTS_TRACE      // timeline build (tools/trace_fwd.py): RTTS_DEFS=-DRTTS_TRACE python reformer_tts_b200/csrc/build.py -f
@@ -135,9 +135,10 @@ __device__ __forceinline__ constexpr uint32_t p_col(int q) {
 // (MASK) or is the query itself (SELF); accumulates the row sum and packs the chunk into 8 registers of bf16 pairs.
 // EXACT: neg_m is minus the true row maximum and masked / self entries take the reference's fill values instead of zero.
 // a_pos / a_scale: shared addresses of key_pos / key_scale at this chunk's first column.
-template <bool MASK, bool SELF, bool EXACT>
+// DUP: also record whether a key of this chunk is the query's own token (look-back chunk of the first tile of a hash round).
+template <bool MASK, bool SELF, bool EXACT, bool DUP = false>
 __device__ __forceinline__ void soft_chunk(uint32_t* r, uint32_t a_pos, uint32_t a_scale, float neg_m, int q_limit, int q_enc, float mv,
-                                           float sv, float* sum4, uint32_t* pk) {
+                                           float sv, float* sum4, uint32_t* pk, uint32_t* dup = nullptr) {
   // Written as whole-chunk stages over r[] in place (16 independent elements per stage), so that every stage has 16-way
   // instruction-level parallelism and no stage waits on the previous element's latency.
   float* x = reinterpret_cast<float*>(r);
@@ -185,6 +186,7 @@ __device__ __forceinline__ void soft_chunk(uint32_t* r, uint32_t a_pos, uint32_t
       for (int i = 0; i < 4; ++i) {
         if (MASK) x[q * 4 + i] = kp[i] > q_limit ? 0.f : x[q * 4 + i];       // exp2(mask_value - m) == 0
         if (SELF) x[q * 4 + i] = kp[i] == q_enc ? 0.f : x[q * 4 + i];        // exp2(self_value - m) == 0
+        if (DUP) *dup = kp[i] == q_enc ? 0x80000000u : *dup;
       }
     }
   }
@@ -228,8 +230,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
   constexpr int kGroups = kSoftmaxWarps / (4 * kParts);         // softmax groups: group w takes tiles k = w (mod kGroups)
   constexpr int kSoftmaxThreads = 128 * kParts;                 // threads working on one tile
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();     // SWIZZLE_128B tiles need 1024-byte alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* full = bars;                       // [kSlots]
   uint64_t* slot_free = bars + kSlots;         // [kSlots]
@@ -364,9 +367,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const uint32_t ph = (k >> 1) & 1;
       const uint32_t a_fin = smem_u32(smem + L::kOffFin) + (g * 2 + ph) * L::kFinBytes;
       mbar_wait_relaxed(p_full + g, ph, 100);        // the group's row sums / slots are in shared memory
-      const float row_sum = __uint_as_float(lds32(a_fin + L::kFinSum + m * 4));
-      const float row_max = __uint_as_float(lds32(a_fin + L::kFinMax + m * 4));
-      const int64_t row_base = static_cast<int64_t>(lds32(a_fin + L::kFinRow)) * RT;
+      const uint32_t a_part = smem_u32(smem + L::kOffPart) + (g * 2 + ph) * kMaxParts * kQRows * 4;
+      float row_sum = 0.f;
+      uint32_t dup = 0;
+#pragma unroll
+      for (int q = 0; q < kParts; ++q) {
+        const uint32_t u = lds32(a_part + (q * kQRows + m) * 4);
+        row_sum += __uint_as_float(u & 0x7fffffffu);
+        dup |= u;
+      }
+      float row_max = __uint_as_float(lds32(a_fin + L::kFinMax + m * 4));
+      const int row_bh = static_cast<int>(lds32(a_fin + L::kFinRow));
+      const int64_t row_base = static_cast<int64_t>(row_bh) * RT;
+      const int own_slot = static_cast<int>(lds32(a_fin + L::kFinSlot + m * 4));
+      // all terms exactly zero: the row sees only itself (see the softmax role); exact-mode rows always have a positive sum
+      const bool lonely = !(row_sum > 0.f);
+      if (lonely) {
+        row_sum = (dup >> 31) ? 2.f : 1.f;      // number of self columns
+        row_max = p.self_value_log2;
+      }
       const float inv_sum = 1.f / row_sum;
       mbar_wait_relaxed(o_full + g, ph, 40);
       tc_fence_after_sync();
@@ -387,11 +406,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           sts128(a_stage + lane * 128 + (((hh * 4 + q4) ^ (lane & 7)) << 4), u);
         }
       }
+      if (lonely) {
+        // out = v[own position] (every self column holds the query's own token); P of this row is all zero, so O was zero
+        const int pos = own_slot % p.T, b = row_bh / p.H, h = row_bh - b * p.H;
+        const uint4* vrow = reinterpret_cast<const uint4*>(p.v + (static_cast<int64_t>(b) * p.T + pos) * p.ld + h * kDh);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) sts128(a_stage + lane * 128 + ((ch ^ (lane & 7)) << 4), __ldg(vrow + ch));
+      }
       tc_fence_before_sync();
       __syncwarp();                 // staging tile complete; all TMEM reads of this warp done
       if (lane == 0) mbar_arrive(o_free + g);      // O columns of this group may be overwritten
       // scatter-store at the UNSORTED slot, one full 128-byte row per 8 lanes (four rows per instruction)
-      const int64_t my_slot = row_base + static_cast<int>(lds32(a_fin + L::kFinSlot + m * 4));
+      const int64_t my_slot = row_base + own_slot;
       p.lse_rounds[my_slot] = (row_max + log2f(row_sum)) * kLn2;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -615,12 +641,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
     auto pair_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp_id), "n"(kSoftmaxThreads) : "memory"); };
     // the block of 32 key columns holding this warp's own columns (rows 32*(m/32) .. +31) and the quarter that owns it (warp-uniform)
     const int diag_col = BUCKET + (m & ~31);
-    const int part_own = (diag_col - win0) / kPartCols;
     for (int k = grp_id; k < my_tiles; k += kGroups) {
       const int wg = k & 1;                         // TMEM region / barrier set of this tile
       const uint32_t ph = (k >> 1) & 1;
       const uint32_t t_row = t_lane + wg * 256;
-      const uint32_t a_part = smem_u32(smem + L::kOffPart) + wg * kMaxParts * kQRows * 4;      // float [kParts][128 rows], double-buffered by tile parity
+      const uint32_t a_part = smem_u32(smem + L::kOffPart) + (wg * 2 + ph) * kMaxParts * kQRows * 4;      // float [kParts][128 rows] of this tile
       const int st_i = k % kSlots, sp_i = (st_i + kSlots - 1) % kSlots;
       const uint8_t* meta = smem + L::kOffMeta + st_i * L::kMetaBytes;
       const uint8_t* meta_p = smem + L::kOffMeta + sp_i * L::kMetaBytes;
@@ -665,6 +690,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
         pair_sync();               // every part has read the maxima before the slots are reused for the sums
       }
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t dup = 0;           // bit 31: the query's own token also sits in the look-back chunk (rows with win0 == 0 only count it)
       {
         // The query's own column sits in exactly one 32-column chunk per warp (warp-uniform); the same token can appear a second
         // time only in the look-back chunk of the first tile of a hash round.  Only those chunks pay for the self comparison, and
@@ -685,6 +711,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
             soft_chunk<true, true, true>(r0, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
             tmem_st8(t_p, pk);
             soft_chunk<true, true, true>(r1, a_pos + 64, a_scale + 64, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+          } else if (self_chunk && col < BUCKET) {       // look-back block of the first tile of a hash round: the own token may be there
+            soft_chunk<true, true, false, true>(r0, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk, &dup);
+            tmem_st8(t_p, pk);
+            soft_chunk<true, true, false, true>(r1, a_pos + 64, a_scale + 64, neg_m, q_limit, q_enc, mv, sv, sum4, pk, &dup);
           } else if (self_chunk) {
             soft_chunk<true, true, false>(r0, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
             tmem_st8(t_p, pk);
@@ -715,6 +745,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
             const long long t_b = clock64();
 #endif
             if (exact) soft_chunk<true, true, true>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
+            else if (self_chunk && col < BUCKET) soft_chunk<true, true, false, true>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk, &dup);
             else if (self_chunk) soft_chunk<true, true, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
             else if (need_mask) soft_chunk<true, false, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
             else soft_chunk<false, false, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
@@ -738,71 +769,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
         const int dead_q = m < 64 ? 4 : 0;
         if (part < 2) tmem_st16(t_row + p_col<BUCKET>(dead_q + part), z);      // parts 0 / 1: the same blocks they own in the duplicate scan below
       }
-      float row_sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      sts32(a_part + (part * kQRows + m) * 4, __float_as_uint(row_sum));
-      pair_sync();                 // all parts of every row are summed and stored
-      row_sum = __uint_as_float(lds32(a_part + m * 4)) + __uint_as_float(lds32(a_part + (kQRows + m) * 4));
-      if (kParts == 4) row_sum += __uint_as_float(lds32(a_part + (2 * kQRows + m) * 4)) + __uint_as_float(lds32(a_part + (3 * kQRows + m) * 4));
-      if (m == 0 && part == 0) RTTS_STAMP(2, k, 5);
-      const bool lonely = !exact && !(row_sum > 0.f);
-      if (__any_sync(0xffffffffu, lonely)) {
-        // Every term of a lonely row was exactly zero: with bound < 60 a visible key cannot underflow (s - bound >= -2*bound > -126),
-        // so no key is visible: only the query itself (masked to self_value) remains and the softmax is uniform over the self columns
-        // (rp R8 "except when no other targets are available").  The query's own column is known; the same token can appear a
-        // second time only when the look-back chunk comes from the previous hash round (first tile of a round).
-        int n_self = 1;
-        const bool dup_possible = round_start && win0 == 0;
-        if (part == part_own) {    // the thread that wrote the P block holding the own column (BUCKET + m) rewrites it
-          uint32_t blk[16];
-          const uint32_t t_blk = t_row + p_col<BUCKET>(diag_col >> 5);
-          tmem_ld16(t_blk, blk);
-          tmem_ld_wait();
-          if (lonely) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) blk[i] = (i == ((m & 31) >> 1)) ? ((m & 1) ? 0x3F800000u : 0x00003F80u) : 0u;
-          }
-          tmem_st16(t_blk, blk);
-        }
-        if (dup_possible && lonely) {
-          // branch-free count first: a duplicate is rare, the scan is not
-          int n_dup = 0;
-#pragma unroll 4
-          for (int c4 = 0; c4 < BUCKET; c4 += 4) {
-            const uint4 k4 = lds128(a_pos_lb + c4 * 4);
-            n_dup += (static_cast<int>(k4.x) == q_enc) + (static_cast<int>(k4.y) == q_enc) + (static_cast<int>(k4.z) == q_enc) +
-                     (static_cast<int>(k4.w) == q_enc);
-          }
-          n_self += n_dup;
-        }
-        if (part * kPartCols < BUCKET && __any_sync(0xffffffffu, lonely && n_self > 1)) {
-          // the duplicates live in the look-back columns [0, BUCKET) of rows with win0 == 0: each part rewrites the blocks it wrote
-#pragma unroll 1
-          for (int c0 = part * kPartCols; c0 < (part + 1) * kPartCols; c0 += 32) {
-            uint32_t blk[16];
-            const uint32_t t_blk = t_row + p_col<BUCKET>(c0 >> 5);
-            tmem_ld16(t_blk, blk);
-            tmem_ld_wait();
-            if (lonely && n_self > 1) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int k0 = static_cast<int>(lds32(a_pos_lb + (c0 + 2 * i) * 4));
-                const int k1 = static_cast<int>(lds32(a_pos_lb + (c0 + 2 * i + 1) * 4));
-                blk[i] = (k0 == q_enc ? 0x00003F80u : 0u) | (k1 == q_enc ? 0x3F800000u : 0u);
-              }
-            }
-            tmem_st16(t_blk, blk);
-          }
-        }
-        if (lonely) {
-          row_sum = static_cast<float>(n_self);
-          row_max = sv;
-        }
-      }
+      // No exchange between the parts of a row: each leaves its partial row sum (>= 0; bit 31 = duplicate of the own token seen in
+      // the look-back chunk) for the epilogue thread of the row, which adds them up.  A row whose terms are all exactly zero sees
+      // only itself (with bound < 60 a visible key cannot underflow: s - bound >= -2*bound > -126): its P row stays zero and the
+      // epilogue substitutes the exact result (rp R8 "except when no other targets are available": softmax uniform over the self
+      // columns, all of which hold the query's own token, so out = v[own position], lse = self_value + log(#self columns)).
+      const float row_sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      sts32(a_part + (part * kQRows + m) * 4, __float_as_uint(row_sum) | (win0 == 0 ? dup : 0u));
       if (part == 0) {
-        // what the epilogue warps need for this row (double-buffered by tile parity: tile k+4 of this pair writes the same buffer, and
-        // its S is issued only after PV(k+2) has waited for epilogue(k))
+        // (buffers are per (tile parity, phase): tile k+4 writes the same ones, and its S is issued only after PV(k+2) has waited
+        // for epilogue(k))
         const uint32_t a_fin = smem_u32(smem + L::kOffFin) + (wg * 2 + ph) * L::kFinBytes;
-        sts32(a_fin + L::kFinSum + m * 4, __float_as_uint(row_sum));
         sts32(a_fin + L::kFinMax + m * 4, __float_as_uint(row_max));
         sts32(a_fin + L::kFinSlot + m * 4, static_cast<uint32_t>(my_slot));
         if (m == 0) sts32(a_fin + L::kFinRow, static_cast<uint32_t>(row_bh));
