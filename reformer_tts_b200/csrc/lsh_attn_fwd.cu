@@ -84,7 +84,10 @@ constexpr int kMaxParts = 4;
 constexpr int kFirstEpiWarp = kSoftmaxWarps;
 constexpr int kEpiThreads = 128;       // thread = query row = TMEM lane
 constexpr int kFirstLoaderWarp = kFirstEpiWarp + 4;
-constexpr int kLoaderWarps = 4;
+#ifndef RTTS_LOADER_WARPS
+#define RTTS_LOADER_WARPS 4
+#endif
+constexpr int kLoaderWarps = RTTS_LOADER_WARPS;
 #ifndef RTTS_LOADER_GROUPS
 #define RTTS_LOADER_GROUPS 1
 #endif
@@ -653,7 +656,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const uint32_t a_scale_lb = smem_u32(meta_p + L::kMetaScale) + kTail * 4, a_pos_lb = smem_u32(meta_p + L::kMetaPos) + kTail * 4;
       const uint32_t a_scale_mn = smem_u32(meta + L::kMetaScale) - BUCKET * 4, a_pos_mn = smem_u32(meta + L::kMetaPos) - BUCKET * 4;
       if (m == 0 && part == 0) RTTS_STAMP(2, k, 0);
-      mbar_wait(full + st_i, (k / kSlots) & 1);      // metadata of this tile (and of its look-back rows) is visible
+      // (sleeping waits: 16 polling warps would starve the loader warps they are waiting for of issue slots)
+      mbar_wait_relaxed(full + st_i, (k / kSlots) & 1, 100);      // metadata of this tile (and of its look-back rows) is visible
       if (m == 0 && part == 0) RTTS_STAMP(2, k, 3);
       const uint32_t a_meta = smem_u32(meta);
       const uint4 geo = lds128(a_meta + L::kMetaGeo);
@@ -667,7 +671,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       // stabiliser: |q_i| * score_scale * log2(e) = score_scale_log2^2 / key_scale[own row] for both key-norm variants ...
       // (key_scale = score_scale_log2 / |x| up to the norm's epsilon), times (1 + 2^-10) so rounding cannot push a score above it
       const float row_bound = p.score_scale_log2 * p.score_scale_log2 / __uint_as_float(lds32(a_meta + L::kMetaScale + m * 4)) * 1.001f;
-      mbar_wait(s_full + wg, ph);
+      mbar_wait_relaxed(s_full + wg, ph, 40);
       tc_fence_after_sync();
       if (m == 0 && part == 0) RTTS_STAMP(2, k, 1);
 
