@@ -369,7 +369,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const int g = k & 1;
       const uint32_t ph = (k >> 1) & 1;
       const uint32_t a_fin = smem_u32(smem + L::kOffFin) + (g * 2 + ph) * L::kFinBytes;
-      mbar_wait_relaxed(p_full + g, ph, 100);        // the group's row sums / slots are in shared memory
+      // Only o_full is waited for.  PV(k) is issued after p_full(k), so o_full(k) implies that the softmax group's partial sums and
+      // slots are in shared memory; and p_full must NOT be waited on here: p_full(k+2) needs only PV(k) (not this role), so with a
+      // slow epilogue the barrier can run two phases ahead of a waiter, whose parity test would then never pass.  o_full cannot:
+      // PV(k+2) waits for this role's o_free(k).
+      mbar_wait_relaxed(o_full + g, ph, 40);
+      tc_fence_after_sync();
       const uint32_t a_part = smem_u32(smem + L::kOffPart) + (g * 2 + ph) * kMaxParts * kQRows * 4;
       float row_sum = 0.f;
       uint32_t dup = 0;
@@ -390,8 +395,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
         row_max = p.self_value_log2;
       }
       const float inv_sum = 1.f / row_sum;
-      mbar_wait_relaxed(o_full + g, ph, 40);
-      tc_fence_after_sync();
       if (m == 0) RTTS_STAMP(3, k, 0);
       // O row / row sum -> bf16 -> this warp's staging tile (row = lane, 16-byte chunks swizzled by the row)
 #pragma unroll
@@ -409,16 +412,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           sts128(a_stage + lane * 128 + (((hh * 4 + q4) ^ (lane & 7)) << 4), u);
         }
       }
-      if (lonely) {
-        // out = v[own position] (every self column holds the query's own token); P of this row is all zero, so O was zero
-        const int pos = own_slot % p.T, b = row_bh / p.H, h = row_bh - b * p.H;
-        const uint4* vrow = reinterpret_cast<const uint4*>(p.v + (static_cast<int64_t>(b) * p.T + pos) * p.ld + h * kDh);
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) sts128(a_stage + lane * 128 + ((ch ^ (lane & 7)) << 4), __ldg(vrow + ch));
-      }
       tc_fence_before_sync();
       __syncwarp();                 // staging tile complete; all TMEM reads of this warp done
       if (lane == 0) mbar_arrive(o_free + g);      // O columns of this group may be overwritten
+      if (__any_sync(0xffffffffu, lonely)) {
+        if (lonely) {
+          // out = v[own position] (every self column holds the query's own token); P of this row is all zero, so O was zero
+          const int pos = own_slot % p.T, b = row_bh / p.H, h = row_bh - b * p.H;
+          const uint4* vrow = reinterpret_cast<const uint4*>(p.v + (static_cast<int64_t>(b) * p.T + pos) * p.ld + h * kDh);
+          uint4 vv[8];
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) vv[ch] = __ldg(vrow + ch);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) sts128(a_stage + lane * 128 + ((ch ^ (lane & 7)) << 4), vv[ch]);
+        }
+        __syncwarp();
+      }
       // scatter-store at the UNSORTED slot, one full 128-byte row per 8 lanes (four rows per instruction)
       const int64_t my_slot = row_base + own_slot;
       p.lse_rounds[my_slot] = (row_max + log2f(row_sum)) * kLn2;
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       for (int it = 0; it < 8; ++it) {
         const int row = it * 4 + (lane >> 3), ch = lane & 7;
         const uint4 u = lds128(a_stage + row * 128 + ((ch ^ (row & 7)) << 4));
-        const int64_t slot = row_base + static_cast<int>(lds32(a_fin + L::kFinSlot + ((warp & 3) * 32 + row) * 4));
+        const int64_t slot = row_base + __shfl_sync(0xffffffffu, own_slot, row);      // (registers: the shared copy may be rewritten by tile k+4 once o_free is signalled)
         reinterpret_cast<uint4*>(p.o_rounds + slot * kDh)[ch] = u;
       }
       __syncwarp();                 // the staging tile is free again

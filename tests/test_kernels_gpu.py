@@ -171,6 +171,42 @@ def test_attention_sizes_of_baseline_configs(ops, core):
     assert torch.isfinite(out.float()).all() and (out.float() - 1).abs().max().item() <= 2 ** -7    # rows of P sum to 1
 
 
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_full_size_with_heavy_padding(ops, core, causal):
+    """BASELINE.json config 2 decoder shape (B=20, T=1024, 8 heads, 8 rounds, bucket 64) with 224 padded positions per sequence
+    (800 mel frames padded to 1024).  22 % of the rows see only themselves, which makes the epilogue the slowest role: this is the
+    configuration in which a consumer waiting on a barrier that may run two phases ahead deadlocks.  Properties: finishes, is
+    deterministic, a padded query returns exactly its own value row (rp R8: everything but the self column masked), and one
+    (batch, head) slice equals the oracle."""
+    B, T, H, R, bucket, pad = 20, 1024, 8, 8, 64, 224
+    torch.manual_seed(5)
+    qk = torch.randn(B, T, H * 64, device=DEV).bfloat16()
+    v = torch.randn(B, T, H * 64, device=DEV).bfloat16()
+    rot = torch.randn(1, 64, R, (T // bucket) // 2, device=DEV)
+    mask = torch.ones(B, T, dtype=torch.uint8, device=DEV)
+    mask[:, T - pad:] = 0
+    buckets = ops.lsh_hash(qk, rot, H, R, T // bucket)
+    sticker, undo = ops.lsh_sort(buckets, T, R, T // bucket)
+    spec = ops.LSHSpec.reformer_pytorch(64, causal)
+    o1, l1 = ops.lsh_attn_fwd(qk, v, sticker, mask, spec, H, R, bucket)
+    o2, l2 = ops.lsh_attn_fwd(qk, v, sticker, mask, spec, H, R, bucket)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2) and torch.equal(l1, l2)
+    assert torch.isfinite(o1.float()).all() and torch.isfinite(l1).all()
+    v_bh = v.view(B, T, H, 64).permute(0, 2, 1, 3)                          # [B,H,T,64]
+    assert torch.equal(o1[:, :, :, T - pad:], v_bh[:, :, None, T - pad:].expand(B, H, R, pad, 64))
+    # one (batch, head) slice against the oracle, fed our bucket ids
+    b, h = 7, 3
+    bk = buckets[b, h].cpu().long().view(1, R * T)
+    st, ud = core.sort_buckets(bk, T)
+    q1, v1 = qk[b:b + 1, :, h * 64:(h + 1) * 64], v[b:b + 1, :, h * 64:(h + 1) * 64]
+    so, slse = core.chunk_attention(to_bh(q1, 1), to_bh(v1, 1), st, bucket, R, core.LSHSpec.reformer_pytorch(64, causal),
+                                    mask[b:b + 1].bool().cpu())
+    out_ref, o_ref, lse_ref = core.unsort_and_merge(so, slse, ud, R)
+    assert rel_l2(o1[b, h], o_ref[0]) <= TOL_BF16_STORED
+    assert ((l1[b, h].cpu() - lse_ref[0]).abs() <= 1e-4 + 2e-7 * lse_ref[0].abs()).all()
+
+
 # ---------------------------------------------------------------------------------------------- GEMM / row-wise kernels
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (256, 384, 512), (2048, 2048, 512), (1024, 512, 2048)])
 def test_gemm_layouts_and_epilogues(ops, m, n, k):
