@@ -817,6 +817,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
 // Round merge (rp R11): out[t] = sum_r o_r[t] * exp(lse_r[t] - logsumexp_r lse_r[t]).  8 lanes per (b,h,t) row,
 // each lane owns 16 bytes of the 128-byte head slice.  HBM-bound: reads R*(128+4) B, writes 128+4 B per row.
 // ------------------------------------------------------------------------------------------------------------
+// RC > 0: the number of rounds is a compile-time constant, so all R lse values and all R 16-byte slices of a row are requested
+// before anything is computed (R loads in flight per lane instead of one at a time).  RC == 0: any R, rolled loops.
+template <int RC>
 __global__ void __launch_bounds__(256) lsh_merge_fwd_kernel(const __nv_bfloat16* __restrict__ o_rounds,
                                                             const float* __restrict__ lse_rounds,
                                                             __nv_bfloat16* __restrict__ out, int64_t ld_out,
@@ -827,19 +830,38 @@ __global__ void __launch_bounds__(256) lsh_merge_fwd_kernel(const __nv_bfloat16*
   const int64_t bh = row / T;
   const int t = static_cast<int>(row - bh * T);
   const float* l = lse_rounds + bh * R * T + t;
-  float mx = -FLT_MAX;
-  for (int r = 0; r < R; ++r) mx = fmaxf(mx, l[static_cast<int64_t>(r) * T]);
-  float den = 0.f;
-  for (int r = 0; r < R; ++r) den += __expf(l[static_cast<int64_t>(r) * T] - mx);
-  const float inv_den = 1.f / den;
+  const uint4* o = reinterpret_cast<const uint4*>(o_rounds + (bh * R * T + t) * kDh) + c;
+  const int64_t o_step = static_cast<int64_t>(T) * (kDh * 2 / 16);      // uint4 elements between rounds
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int r = 0; r < R; ++r) {
-    const float w = __expf(l[static_cast<int64_t>(r) * T] - mx) * inv_den;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(o_rounds + ((bh * R + r) * T + t) * kDh) + c);
+  float mx = -FLT_MAX, den = 0.f;
+  auto add_row = [&](float w, const uint4& u) {
     acc[0] = fmaf(w, bf16_lo(u.x), acc[0]); acc[1] = fmaf(w, bf16_hi(u.x), acc[1]);
     acc[2] = fmaf(w, bf16_lo(u.y), acc[2]); acc[3] = fmaf(w, bf16_hi(u.y), acc[3]);
     acc[4] = fmaf(w, bf16_lo(u.z), acc[4]); acc[5] = fmaf(w, bf16_hi(u.z), acc[5]);
     acc[6] = fmaf(w, bf16_lo(u.w), acc[6]); acc[7] = fmaf(w, bf16_hi(u.w), acc[7]);
+  };
+  if (RC > 0) {
+    float lv[RC > 0 ? RC : 1];
+    uint4 ov[RC > 0 ? RC : 1];
+#pragma unroll
+    for (int r = 0; r < RC; ++r) lv[r] = __ldg(l + static_cast<int64_t>(r) * T);
+#pragma unroll
+    for (int r = 0; r < RC; ++r) ov[r] = __ldg(o + r * o_step);
+#pragma unroll
+    for (int r = 0; r < RC; ++r) mx = fmaxf(mx, lv[r]);
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+      lv[r] = __expf(lv[r] - mx);
+      den += lv[r];
+    }
+    const float inv_den = 1.f / den;
+#pragma unroll
+    for (int r = 0; r < RC; ++r) add_row(lv[r] * inv_den, ov[r]);
+  } else {
+    for (int r = 0; r < R; ++r) mx = fmaxf(mx, l[static_cast<int64_t>(r) * T]);
+    for (int r = 0; r < R; ++r) den += __expf(l[static_cast<int64_t>(r) * T] - mx);
+    const float inv_den = 1.f / den;
+    for (int r = 0; r < R; ++r) add_row(__expf(l[static_cast<int64_t>(r) * T] - mx) * inv_den, __ldg(o + r * o_step));
   }
   const int64_t b = bh / H;
   const int h = static_cast<int>(bh - b * H);
@@ -910,8 +932,16 @@ extern "C" int rtts_lsh_merge_fwd(const void* o_rounds, const float* lse_rounds,
   RTTS_REQUIRE(ld_out % 8 == 0, "rtts_lsh_merge_fwd: ld_out must be a multiple of 8");
   const int64_t rows = static_cast<int64_t>(B) * H * T;
   const int64_t blocks = (rows * 8 + 255) / 256;
-  lsh_merge_fwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(o_rounds), lse_rounds, static_cast<__nv_bfloat16*>(out), ld_out, lse, T, H, R, rows);
+  const auto launch = [&](auto kernel) {
+    kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(o_rounds), lse_rounds, static_cast<__nv_bfloat16*>(out), ld_out, lse, T, H, R, rows);
+  };
+  switch (R) {      // the reference configs use 8 (RP / HF default) and 4 (long-sequence sweep) hash rounds
+    case 8: launch(lsh_merge_fwd_kernel<8>); break;
+    case 4: launch(lsh_merge_fwd_kernel<4>); break;
+    case 2: launch(lsh_merge_fwd_kernel<2>); break;
+    default: launch(lsh_merge_fwd_kernel<0>); break;
+  }
   return check_launch("rtts_lsh_merge_fwd");
 }
 

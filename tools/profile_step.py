@@ -46,3 +46,11 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     bench.train_step(model, loss_fn, opt, data)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
+
+# kernels only, by name
+from torch.autograd import DeviceType  # noqa: E402
+ks = [e for e in prof.key_averages() if e.device_type == DeviceType.CUDA]
+tot_k = sum(e.self_device_time_total for e in ks)
+print(f"\nkernels only: {tot_k / 1e3:.2f} ms in {sum(e.count for e in ks)} launches")
+for e in sorted(ks, key=lambda e: -e.self_device_time_total)[:45]:
+    print(f"  {e.self_device_time_total / 1e3:8.3f} ms {100 * e.self_device_time_total / tot_k:5.1f}%  n={e.count:4d}  {e.key[:110]}")
