@@ -115,6 +115,10 @@ __device__ __forceinline__ void bwd_gather_tile(const AttnBwdParams& p, uint8_t*
   const int ahead_first = first_slot + kKeyRows >= RT ? first_slot + kKeyRows - RT : first_slot + kKeyRows;   // look-ahead chunk
   const int base_main = (first_slot / p.T) * p.T, base_ahead = (ahead_first / p.T) * p.T;
   const int64_t head_off = static_cast<int64_t>(h) * kBDh + c * 8;
+  const uint32_t ld32 = static_cast<uint32_t>(p.ld), ld_do32 = static_cast<uint32_t>(p.ld_do);
+  const __nv_bfloat16* qk_b = p.qk + static_cast<int64_t>(b) * p.T * p.ld + head_off;
+  const __nv_bfloat16* v_b = p.v + static_cast<int64_t>(b) * p.T * p.ld + head_off;
+  const __nv_bfloat16* do_b = p.dout + static_cast<int64_t>(b) * p.T * p.ld_do + head_off;
   // all sticker loads first (one exposed latency per tile), then every row copy, then the statistics while the copies fly
   int stv[kPasses];
 #pragma unroll
@@ -127,11 +131,11 @@ __device__ __forceinline__ void bwd_gather_tile(const AttnBwdParams& p, uint8_t*
     const int r = i * G + g;
     if (r < kQRows) {
       const int pos = stv[i] - (r < kKeyRows ? base_main : base_ahead);
-      const int64_t tok = static_cast<int64_t>(b) * p.T + pos;
       const uint32_t so = sw128_offset(r, c);
-      cp_async16(sX + so, p.qk + tok * p.ld + head_off);
-      cp_async16(sDO + so, p.dout + tok * p.ld_do + head_off);
-      if (r < kKeyRows) cp_async16(sV + so, p.v + tok * p.ld + head_off);
+      const uint32_t off = static_cast<uint32_t>(pos) * ld32, off_do = static_cast<uint32_t>(pos) * ld_do32;      // T * ld < 2^31 (checked by the host)
+      cp_async16(sX + so, qk_b + off);
+      cp_async16(sDO + so, do_b + off_do);
+      if (r < kKeyRows) cp_async16(sV + so, v_b + off);
     }
   }
   cp_async_commit();
@@ -539,6 +543,7 @@ extern "C" int rtts_lsh_attn_bwd(const void* qk, const void* v, int64_t ld, cons
   RTTS_REQUIRE(dh == kBDh, "rtts_lsh_attn_bwd: head size %d unsupported (64 only)", dh);
   RTTS_REQUIRE(bucket == 64 || bucket == 128, "rtts_lsh_attn_bwd: bucket size %d unsupported (64 or 128)", bucket);
   RTTS_REQUIRE(T % (2 * bucket) == 0, "rtts_lsh_attn_bwd: T=%d must be a multiple of 2*bucket", T);
+  RTTS_REQUIRE(static_cast<int64_t>(T) * ld < (1ll << 31) && static_cast<int64_t>(T) * ld_dout < (1ll << 31), "rtts_lsh_attn_bwd: T * ld must be below 2^31");
   RTTS_REQUIRE(ld % 8 == 0 && ld_dout % 8 == 0 && ((reinterpret_cast<uintptr_t>(qk) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0,
                "rtts_lsh_attn_bwd: tensors must be 16-byte aligned");
   AttnBwdParams p;

@@ -477,6 +477,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       for (int i = 0; i < kPasses; ++i) x = (i == which) ? a[i] : x;
       return x;
     };
+    const uint32_t ld32 = static_cast<uint32_t>(p.ld);      // 32-bit row offsets: one IMAD + one IMAD.WIDE per copy instead of 64-bit multiplies
     int pos_cur[kPasses], st_nxt[kPasses], st_nn[kPasses];
     float ssq_cur[2] = {1.f, 1.f}, ssq_nxt[2] = {1.f, 1.f};
     uint32_t valid_cur[2] = {1u, 1u}, valid_nxt[2] = {1u, 1u};
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
 #pragma unroll
         for (int i = 0; i < kLbPasses; ++i) {
           const int j = kTail + i * kGroups + grp;
-          const int64_t off = static_cast<int64_t>(lb[i]) * p.ld;
+          const uint32_t off = static_cast<uint32_t>(lb[i]) * ld32;      // element offset inside the batch entry: T * ld < 2^31 (checked by the host)
           const uint32_t so = sw128_offset(j, c);
           cp_async16(sKp + so, qk_b + off);
           cp_async16(sVp + so, v_b + off);
@@ -591,7 +592,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
 #pragma unroll
       for (int i = 0; i < kPasses; ++i) {
         const int j = i * kGroups + grp;
-        const int64_t off = static_cast<int64_t>(pos_cur[i]) * p.ld;
+        const uint32_t off = static_cast<uint32_t>(pos_cur[i]) * ld32;
         const uint32_t so = sw128_offset(j, c);
         cp_async16(sK + so, qk_b + off);
         cp_async16(sV + so, v_b + off);
@@ -902,7 +903,7 @@ extern "C" int rtts_lsh_attn_fwd(const void* qk, const void* v, int64_t ld, cons
   RTTS_REQUIRE(ld % 8 == 0 && ((reinterpret_cast<uintptr_t>(qk) | reinterpret_cast<uintptr_t>(v) |
                                 reinterpret_cast<uintptr_t>(o_rounds)) & 15) == 0,
                "rtts_lsh_attn_fwd: tensors must be 16-byte aligned");
-  RTTS_REQUIRE(static_cast<int64_t>(T) < kPadFlag, "rtts_lsh_attn_fwd: T too large");
+  RTTS_REQUIRE(static_cast<int64_t>(T) < kPadFlag && static_cast<int64_t>(T) * ld < (1ll << 31), "rtts_lsh_attn_fwd: T * ld must be below 2^31");
   AttnFwdParams p;
   p.qk = static_cast<const __nv_bfloat16*>(qk);
   p.v = static_cast<const __nv_bfloat16*>(v);
