@@ -88,6 +88,30 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   __trap();
 }
 
+// Same, barrier given as a shared-space address (saves the generic-to-shared conversion in per-tile code).
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_relaxed_a(uint32_t bar_addr, uint32_t parity, uint32_t sleep_ns) {
+  if (mbar_try_wait_a(bar_addr, parity)) return;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    __nanosleep(sleep_ns);
+    if (mbar_try_wait_a(bar_addr, parity)) return;
+  }
+  __trap();
+}
+
 // ---------------------------------------------------------------- proxies / fences
 // Generic-proxy writes to shared memory (st.shared, cp.async) become visible to the async proxy
 // (tcgen05.mma operand reads, TMA stores) only after this fence.

@@ -654,29 +654,33 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
     auto pair_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp_id), "n"(kSoftmaxThreads) : "memory"); };
     // the block of 32 key columns holding this warp's own columns (rows 32*(m/32) .. +31) and the quarter that owns it (warp-uniform)
     const int diag_col = BUCKET + (m & ~31);
+    // Every instruction of this per-tile prologue is executed by 16 warps (the kernel is bound by instruction issue), so the ring
+    // position is carried incrementally instead of being re-derived from k (k % 6, k / 6 are multiply-high sequences).
+    const uint32_t a_meta0 = smem_u32(smem + L::kOffMeta), a_full0 = smem_u32(full);
+    int st_i = grp_id % kSlots;                     // ring slot of tile k
+    uint32_t full_par = 0;                          // (k / kSlots) & 1
     for (int k = grp_id; k < my_tiles; k += kGroups) {
       const int wg = k & 1;                         // TMEM region / barrier set of this tile
       const uint32_t ph = (k >> 1) & 1;
       const uint32_t t_row = t_lane + wg * 256;
       const uint32_t a_part = smem_u32(smem + L::kOffPart) + (wg * 2 + ph) * kMaxParts * kQRows * 4;      // float [kParts][128 rows] of this tile
-      const int st_i = k % kSlots, sp_i = (st_i + kSlots - 1) % kSlots;
-      const uint8_t* meta = smem + L::kOffMeta + st_i * L::kMetaBytes;
-      const uint8_t* meta_p = smem + L::kOffMeta + sp_i * L::kMetaBytes;
+      const int sp_i = st_i == 0 ? kSlots - 1 : st_i - 1;
+      const uint32_t a_meta = a_meta0 + st_i * L::kMetaBytes, a_meta_p = a_meta0 + sp_i * L::kMetaBytes;
       // key column j of the tile: j < BUCKET -> look-back row kTail + j of the previous slot, else main row j - BUCKET
-      const uint32_t a_scale_lb = smem_u32(meta_p + L::kMetaScale) + kTail * 4, a_pos_lb = smem_u32(meta_p + L::kMetaPos) + kTail * 4;
-      const uint32_t a_scale_mn = smem_u32(meta + L::kMetaScale) - BUCKET * 4, a_pos_mn = smem_u32(meta + L::kMetaPos) - BUCKET * 4;
+      const uint32_t a_scale_lb = a_meta_p + L::kMetaScale + kTail * 4, a_pos_lb = a_meta_p + L::kMetaPos + kTail * 4;
+      const uint32_t a_scale_mn = a_meta + L::kMetaScale - BUCKET * 4, a_pos_mn = a_meta + L::kMetaPos - BUCKET * 4;
       if (m == 0 && part == 0) RTTS_STAMP(2, k, 0);
       // (sleeping waits: 16 polling warps would starve the loader warps they are waiting for of issue slots)
-      mbar_wait_relaxed(full + st_i, (k / kSlots) & 1, 100);      // metadata of this tile (and of its look-back rows) is visible
+      mbar_wait_relaxed_a(a_full0 + st_i * 8, full_par, 100);      // metadata of this tile (and of its look-back rows) is visible
       if (m == 0 && part == 0) RTTS_STAMP(2, k, 3);
-      const uint32_t a_meta = smem_u32(meta);
+      st_i += kGroups;                              // (for the next tile)
+      if (st_i >= kSlots) { st_i -= kSlots; full_par ^= 1u; }
       const uint4 geo = lds128(a_meta + L::kMetaGeo);
       const int row_bh = static_cast<int>(geo.x), base_main = static_cast<int>(geo.y);
       const bool round_start = geo.z != 0;
       const int q_enc = static_cast<int>(lds32(a_meta + L::kMetaPos + m * 4));
       int q_limit = p.causal ? (q_enc & ~kPadFlag) : (kPadFlag - 1);
       if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && (q_enc & kPadFlag)) q_limit = -1;   // padded query: all masked
-      const int my_slot = base_main + (q_enc & ~kPadFlag);        // unsorted slot = round * T + position
       const bool exact = static_cast<int>(lds32(a_meta + L::kMetaTag)) == k + 1;
       // stabiliser: |q_i| * score_scale * log2(e) = score_scale_log2^2 / key_scale[own row] for both key-norm variants ...
       // (key_scale = score_scale_log2 / |x| up to the norm's epsilon), times (1 + 2^-10) so rounding cannot push a score above it
@@ -795,7 +799,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
         // for epilogue(k))
         const uint32_t a_fin = smem_u32(smem + L::kOffFin) + (wg * 2 + ph) * L::kFinBytes;
         sts32(a_fin + L::kFinMax + m * 4, __float_as_uint(row_max));
-        sts32(a_fin + L::kFinSlot + m * 4, static_cast<uint32_t>(my_slot));
+        sts32(a_fin + L::kFinSlot + m * 4, static_cast<uint32_t>(base_main + (q_enc & ~kPadFlag)));      // unsorted slot = round * T + position
         if (m == 0) sts32(a_fin + L::kFinRow, static_cast<uint32_t>(row_bh));
       }
       tmem_st_wait();
