@@ -54,6 +54,17 @@ int rtts_lsh_hash(const void* qk, int64_t ld, const float* rot, int rot_heads, c
                   int use_pad_bucket, int32_t* buckets, float* sumsq, int B, int T, int H, int dh, int R,
                   int n_buckets, void* stream);
 
+/* The same hash on the tensor pipe (tcgen05): each fp32 rotation is split into three bf16 parts whose sum is the fp32 value, so every
+ * product is formed exactly and only the fp32 accumulation rounds (as in the reference's fp32 einsum).  Same inputs / outputs as
+ * rtts_lsh_hash plus `workspace` (device, rtts_lsh_hash_tc_workspace_bytes bytes, 16-byte aligned, overwritten on every call).
+ * Supported when rtts_lsh_hash_tc_supported() != 0: dh = 64, T % 128 == 0, R * n_buckets / 2 a multiple of 16 in [16, 256];
+ * callers fall back to rtts_lsh_hash otherwise (e.g. the 16k-token sweep with 512 projections). */
+int rtts_lsh_hash_tc(const void* qk, int64_t ld, const float* rot, int rot_heads, const uint8_t* pad_mask,
+                     int use_pad_bucket, int32_t* buckets, float* sumsq, void* workspace, int B, int T, int H, int dh,
+                     int R, int n_buckets, void* stream);
+int64_t rtts_lsh_hash_tc_workspace_bytes(int rot_heads, int R, int n_buckets);
+int rtts_lsh_hash_tc_supported(int T, int dh, int R, int n_buckets);
+
 /* sumsq fp32 [B,H,T] = |qk[b,t,h,:]|^2 on its own (same values rtts_lsh_hash emits). */
 int rtts_lsh_sumsq(const void* qk, int64_t ld, float* sumsq, int B, int T, int H, int dh, void* stream);
 

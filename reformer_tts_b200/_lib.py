@@ -27,6 +27,9 @@ SIGNATURES = {
     "rtts_lsh_sumsq": [_P, _L, _P, _I, _I, _I, _I, _P],
     "rtts_lsh_sort": [_P, _P, _P, _I, _I, _I, _I, _P],
     "rtts_lsh_attn_fwd": [_P, _P, _L, _P, _P, _P, _SPEC, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "rtts_lsh_hash_tc": [_P, _L, _P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "rtts_lsh_hash_tc_supported": [_I, _I, _I, _I],
+    "rtts_lsh_hash_tc_workspace_bytes": [_I, _I, _I],
     "rtts_lsh_merge_fwd": [_P, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P],
     "rtts_lsh_delta": [_P, _P, _L, _P, _I, _I, _I, _I, _P],
     "rtts_lsh_attn_bwd": [_P, _P, _L, _P, _P, _P, _SPEC, _P, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
@@ -36,6 +39,8 @@ SIGNATURES = {
     "rtts_gemm_bf16": [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P],
     "rtts_cast_bf16_colsum": [_P, _P, _P, _I, _I, _P],
 }
+
+RESTYPES = {"rtts_lsh_hash_tc_workspace_bytes": c_int64}      # everything else returns an int status / flag
 
 _lib = None
 
@@ -53,7 +58,7 @@ def load() -> ctypes.CDLL:
         lib.rtts_abi_version.argtypes = []
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError here = header / library mismatch: fail loudly
-            fn.restype = c_int
+            fn.restype = RESTYPES.get(name, c_int)
             fn.argtypes = argtypes
         _lib = lib
     return _lib

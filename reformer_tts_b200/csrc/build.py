@@ -9,7 +9,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 LIB = HERE.parent / "libreformer_b200.so"
-SOURCES = ["api.cu", "lsh_bucket.cu", "lsh_attn_fwd.cu", "lsh_attn_bwd.cu", "gemm.cu", "rowwise.cu"]
+SOURCES = ["api.cu", "lsh_bucket.cu", "lsh_hash_tc.cu", "lsh_attn_fwd.cu", "lsh_attn_bwd.cu", "gemm.cu", "rowwise.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",
          "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"), "-I", str(HERE)]

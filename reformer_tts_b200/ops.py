@@ -142,8 +142,14 @@ def lsh_hash(qk: torch.Tensor, rot: torch.Tensor, n_heads: int, n_rounds: int, n
         pad_mask = pad_mask.contiguous()
     out = torch.empty((b, n_heads, n_rounds * t), dtype=torch.int32, device=qk.device)
     sumsq = torch.empty((b, n_heads, t), dtype=torch.float32, device=qk.device) if return_sumsq else None
-    _launch(_tag("lsh_hash", locals()), "rtts_lsh_hash", _ptr(qk), ld, _ptr(rot), rot.shape[0], _ptr(pad_mask), int(use_pad_bucket), _ptr(out),
-              _ptr(sumsq), b, t, n_heads, dh, n_rounds, n_buckets, _stream())
+    if _lib.load().rtts_lsh_hash_tc_supported(t, dh, n_rounds, n_buckets):
+        # tensor-pipe path: exact products of the bf16 rows with the three-way bf16 split of the fp32 rotations
+        ws = torch.empty(_lib.load().rtts_lsh_hash_tc_workspace_bytes(rot.shape[0], n_rounds, n_buckets) // 2, dtype=torch.bfloat16, device=qk.device)
+        _launch(_tag("lsh_hash", locals()), "rtts_lsh_hash_tc", _ptr(qk), ld, _ptr(rot), rot.shape[0], _ptr(pad_mask), int(use_pad_bucket),
+                _ptr(out), _ptr(sumsq), _ptr(ws), b, t, n_heads, dh, n_rounds, n_buckets, _stream())
+    else:
+        _launch(_tag("lsh_hash", locals()), "rtts_lsh_hash", _ptr(qk), ld, _ptr(rot), rot.shape[0], _ptr(pad_mask), int(use_pad_bucket), _ptr(out),
+                _ptr(sumsq), b, t, n_heads, dh, n_rounds, n_buckets, _stream())
     return (out, sumsq) if return_sumsq else out
 
 
