@@ -26,7 +26,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NCU_DRAM_BYTES_FWD_DEC_CFG2 = 61_466_880 + 120_846_848      # profiles/r1_attn_v2_ncu_full.txt (read + write), B=20 T=1024 R=8 bucket 64
+NCU_DRAM_BYTES_FWD_DEC_CFG2 = 63_337_472 + 121_166_336      # profiles/r1_attn_v3_ncu_full.txt (read + write), B=20 T=1024 R=8 bucket 64
 DEFAULT_CONFIG = "bucket-size-64-18-06"       # BASELINE.json configs[1]: the configuration the metric is quoted on
 PHONEMES, FRAMES, N_MELS = 200, 800, 80       # "~200 phonemes -> ~800x80 mel frames" (BASELINE.json configs[0])
 

@@ -57,8 +57,9 @@ int rtts_lsh_hash(const void* qk, int64_t ld, const float* rot, int rot_heads, c
 /* The same hash on the tensor pipe (tcgen05): each fp32 rotation is split into three bf16 parts whose sum is the fp32 value, so every
  * product is formed exactly and only the fp32 accumulation rounds (as in the reference's fp32 einsum).  Same inputs / outputs as
  * rtts_lsh_hash plus `workspace` (device, rtts_lsh_hash_tc_workspace_bytes bytes, 16-byte aligned, overwritten on every call).
- * Supported when rtts_lsh_hash_tc_supported() != 0: dh = 64, T % 128 == 0, R * n_buckets / 2 a multiple of 16 in [16, 256];
- * callers fall back to rtts_lsh_hash otherwise (e.g. the 16k-token sweep with 512 projections). */
+ * Supported when rtts_lsh_hash_tc_supported() != 0: dh = 64, T % 128 == 0, n_buckets / 2 <= 256, and the projections of one launch
+ * (all R rounds when R * n_buckets / 2 <= 256, else the largest group of whole rounds that fits: the 16k-token sweep hashes its 4
+ * rounds of 128 projections in two launches) a multiple of 16; callers fall back to rtts_lsh_hash otherwise. */
 int rtts_lsh_hash_tc(const void* qk, int64_t ld, const float* rot, int rot_heads, const uint8_t* pad_mask,
                      int use_pad_bucket, int32_t* buckets, float* sumsq, void* workspace, int B, int T, int H, int dh,
                      int R, int n_buckets, void* stream);

@@ -38,11 +38,13 @@ struct HashTcSmem {
 };
 
 // rot fp32 [rot_heads][64][P]  ->  ws bf16 [rot_heads][3 parts: lo, mid, hi][P][64]
-__global__ void __launch_bounds__(256) lsh_hash_split_kernel(const float* __restrict__ rot, __nv_bfloat16* __restrict__ ws, int P, int total) {
+// (P projections starting at column p0 of the P_all = R * n_buckets / 2 the rotation tensor holds: one group of hash rounds)
+__global__ void __launch_bounds__(256) lsh_hash_split_kernel(const float* __restrict__ rot, __nv_bfloat16* __restrict__ ws, int P, int P_all, int p0,
+                                                             int total) {
   const int idx = blockIdx.x * 256 + threadIdx.x;      // (hr, p, k), k fastest
   if (idx >= total) return;
   const int k = idx & 63, p = (idx >> 6) % P, hr = (idx >> 6) / P;
-  const float w = rot[(static_cast<int64_t>(hr) * 64 + k) * P + p];
+  const float w = rot[(static_cast<int64_t>(hr) * 64 + k) * P_all + p0 + p];
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
   const float e1 = w - __bfloat162float(hi);
   const __nv_bfloat16 mid = __float2bfloat16_rn(e1);
@@ -59,7 +61,8 @@ struct HashTcParams {
   const uint8_t* pad_mask;
   int32_t* buckets;
   float* sumsq;
-  int T, H, R, n_buckets, use_pad_bucket, rot_heads;
+  int T, H, R, n_buckets, use_pad_bucket, rot_heads;      // R = rounds of THIS launch
+  int r_base, R_all;      // first round of this launch, rounds of the bucket tensor
   int tiles_per_seq;      // T / 128
   int num_tiles;          // tiles this grid row (blockIdx.y) walks: B*H*T/128 (shared rotations) or B*T/128 (per head)
 };
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) lsh_hash_mma_kernel(const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);            // this warp is done with the stage
       const bool padded = p.use_pad_bucket && p.pad_mask != nullptr && p.pad_mask[static_cast<int64_t>(b) * p.T + t] == 0;
-      int32_t* out = p.buckets + bh * p.R * p.T + t;
+      int32_t* out = p.buckets + (bh * p.R_all + p.r_base) * p.T + t;
       mbar_wait(acc_full + a, (i >> 1) & 1);
       tc_fence_after_sync();
       float vmax = 0.f, vmin = 0.f;
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) lsh_hash_mma_kernel(const __gri
             // torch.argmax returns the FIRST maximum of cat([r, -r]): every +r precedes every -r, so a tie goes to +r
             int id = (vmax >= -vmin) ? imax : half + imin;
             if (padded) id = p.n_buckets;
-            out[static_cast<int64_t>(r) * p.T] = r * stride + id;
+            out[static_cast<int64_t>(r) * p.T] = (p.r_base + r) * stride + id;
             idx = 0;
             ++r;
           }
@@ -233,31 +236,37 @@ __global__ void __launch_bounds__(kHtThreads, 1) lsh_hash_mma_kernel(const __gri
 
 using namespace rtts;
 
+// Rounds per launch: all of them when their projections fit one accumulator (<= 256 columns), else the largest divisor of R that does.
+static int rounds_per_launch(int R, int n_buckets) {
+  const int half = n_buckets / 2;
+  if (half < 1 || half > kHtMaxP) return 0;
+  int g = R;
+  while (g > 1 && (g * half > kHtMaxP || R % g != 0)) --g;
+  return g * half <= kHtMaxP ? g : 0;
+}
+
 extern "C" int64_t rtts_lsh_hash_tc_workspace_bytes(int rot_heads, int R, int n_buckets) {
-  return static_cast<int64_t>(rot_heads) * 3 * R * (n_buckets / 2) * 64 * 2;
+  const int g = rounds_per_launch(R, n_buckets);
+  return static_cast<int64_t>(rot_heads) * 3 * (g > 0 ? g : R) * (n_buckets / 2) * 64 * 2;
 }
 
 extern "C" int rtts_lsh_hash_tc_supported(int T, int dh, int R, int n_buckets) {
-  const int P = R * (n_buckets / 2);
-  return dh == 64 && T % 128 == 0 && n_buckets % 2 == 0 && P % 16 == 0 && P >= 16 && P <= kHtMaxP;
+  const int g = rounds_per_launch(R, n_buckets);
+  const int P = g * (n_buckets / 2);      // projections per launch
+  return dh == 64 && T % 128 == 0 && n_buckets % 2 == 0 && g > 0 && P % 16 == 0 && P >= 16;
 }
 
 extern "C" int rtts_lsh_hash_tc(const void* qk, int64_t ld, const float* rot, int rot_heads, const uint8_t* pad_mask, int use_pad_bucket,
                                 int32_t* buckets, float* sumsq, void* workspace, int B, int T, int H, int dh, int R, int n_buckets,
                                 void* stream) {
   RTTS_REQUIRE(qk && rot && buckets && workspace, "rtts_lsh_hash_tc: null pointer");
-  RTTS_REQUIRE(rtts_lsh_hash_tc_supported(T, dh, R, n_buckets), "rtts_lsh_hash_tc: unsupported shape (T %% 128, R * n_buckets / 2 in 16..256 step 16, dh 64)");
+  RTTS_REQUIRE(rtts_lsh_hash_tc_supported(T, dh, R, n_buckets), "rtts_lsh_hash_tc: unsupported shape (dh 64, T %% 128, projections per launch a multiple of 16)");
   RTTS_REQUIRE(rot_heads == 1 || rot_heads == H, "rtts_lsh_hash_tc: rot_heads must be 1 or H");
   RTTS_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(qk) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
                "rtts_lsh_hash_tc: qk / workspace must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int P = R * (n_buckets / 2);
-  const int total = rot_heads * P * 64;
-  lsh_hash_split_kernel<<<(total + 255) / 256, 256, 0, s>>>(rot, static_cast<__nv_bfloat16*>(workspace), P, total);
-  int rc = check_launch("rtts_lsh_hash_tc (split)");
-  if (rc != kOk) return rc;
   CUtensorMap tmap;
-  rc = make_tmap_bf16(&tmap, qk, static_cast<uint64_t>(H) * 64, static_cast<uint64_t>(B) * T, ld, 64, 128);
+  int rc = make_tmap_bf16(&tmap, qk, static_cast<uint64_t>(H) * 64, static_cast<uint64_t>(B) * T, ld, 64, 128);
   if (rc != kOk) return rc;
   static bool configured = false;
   if (!configured) {
@@ -265,14 +274,27 @@ extern "C" int rtts_lsh_hash_tc(const void* qk, int64_t ld, const float* rot, in
     if (e != cudaSuccess) return fail(kErrCuda, "rtts_lsh_hash_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
+  const int half = n_buckets / 2, P_all = R * half;
+  const int g = rounds_per_launch(R, n_buckets), P = g * half;
   HashTcParams p;
   p.ws = static_cast<const __nv_bfloat16*>(workspace);
-  p.pad_mask = pad_mask; p.buckets = buckets; p.sumsq = sumsq;
-  p.T = T; p.H = H; p.R = R; p.n_buckets = n_buckets; p.use_pad_bucket = use_pad_bucket; p.rot_heads = rot_heads;
+  p.pad_mask = pad_mask; p.buckets = buckets;
+  p.T = T; p.H = H; p.R = g; p.R_all = R; p.n_buckets = n_buckets; p.use_pad_bucket = use_pad_bucket; p.rot_heads = rot_heads;
   p.tiles_per_seq = T / 128;
   p.num_tiles = rot_heads == 1 ? B * H * p.tiles_per_seq : B * p.tiles_per_seq;
   const int per_row = rot_heads == 1 ? kNumSMs : (kNumSMs / H > 0 ? kNumSMs / H : 1);
   dim3 grid(p.num_tiles < per_row ? p.num_tiles : per_row, rot_heads == 1 ? 1 : H);
-  lsh_hash_mma_kernel<<<grid, kHtThreads, HashTcSmem::kTotal, s>>>(tmap, p);
-  return check_launch("rtts_lsh_hash_tc");
+  // one launch per group of g rounds (all R at once unless R * n_buckets / 2 > 256); the workspace is reused in stream order
+  for (int r0 = 0; r0 < R; r0 += g) {
+    const int total = rot_heads * P * 64;
+    lsh_hash_split_kernel<<<(total + 255) / 256, 256, 0, s>>>(rot, static_cast<__nv_bfloat16*>(workspace), P, P_all, r0 * half, total);
+    rc = check_launch("rtts_lsh_hash_tc (split)");
+    if (rc != kOk) return rc;
+    p.r_base = r0;
+    p.sumsq = r0 == 0 ? sumsq : nullptr;
+    lsh_hash_mma_kernel<<<grid, kHtThreads, HashTcSmem::kTotal, s>>>(tmap, p);
+    rc = check_launch("rtts_lsh_hash_tc");
+    if (rc != kOk) return rc;
+  }
+  return kOk;
 }

@@ -25,10 +25,10 @@ def core():
 # ---------------------------------------------------------------------------------------------- hash / sort
 @pytest.mark.parametrize("nb,per_head,pad,T", [(4, False, False, 256), (8, False, False, 1024), (16, False, False, 1024),
                                                (16, True, True, 1024), (8, True, False, 256), (256, False, False, 2048),
-                                               (64, False, False, 4096), (128, True, False, 8192)])
+                                               (64, False, False, 4096), (128, True, False, 8192), (6, False, False, 384)])
 def test_hash_bit_exact(ops, core, nb, per_head, pad, T):
     torch.manual_seed(nb + T)
-    # projections per token P = R * nb / 2: 16 .. 256 run on the tensor pipe (rtts_lsh_hash_tc), 512 (nb = 256) on the fp32 FMA kernel
+    # projections per token P = R * nb / 2: 16 .. 256 are one tensor-pipe launch (rtts_lsh_hash_tc), 512 (nb = 256) two launches of two rounds
     B, H, R = 3 if T <= 2048 else 1, 8, 8 if nb < 64 else 4
     qk = torch.randn(B, T, H * 64, device=DEV).bfloat16()
     rot = torch.randn(H if per_head else 1, 64, R, nb // 2, device=DEV)
