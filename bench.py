@@ -182,6 +182,8 @@ def run_ours(args, kwargs, world, rank, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries the ONE result line: whatever NCCL_DEBUG asks NCCL to print (e.g. its version banner) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = True      # non-hot-path torch modules (cross-attention, pre/post nets): fp32 storage, TF32 math
     torch.backends.cudnn.allow_tf32 = True
