@@ -182,9 +182,19 @@ def run_ours(args, kwargs, world, rank, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries the ONE result line: whatever NCCL_DEBUG asks NCCL to print (e.g. its version banner) goes to stderr
+        # stdout carries the ONE result line: whatever NCCL_DEBUG asks NCCL to print while the communicator comes up (its version
+        # banner goes to the process's stdout whatever NCCL_DEBUG_FILE says) is sent to stderr instead
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     torch.backends.cuda.matmul.allow_tf32 = True      # non-hot-path torch modules (cross-attention, pre/post nets): fp32 storage, TF32 math
     torch.backends.cudnn.allow_tf32 = True
     torch.manual_seed(42)                               # same initial weights on every rank

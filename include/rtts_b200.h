@@ -133,6 +133,8 @@ int rtts_layernorm_bwd(const float* dy, const float* x, const float* gamma, cons
 #define RTTS_EPI_OUT_BF16 8  /* C is bf16 (else fp32)                    */
 #define RTTS_EPI_ATOMIC 16   /* C (fp32) += result, split-K allowed      */
 #define RTTS_EPI_COLSUM 32   /* also accumulate column sums into colsum  */
+#define RTTS_EPI_RESID_ADD 64   /* C (fp32) = resid + result: `gate` points at the fp32 residual [M,N], ldgate its row stride   */
+#define RTTS_EPI_RESID_SUB 128  /* C (fp32) = resid - result (reversible reconstruction x1 = y1 - f(x2)); C may alias resid */
 
 /* C[M,N] = epilogue(A . B^T).  Operands bf16, fp32 accumulate in TMEM (tcgen05).
  * a_mn_major = 0: A is [M,K] row-major (lda = K stride); 1: A is stored [K,M] row-major.

@@ -40,7 +40,8 @@ class _CrossAttentionFn(torch.autograd.Function):
         o2 = o.detach().transpose(1, 2).reshape(b * t, d)
         if not o2.is_contiguous():
             o2 = o2.contiguous()
-        y = ops.gemm(o2, wo_bf16, bias=b_out).view(b, t, d)
+        resid, resid_sub = ops.ResidualRequest.take(x.shape, x.device)     # reversible residual fused into the output projection
+        y = ops.gemm(o2, wo_bf16, bias=b_out, resid=resid, resid_sub=resid_sub).view(b, t, d)
         ctx.inner = (ql, kl, vl, o) if need_grad else None
         ctx.has_ln = ln_w is not None
         ctx.dims = (b, t, s, d, h)

@@ -169,6 +169,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
       const int row = m0 + quarter * 32 + lane;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        // residual rows of this chunk (coalesced, the layout of the store phase): requested before anything else so that their
+        // latency hides under the TMEM load and the staging pass
+        float4 rv[8];
+        if (epi & (RTTS_EPI_RESID_ADD | RTTS_EPI_RESID_SUB)) {
+          const float* rbase = reinterpret_cast<const float*>(p.gate) + static_cast<int64_t>(m0 + quarter * 32) * p.ldgate + n0 + c0;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) rv[it] = *reinterpret_cast<const float4*>(rbase + static_cast<int64_t>(it * 4 + srow) * p.ldgate + sch * 4);
+        }
         uint32_t raw[32];
         tmem_ld32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c0, raw);
         tmem_ld_wait();
@@ -241,10 +249,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
                    make_uint4(__float_as_uint(r[q * 4]), __float_as_uint(r[q * 4 + 1]), __float_as_uint(r[q * 4 + 2]), __float_as_uint(r[q * 4 + 3])));
           __syncwarp();
           float* base = static_cast<float*>(p.C) + static_cast<int64_t>(m0 + quarter * 32) * p.ldc + col;
+          if (epi & (RTTS_EPI_RESID_ADD | RTTS_EPI_RESID_SUB)) {
+            // residual stream fused into the store: C = resid + result (reversible forward) or resid - result (reconstruction of the
+            // block input in the reversible backward).  Same coalesced 16-byte accesses as the store; C may alias resid.
+            const float sgn = (epi & RTTS_EPI_RESID_SUB) ? -1.f : 1.f;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + srow;
-            reinterpret_cast<uint4*>(base + static_cast<int64_t>(rr) * p.ldc)[sch] = lds128(stage + rr * 128 + ((sch ^ (rr & 7)) << 4));
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + srow;
+              const uint4 u = lds128(stage + rr * 128 + ((sch ^ (rr & 7)) << 4));
+              float4 o;
+              o.x = fmaf(sgn, __uint_as_float(u.x), rv[it].x); o.y = fmaf(sgn, __uint_as_float(u.y), rv[it].y);
+              o.z = fmaf(sgn, __uint_as_float(u.z), rv[it].z); o.w = fmaf(sgn, __uint_as_float(u.w), rv[it].w);
+              *reinterpret_cast<float4*>(base + static_cast<int64_t>(rr) * p.ldc + sch * 4) = o;
+            }
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + srow;
+              reinterpret_cast<uint4*>(base + static_cast<int64_t>(rr) * p.ldc)[sch] = lds128(stage + rr * 128 + ((sch ^ (rr & 7)) << 4));
+            }
           }
           __syncwarp();
         }
@@ -318,6 +341,10 @@ extern "C" int rtts_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
                "rtts_gemm_bf16: RTTS_EPI_ATOMIC cannot be combined with other epilogue flags");
   RTTS_REQUIRE(!(epilogue & RTTS_EPI_BIAS) || bias, "rtts_gemm_bf16: bias flag without bias pointer");
   RTTS_REQUIRE(!(epilogue & RTTS_EPI_GATE) || gate, "rtts_gemm_bf16: gate flag without gate pointer");
+  constexpr int kResid = RTTS_EPI_RESID_ADD | RTTS_EPI_RESID_SUB;
+  RTTS_REQUIRE(!(epilogue & kResid) || (gate && !(epilogue & (RTTS_EPI_GATE | RTTS_EPI_OUT_BF16 | RTTS_EPI_ATOMIC)) && (epilogue & kResid) != kResid &&
+                                        ldgate % 4 == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0),
+               "rtts_gemm_bf16: a residual needs its fp32 pointer in `gate` (16-byte aligned), an fp32 non-atomic output and one of ADD / SUB");
   RTTS_REQUIRE(!(epilogue & RTTS_EPI_COLSUM) || colsum, "rtts_gemm_bf16: colsum flag without colsum pointer");
   RTTS_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && (ldgate % 8 == 0), "rtts_gemm_bf16: leading dimensions must be multiples of 8");
   RTTS_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) == 0,

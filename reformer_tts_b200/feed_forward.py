@@ -16,6 +16,7 @@ class _LNFeedForwardFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, w1_bf16, w2_bf16, eps):
         shape = x.shape
+        resid, resid_sub = ops.ResidualRequest.take(shape, x.device)      # reversible residual fused into the last GEMM's epilogue
         d = shape[-1]
         x2 = x.reshape(-1, d)
         if ln_w is not None:
@@ -23,7 +24,7 @@ class _LNFeedForwardFn(torch.autograd.Function):
         else:
             xn, mean, rstd = ops.cast_bf16_colsum(x2), None, None
         hid = ops.gemm(xn, w1_bf16, bias=b1, relu=True, out_dtype=torch.bfloat16)
-        y = ops.gemm(hid, w2_bf16, bias=b2)
+        y = ops.gemm(hid, w2_bf16, bias=b2, resid=resid, resid_sub=resid_sub)
         ctx.has_ln = ln_w is not None
         ctx.save_for_backward(x2, ln_w, mean, rstd, xn, hid, w1_bf16, w2_bf16)
         return y.view(shape)

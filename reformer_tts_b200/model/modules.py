@@ -19,6 +19,7 @@ class FeedForward(nn.Module):
     """Linear(dim, hidden) - ReLU - Dropout - Linear(hidden, dim); parameters at ``net.0`` / ``net.3``
     (ref:...modules.py:195-207)."""
     rowwise = True
+    takes_residual = True      # its last GEMM can write x + f(.) / y - f(.) (reformer_tts_b200.residual.ResidualRequest)
 
     def __init__(self, dim=512, hidden=2048, dropout=0.):
         super().__init__()

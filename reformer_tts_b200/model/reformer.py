@@ -89,6 +89,8 @@ class MultiheadAttentionWrapper(nn.Module):
     ``scaled_dot_product_attention`` under bf16 autocast (same operand precision as the rest of the step); eval keeps the stock
     module call and returns the weights."""
 
+    takes_residual = True      # kernel path only: the output projection can write x + f(.) / y - f(.) (ResidualRequest)
+
     def __init__(self, dim: int, attention_matrices: Optional[List[torch.Tensor]] = None, **kwargs):
         super().__init__()
         self.layer = nn.MultiheadAttention(dim, **kwargs)

@@ -20,6 +20,8 @@ from torch import nn
 from torch.autograd.function import Function
 from torch.utils.checkpoint import get_device_states, set_device_states
 
+from ..residual import ResidualRequest
+
 
 class Deterministic(nn.Module):
     """Runs ``net``; can record the RNG state before a run and replay it later (ref:...reversible.py:11-41), so the
@@ -79,14 +81,44 @@ class Deterministic(nn.Module):
             return self.net(*args, **kwargs)
 
 
-def _grad_through(fn, inp, grad_out, **kwargs):
-    """Re-run ``fn`` on a detached copy of ``inp`` with grad enabled, push ``grad_out`` through it.
-    Returns (fn(inp) detached, d loss / d inp).  Parameter gradients accumulate into ``.grad`` as usual."""
+def _takes_residual(fn) -> bool:
+    """True when the sub-network is a (WithNorm / Chunk wrapped) layer of this library whose LAST kernel is a GEMM that can take
+    the residual in its epilogue (FeedForward, the cross-attention block).  Anything else is never offered one."""
+    net = getattr(fn, "net", fn)
+    for _ in range(4):
+        if getattr(net, "takes_residual", False):
+            return True
+        if type(net).__name__ not in ("WithNorm", "Chunk") or not hasattr(net, "fn"):
+            return False
+        net = net.fn
+    return False
+
+
+def _grad_through(fn, inp, grad_out, y, **kwargs):
+    """Re-run ``fn`` on a detached copy of ``inp`` with grad enabled, push ``grad_out`` through it, and reconstruct the
+    block input ``y - fn(inp)``.  Returns (y - fn(inp), d loss / d inp).  Parameter gradients accumulate into ``.grad`` as
+    usual.  The subtraction is offered to the sub-network (``ResidualRequest``): a layer ending in one of this library's GEMMs
+    writes ``y - f`` from its epilogue and no separate pass over the residual stream is needed."""
     with torch.enable_grad():
         leaf = inp.detach().requires_grad_(True)
-        out = fn(leaf, set_rng=True, **kwargs)
+        if _takes_residual(fn):
+            with ResidualRequest(y, "reconstruct") as req:
+                out = fn(leaf, set_rng=True, **kwargs)
+            fused = req.consumed
+        else:
+            out, fused = fn(leaf, set_rng=True, **kwargs), False
         torch.autograd.backward(out, grad_out)
-    return out.detach(), leaf.grad
+    out = out.detach()
+    return (out if fused else y - out), leaf.grad
+
+
+def _residual_forward(fn, x_res, inp, **kwargs):
+    """``x_res + fn(inp)`` with the addition offered to the sub-network's last GEMM epilogue."""
+    if not _takes_residual(fn):
+        return x_res + fn(inp, **kwargs)
+    with ResidualRequest(x_res, "add") as req:
+        out = fn(inp, **kwargs)
+    return out if req.consumed else x_res + out
 
 
 class ReversibleBlock(nn.Module):
@@ -99,18 +131,16 @@ class ReversibleBlock(nn.Module):
 
     def forward_halves(self, x1, x2, f_args={}, g_args={}):
         with torch.no_grad():
-            y1 = x1 + self.f(x2, record_rng=self.training, **f_args)
-            y2 = x2 + self.g(y1, record_rng=self.training, **g_args)
+            y1 = _residual_forward(self.f, x1, x2, record_rng=self.training, **f_args)
+            y2 = _residual_forward(self.g, x2, y1, record_rng=self.training, **g_args)
         return y1, y2
 
     def backward_halves(self, y1, y2, dy1, dy2, f_args={}, g_args={}):
-        gy1, dg = _grad_through(self.g, y1, dy2, **g_args)
+        x2, dg = _grad_through(self.g, y1, dy2, y2, **g_args)         # x2 = y2 - g(y1)
         with torch.no_grad():
-            x2 = y2 - gy1
             dx1 = dy1 + dg
-        fx2, df = _grad_through(self.f, x2, dx1, **f_args)
+        x1, df = _grad_through(self.f, x2, dx1, y1, **f_args)         # x1 = y1 - f(x2)
         with torch.no_grad():
-            x1 = y1 - fx2
             dx2 = dy2 + df
         return x1, x2, dx1, dx2
 
@@ -134,13 +164,12 @@ class ReversibleHalfResidual(nn.Module):
 
     def forward_halves(self, x1, x2, **f_args):
         with torch.no_grad():
-            y1 = x1 + self.f(x2, record_rng=self.training, **f_args)
+            y1 = _residual_forward(self.f, x1, x2, record_rng=self.training, **f_args)
         return y1, x2
 
     def backward_halves(self, y1, x2, dy1, dx2, **f_args):
-        fx2, df = _grad_through(self.f, x2, dy1, **f_args)
+        x1, df = _grad_through(self.f, x2, dy1, y1, **f_args)         # x1 = y1 - f(x2)
         with torch.no_grad():
-            x1 = y1 - fx2
             dx2 = dx2 + df
         return x1, x2, dy1, dx2
 

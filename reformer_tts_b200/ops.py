@@ -15,7 +15,9 @@ from . import _lib
 
 KEYNORM_L2, KEYNORM_RMS = 0, 1
 MASK_QUERY_AND_KEY, MASK_KEY_ONLY = 0, 1
-EPI_BIAS, EPI_RELU, EPI_GATE, EPI_OUT_BF16, EPI_ATOMIC, EPI_COLSUM = 1, 2, 4, 8, 16, 32
+from .residual import ResidualRequest  # noqa: F401  (re-exported: layers call ops.ResidualRequest.take)
+
+EPI_BIAS, EPI_RELU, EPI_GATE, EPI_OUT_BF16, EPI_ATOMIC, EPI_COLSUM, EPI_RESID_ADD, EPI_RESID_SUB = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 @dataclass(frozen=True)
@@ -278,8 +280,9 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_major: bool = False, bias=None, relu=False,
          gate=None, out_dtype=torch.float32, out: Optional[torch.Tensor] = None, accumulate: bool = False,
-         colsum: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
-    """C = epilogue(A . B^T) with bf16 operands.  A: [M,K] (or stored [K,M] when a_mn_major); B: [N,K] (or [K,N])."""
+         colsum: Optional[torch.Tensor] = None, split_k: int = 1, resid: Optional[torch.Tensor] = None, resid_sub: bool = False) -> torch.Tensor:
+    """C = epilogue(A . B^T) with bf16 operands.  A: [M,K] (or stored [K,M] when a_mn_major); B: [N,K] (or [K,N]).
+    ``resid`` (fp32 [M,N]): C = resid + result, or resid - result with ``resid_sub`` (fp32 output only)."""
     _check(a, torch.bfloat16, "a")
     _check(b, torch.bfloat16, "b")
     assert a.dim() == 2 and b.dim() == 2
@@ -298,6 +301,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     if colsum is not None:
         _check(colsum, torch.float32, "colsum")
         flags |= EPI_COLSUM
+    if resid is not None:
+        _check(resid, torch.float32, "resid")
+        assert gate is None and not accumulate and out_dtype == torch.float32 and resid.dim() == 2 and resid.stride(1) == 1
+        flags |= EPI_RESID_SUB if resid_sub else EPI_RESID_ADD
+        gate = resid
     if accumulate:
         assert out is not None and out.dtype == torch.float32
         flags |= EPI_ATOMIC

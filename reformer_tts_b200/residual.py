@@ -1,0 +1,40 @@
+"""The reversible residual offered to a sub-network's last GEMM epilogue (no kernels here: importable without the CUDA library)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+class ResidualRequest:
+    """A reversible block's offer to the sub-network it is about to run: "your last GEMM may write ``resid + f`` (mode 'add', the
+    reversible forward) or ``resid - f`` (mode 'reconstruct', the recompute in the reversible backward) straight from its epilogue".
+    A layer whose last kernel is one of this library's GEMMs with an fp32 output takes the offer (``take()``) and returns the
+    combined tensor; the block checks ``consumed`` and otherwise adds / subtracts itself.  In 'reconstruct' mode the returned tensor
+    is x1 = y1 - f(x2) while its autograd node still maps an incoming gradient as d loss / d f (the block never differentiates
+    through the reconstruction)."""
+    current: Optional["ResidualRequest"] = None
+
+    def __init__(self, resid: torch.Tensor, mode: str):
+        assert mode in ("add", "reconstruct")
+        self.resid, self.mode, self.consumed = resid, mode, False
+
+    def __enter__(self):
+        self._prev, ResidualRequest.current = ResidualRequest.current, self
+        return self
+
+    def __exit__(self, *exc):
+        ResidualRequest.current = self._prev
+        return False
+
+    @staticmethod
+    def take(shape, device):
+        """-> (resid as fp32 [rows, cols] or None, subtract?)  Marks the pending request as consumed when it fits."""
+        req = ResidualRequest.current
+        if req is None or req.consumed:
+            return None, False
+        r = req.resid
+        if r.dtype != torch.float32 or r.device != device or tuple(r.shape) != tuple(shape) or not r.is_contiguous():
+            return None, False
+        req.consumed = True
+        return r.view(-1, shape[-1]), req.mode == "reconstruct"

@@ -263,6 +263,25 @@ def test_gemm_layouts_and_epilogues(ops, m, n, k):
         assert rel_l2(acc, ref + 2) <= 1e-5
 
 
+@pytest.mark.parametrize("sub", [False, True])
+def test_gemm_residual_epilogue(ops, sub):
+    """C = resid +/- (A . B^T + bias) written from the epilogue (the reversible residual of the FFN / cross-attention blocks:
+    y = x + f(.) in the forward, x = y - f(.) in the recompute), also with C aliasing resid."""
+    torch.manual_seed(11)
+    m, n, k = 512, 256, 384
+    a = torch.randn(m, k, device=DEV).bfloat16()
+    b = torch.randn(n, k, device=DEV).bfloat16()
+    bias = torch.randn(n, device=DEV)
+    resid = torch.randn(m, n, device=DEV) * 10
+    want = a.float() @ b.float().t() + bias
+    want = resid - want if sub else resid + want
+    got = ops.gemm(a, b, bias=bias, resid=resid, resid_sub=sub)
+    assert rel_l2(got, want) <= TOL_FP32
+    inplace = resid.clone()
+    got2 = ops.gemm(a, b, bias=bias, resid=inplace, resid_sub=sub, out=inplace)
+    assert got2.data_ptr() == inplace.data_ptr() and torch.equal(got2, got)
+
+
 def test_gemm_rejects_bad_shapes(ops):
     a = torch.randn(100, 64, device=DEV).bfloat16()
     b = torch.randn(128, 64, device=DEV).bfloat16()
