@@ -143,11 +143,23 @@ int rtts_layernorm_bwd(const float* dy, const float* x, const float* gamma, cons
 int rtts_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
                    int64_t ldc, const float* bias, const void* gate, int64_t ldgate, float* colsum, int M, int N,
                    int K, int epilogue, int split_k, void* stream);
+/* rtts_gemm_bf16 with inverted dropout on the result: C = [resid +/-] keep * keep_scale * (A . B^T + bias) - nn.Dropout after the
+ * output projection of the LSH layer (ref: reformer-pytorch post_attn_dropout) - keep_mask uint8 [M,N] (1 = keep, row stride
+ * ldkeep, multiple of 4), keep_scale = 1 / (1 - p).  fp32 output only; combines with RTTS_EPI_BIAS and RTTS_EPI_RESID_*.
+ * keep_mask == NULL is plain rtts_gemm_bf16. */
+int rtts_gemm_bf16_dropout(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
+                           int64_t ldc, const float* bias, const void* gate, int64_t ldgate, float* colsum,
+                           const uint8_t* keep_mask, int64_t ldkeep, float keep_scale, int M, int N, int K, int epilogue,
+                           int split_k, void* stream);
 
 /* ---- small fused element-wise helpers used by the host mirror -------------------------------- */
 
 /* fp32 -> bf16 cast with optional column-sum accumulation (bias gradients): colsum fp32 [cols] += sum_rows. */
 int rtts_cast_bf16_colsum(const float* x, void* y, float* colsum, int rows, int cols, void* stream);
+/* Same with inverted dropout applied first: y = bf16(keep * scale * x), colsum += column sums of the masked values
+ * (keep uint8 [rows, cols], 1 = keep; the backward of a layer whose output went through rtts_gemm_bf16_dropout). */
+int rtts_cast_bf16_colsum_dropout(const float* x, const uint8_t* keep_mask, float keep_scale, void* y, float* colsum, int rows,
+                                  int cols, void* stream);
 
 #ifdef __cplusplus
 }

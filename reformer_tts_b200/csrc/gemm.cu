@@ -6,7 +6,8 @@
 // CTAs fit per SM and one CTA's epilogue overlaps the other's main loop.
 //   warp 0    : TMA producer (one elected lane)
 //   warp 1    : tcgen05.mma issuer (one elected lane)
-//   warps 2-5 : epilogue, one TMEM lane quarter each: tcgen05.ld -> bias / ReLU / gate / cast -> global
+//   warps 2-9 : epilogue, two warps per TMEM lane quarter (each half of the tile's columns): tcgen05.ld -> bias / ReLU / gate / cast /
+//               dropout / residual -> global
 // Operands may be K-major (row-major [rows, K]) or MN-major (stored [K, rows]); the latter is what the
 // weight-gradient GEMM dW = dY^T X needs, and is loaded as two 64-wide boxes per 128-row tile.
 #include <cuda.h>
@@ -19,7 +20,11 @@
 namespace rtts {
 
 constexpr int kBM = 128, kBK = 64;
-constexpr int kGemmThreads = 192;
+// Epilogue warps: two per TMEM lane quarter, each taking half of the tile's columns.  The K = 512 projections (8 k-blocks per tile) are
+// bound by the epilogue, not by the main loop: 20480x512x512 went 33 -> 26 us, the training step 24.2 -> 23.3 ms.  (Four warps for the
+// 256-column tiles only was measured too: 24.2 ms.)
+__host__ __device__ constexpr int gemm_epi_warps(int bn) { return bn > 0 ? 8 : 4; }
+__host__ __device__ constexpr int gemm_threads(int bn) { return 64 + gemm_epi_warps(bn) * 32; }
 constexpr int kATileBytes = kBM * kBK * 2;                    // 16 KB
 
 template <int BN>
@@ -27,8 +32,8 @@ struct GemmCfg {
   static constexpr int kBTileBytes = BN * kBK * 2;            // 16 | 32 KB
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStages = BN == 128 ? 6 : 4;           // 192 KB of operand ring either way
-  static constexpr int kOffStaging = kStages * kStageBytes + 256;                 // after the barriers: 4 epilogue warps x (output tile + gate tile) x 32 rows x 128 B
-  static constexpr int kSmem = kOffStaging + 4 * 8192 + 1024 /*align*/;
+  static constexpr int kOffStaging = kStages * kStageBytes + 256;                 // after the barriers: 8 epilogue warps x one 32-row x 128-B tile (gate rows, then output rows)
+  static constexpr int kSmem = kOffStaging + 8 * 4096 + 1024 /*align*/;
   static constexpr uint32_t kTmemCols = 2 * BN;               // two accumulators: the epilogue of tile i overlaps the main loop of tile i+1
 };
 
@@ -39,6 +44,9 @@ struct GemmParams {
   const __nv_bfloat16* gate;
   int64_t ldgate;
   float* colsum;
+  const uint8_t* keep;   // dropout keep mask [M,N] (1 = keep), row stride ldkeep; nullptr = no dropout
+  int64_t ldkeep;
+  float keep_scale;      // 1 / (1 - p)
   int M, N, K;       // K = per-split extent
   int epilogue;
   int tiles_n, tiles_mn, work;   // work = tiles_mn * split_k
@@ -62,7 +70,7 @@ __device__ __forceinline__ float warp_column_sums(float* r, int lane) {
 // Persistent: one CTA per SM walks work items w = blockIdx.x, += gridDim.x; w -> (split, m tile, n tile), n fastest so that
 // CTAs running at the same time share A panels in L2.
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
+__global__ void __launch_bounds__(gemm_threads(BN), 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                     const __grid_constant__ CUtensorMap tmap_b,
                                                                     const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full + a, 1);
-      mbar_init(acc_empty + a, 128);
+      mbar_init(acc_empty + a, gemm_epi_warps(BN) * 32);
     }
     fence_mbar_init();
   }
@@ -157,26 +165,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
     // Staging tile of this warp (32 rows x 128 B, 16-byte chunks XOR-swizzled by the row): the thread-per-row register layout that
     // tcgen05.ld produces is transposed through it so that global accesses are whole 128-byte row segments (four rows per warp
     // instruction) instead of 32 rows x 16 B.
-    const uint32_t stage = s_base + Cfg::kOffStaging + quarter * 8192, gstage = stage + 4096;      // output rows | gate rows
+    // K = 512 GEMMs (8 k-blocks per tile) are bound by this epilogue, not by the main loop: two warps per lane quarter split the columns
+    const int chalf = (warp - 2) >> 2;
+    const uint32_t stage = s_base + Cfg::kOffStaging + (warp - 2) * 4096, gstage = stage;      // one tile: gate rows first, then output rows
     const int srow = lane >> 3, sch = lane & 7;      // coalesced phase: lane -> (row within a group of four, 16-byte chunk)
     int t = 0;
     for (int w = blockIdx.x; w < p.work; w += gridDim.x, ++t) {
       const int split = w / p.tiles_mn, tile = w - split * p.tiles_mn;
       const int m0 = (tile / p.tiles_n) * kBM, n0 = (tile % p.tiles_n) * BN;
       const int acc = t & 1;
+      const int row = m0 + quarter * 32 + lane;
+      // residual rows / keep-mask bytes of this tile: pulled into L2 while the main loop of the tile is still running, so that the
+      // epilogue's loads (issued per 32-column chunk) do not each pay an HBM round trip
+      if (epi & (RTTS_EPI_RESID_ADD | RTTS_EPI_RESID_SUB)) {
+        const char* rp = reinterpret_cast<const char*>(reinterpret_cast<const float*>(p.gate) + static_cast<int64_t>(row) * p.ldgate + n0);
+#pragma unroll
+        for (int i = 0; i < BN * 4 / 128; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + i * 128));
+      }
+      if (p.keep != nullptr) {
+        const char* kp = reinterpret_cast<const char*>(p.keep + static_cast<int64_t>(row) * p.ldkeep + n0);
+#pragma unroll
+        for (int i = 0; i < (BN + 127) / 128; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + i * 128));
+      }
       mbar_wait(acc_full + acc, (t >> 1) & 1);
       tc_fence_after_sync();
-      const int row = m0 + quarter * 32 + lane;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        // residual rows of this chunk (coalesced, the layout of the store phase): requested before anything else so that their
-        // latency hides under the TMEM load and the staging pass
-        float4 rv[8];
-        if (epi & (RTTS_EPI_RESID_ADD | RTTS_EPI_RESID_SUB)) {
-          const float* rbase = reinterpret_cast<const float*>(p.gate) + static_cast<int64_t>(m0 + quarter * 32) * p.ldgate + n0 + c0;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) rv[it] = *reinterpret_cast<const float4*>(rbase + static_cast<int64_t>(it * 4 + srow) * p.ldgate + sch * 4);
-        }
+      constexpr int kColsPerWarp = BN / (gemm_epi_warps(BN) / 4);
+      for (int c0 = chalf * kColsPerWarp; c0 < (chalf + 1) * kColsPerWarp; c0 += 32) {
         uint32_t raw[32];
         tmem_ld32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c0, raw);
         tmem_ld_wait();
@@ -196,17 +211,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           for (int i = 0; i < 32; ++i) r[i] = fmaxf(r[i], 0.f);
         }
         if (epi & RTTS_EPI_GATE) {
-          // gate rows [32 x 64 B] -> staging (coalesced: 4 lanes per row, 8 rows per instruction) -> this thread's row
+          // gate rows [32 x 64 B] -> staging (coalesced: 4 lanes per row, 8 rows per instruction) -> this thread's row.  The tile is
+          // shared with the output rows: with a bf16 output the second chunk of a pair must not touch the half of each row that
+          // already holds the first chunk's results, so the gate goes where that chunk's own results will go.
+          const int ghalf = (epi & RTTS_EPI_OUT_BF16) ? ((c0 >> 5) & 1) * 4 : 0;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int gr = it * 8 + (lane >> 2), gc = lane & 3;
             const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.gate + static_cast<int64_t>(m0 + quarter * 32 + gr) * p.ldgate + col) + gc);
-            sts128(gstage + gr * 128 + ((gc ^ (gr & 7)) << 4), u);
+            sts128(gstage + gr * 128 + (((ghalf + gc) ^ (gr & 7)) << 4), u);
           }
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 u = lds128(gstage + lane * 128 + ((q ^ (lane & 7)) << 4));
+            const uint4 u = lds128(gstage + lane * 128 + (((ghalf + q) ^ (lane & 7)) << 4));
             const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -247,19 +265,40 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_kernel(const __grid
           for (int q = 0; q < 8; ++q)
             sts128(stage + lane * 128 + ((q ^ (lane & 7)) << 4),
                    make_uint4(__float_as_uint(r[q * 4]), __float_as_uint(r[q * 4 + 1]), __float_as_uint(r[q * 4 + 2]), __float_as_uint(r[q * 4 + 3])));
+          // residual rows / keep-mask bytes of this chunk in the layout of the store phase (coalesced); they were pulled into L2 at the
+          // start of the tile, and r[] is dead here, so the eight loads in flight cost no extra registers
+          float4 rv[8];
+          uint32_t kw[8];
+          if (epi & (RTTS_EPI_RESID_ADD | RTTS_EPI_RESID_SUB)) {
+            const float* rbase = reinterpret_cast<const float*>(p.gate) + static_cast<int64_t>(m0 + quarter * 32) * p.ldgate + col;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) rv[it] = *reinterpret_cast<const float4*>(rbase + static_cast<int64_t>(it * 4 + srow) * p.ldgate + sch * 4);
+          }
+          if (p.keep != nullptr) {
+            const uint8_t* kbase = p.keep + static_cast<int64_t>(m0 + quarter * 32) * p.ldkeep + col;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) kw[it] = *reinterpret_cast<const uint32_t*>(kbase + static_cast<int64_t>(it * 4 + srow) * p.ldkeep + sch * 4);
+          }
           __syncwarp();
           float* base = static_cast<float*>(p.C) + static_cast<int64_t>(m0 + quarter * 32) * p.ldc + col;
-          if (epi & (RTTS_EPI_RESID_ADD | RTTS_EPI_RESID_SUB)) {
-            // residual stream fused into the store: C = resid + result (reversible forward) or resid - result (reconstruction of the
-            // block input in the reversible backward).  Same coalesced 16-byte accesses as the store; C may alias resid.
+          if ((epi & (RTTS_EPI_RESID_ADD | RTTS_EPI_RESID_SUB)) || p.keep != nullptr) {
+            // dropout and residual stream fused into the store: C = [resid +/-] keep * scale * result (reversible forward: +, reconstruction
+            // of the block input in the reversible backward: -).  Same coalesced 16-byte accesses as the store; C may alias resid.
+            const bool has_resid = (epi & (RTTS_EPI_RESID_ADD | RTTS_EPI_RESID_SUB)) != 0;
             const float sgn = (epi & RTTS_EPI_RESID_SUB) ? -1.f : 1.f;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int rr = it * 4 + srow;
               const uint4 u = lds128(stage + rr * 128 + ((sch ^ (rr & 7)) << 4));
-              float4 o;
-              o.x = fmaf(sgn, __uint_as_float(u.x), rv[it].x); o.y = fmaf(sgn, __uint_as_float(u.y), rv[it].y);
-              o.z = fmaf(sgn, __uint_as_float(u.z), rv[it].z); o.w = fmaf(sgn, __uint_as_float(u.w), rv[it].w);
+              float4 o = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+              if (p.keep != nullptr) {
+                o.x = (kw[it] & 0x000000ffu) ? o.x * p.keep_scale : 0.f; o.y = (kw[it] & 0x0000ff00u) ? o.y * p.keep_scale : 0.f;
+                o.z = (kw[it] & 0x00ff0000u) ? o.z * p.keep_scale : 0.f; o.w = (kw[it] & 0xff000000u) ? o.w * p.keep_scale : 0.f;
+              }
+              if (has_resid) {
+                o.x = fmaf(sgn, o.x, rv[it].x); o.y = fmaf(sgn, o.y, rv[it].y);
+                o.z = fmaf(sgn, o.z, rv[it].z); o.w = fmaf(sgn, o.w, rv[it].w);
+              }
               *reinterpret_cast<float4*>(base + static_cast<int64_t>(rr) * p.ldc + sch * 4) = o;
             }
           } else {
@@ -304,7 +343,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     configured = true;
   }
   const int grid = p.work < kNumSMs ? p.work : kNumSMs;
-  gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(ta, tb, p);
+  gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, gemm_threads(BN), Cfg::kSmem, stream>>>(ta, tb, p);
   return check_launch("rtts_gemm_bf16");
 }
 
@@ -333,6 +372,17 @@ using namespace rtts;
 extern "C" int rtts_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
                               int64_t ldc, const float* bias, const void* gate, int64_t ldgate, float* colsum, int M, int N,
                               int K, int epilogue, int split_k, void* stream) {
+  return rtts_gemm_bf16_dropout(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, bias, gate, ldgate, colsum, nullptr, 0, 1.f, M, N, K, epilogue,
+                                split_k, stream);
+}
+
+extern "C" int rtts_gemm_bf16_dropout(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major, void* C,
+                                      int64_t ldc, const float* bias, const void* gate, int64_t ldgate, float* colsum,
+                                      const uint8_t* keep_mask, int64_t ldkeep, float keep_scale, int M, int N, int K, int epilogue,
+                                      int split_k, void* stream) {
+  RTTS_REQUIRE(!keep_mask || (!(epilogue & (RTTS_EPI_OUT_BF16 | RTTS_EPI_ATOMIC | RTTS_EPI_COLSUM)) && ldkeep % 4 == 0 &&
+                              (reinterpret_cast<uintptr_t>(keep_mask) & 3) == 0),
+               "rtts_gemm_bf16_dropout: the keep mask needs an fp32 non-atomic output without column sums, 4-byte aligned rows");
   RTTS_REQUIRE(A && B && C, "rtts_gemm_bf16: null pointer");
   RTTS_REQUIRE(M > 0 && N > 0 && K > 0 && M % kBM == 0 && N % 128 == 0, "rtts_gemm_bf16: M=%d, N=%d must be multiples of 128", M, N);
   RTTS_REQUIRE(split_k >= 1 && K % (kBK * split_k) == 0, "rtts_gemm_bf16: K=%d must be a multiple of 64*split_k", K);
@@ -351,6 +401,7 @@ extern "C" int rtts_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
                "rtts_gemm_bf16: operands must be 16-byte aligned");
   GemmParams p;
   p.C = C; p.ldc = ldc; p.bias = bias; p.gate = static_cast<const __nv_bfloat16*>(gate); p.ldgate = ldgate; p.colsum = colsum;
+  p.keep = keep_mask; p.ldkeep = ldkeep; p.keep_scale = keep_scale;
   p.M = M; p.N = N; p.K = K / split_k; p.epilogue = epilogue;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // 128x256 tiles halve the shared-memory traffic per flop; use them when they still give every SM several tiles

@@ -120,8 +120,19 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const float*
 // `tpr` threads (float4 each) cover one row of the strip and 256 / tpr rows are in flight per pass, eight passes of loads are
 // issued before any is consumed.  Column sums: registers -> shared-memory reduction over the row lanes -> ONE atomic per column
 // per CTA, and the grid is only ~4 CTAs per SM, so an address sees a few hundred atomics instead of thousands.
+// KEEP: inverted dropout first (x * keep * scale; keep = uint8 mask of x's shape), the backward of a fused dropout epilogue.
+template <bool KEEP>
 __global__ void __launch_bounds__(256) cast_bf16_colsum_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                                               float* __restrict__ colsum, int rows, int cols, int rows_per_cta, int tpr) {
+                                                               float* __restrict__ colsum, int rows, int cols, int rows_per_cta, int tpr,
+                                                               const uint8_t* __restrict__ keep, float keep_scale) {
+  auto masked = [&](float4 v, int64_t off) {
+    if (KEEP) {
+      const uint32_t kw = __ldg(reinterpret_cast<const uint32_t*>(keep + off));
+      v.x = (kw & 0x000000ffu) ? v.x * keep_scale : 0.f; v.y = (kw & 0x0000ff00u) ? v.y * keep_scale : 0.f;
+      v.z = (kw & 0x00ff0000u) ? v.z * keep_scale : 0.f; v.w = (kw & 0xff000000u) ? v.w * keep_scale : 0.f;
+    }
+    return v;
+  };
   __shared__ float4 red[256];
   const int lane_row = threadIdx.x / tpr, lanes = 256 / tpr;
   const int c = (blockIdx.x * tpr + threadIdx.x % tpr) * 4;
@@ -135,6 +146,8 @@ __global__ void __launch_bounds__(256) cast_bf16_colsum_kernel(const float* __re
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(r + i * lanes) * cols + c));
 #pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = masked(v[i], static_cast<int64_t>(r + i * lanes) * cols + c);
+#pragma unroll
       for (int i = 0; i < 8; ++i) {
         uint2 o;
         o.x = pack_bf16(v[i].x, v[i].y);
@@ -144,7 +157,7 @@ __global__ void __launch_bounds__(256) cast_bf16_colsum_kernel(const float* __re
       }
     }
     for (; r < r1; r += lanes) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(r) * cols + c));
+      const float4 v = masked(__ldg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(r) * cols + c)), static_cast<int64_t>(r) * cols + c);
       uint2 o;
       o.x = pack_bf16(v.x, v.y);
       o.y = pack_bf16(v.z, v.w);
@@ -252,7 +265,13 @@ extern "C" int rtts_layernorm_bwd(const float* dy, const float* x, const float* 
 }
 
 extern "C" int rtts_cast_bf16_colsum(const float* x, void* y, float* colsum, int rows, int cols, void* stream) {
+  return rtts_cast_bf16_colsum_dropout(x, nullptr, 1.f, y, colsum, rows, cols, stream);
+}
+
+extern "C" int rtts_cast_bf16_colsum_dropout(const float* x, const uint8_t* keep_mask, float keep_scale, void* y, float* colsum, int rows,
+                                             int cols, void* stream) {
   RTTS_REQUIRE(x && y, "rtts_cast_bf16_colsum: null pointer");
+  RTTS_REQUIRE(!keep_mask || (reinterpret_cast<uintptr_t>(keep_mask) & 3) == 0, "rtts_cast_bf16_colsum_dropout: keep mask must be 4-byte aligned");
   RTTS_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "rtts_cast_bf16_colsum: cols=%d must be a multiple of 4", cols);
   int tpr = 256;                                  // threads per row of a strip: a power of two covering min(cols, 1024) columns
   while (tpr > 1 && (tpr / 2) * 4 >= cols) tpr /= 2;
@@ -261,8 +280,12 @@ extern "C" int rtts_cast_bf16_colsum(const float* x, void* y, float* colsum, int
   if (row_ctas > rows) row_ctas = rows;
   const int rows_per_cta = (rows + row_ctas - 1) / row_ctas;
   dim3 grid(strips, (rows + rows_per_cta - 1) / rows_per_cta);
-  cast_bf16_colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y), colsum, rows, cols,
-                                                                              rows_per_cta, tpr);
+  if (keep_mask != nullptr)
+    cast_bf16_colsum_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y), colsum, rows, cols,
+                                                                                      rows_per_cta, tpr, keep_mask, keep_scale);
+  else
+    cast_bf16_colsum_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y), colsum, rows, cols,
+                                                                                       rows_per_cta, tpr, nullptr, 1.f);
   return check_launch("rtts_cast_bf16_colsum");
 }
 

@@ -63,8 +63,12 @@ class _LSHAttentionFn(torch.autograd.Function):
         sticker, undo = ops.lsh_sort(buckets, t, r, nb + 1 if pad_bucket else nb)
         o_rounds, lse_rounds = ops.lsh_attn_fwd(qk, v, sticker, mask_u8, spec, h, r, bucket, sumsq=sumsq)
         out, lse = ops.lsh_merge_fwd(o_rounds, lse_rounds)
+        keep, keep_scale = cfg.get("keep_mask"), cfg.get("keep_scale", 1.0)
         if wout_bf16 is not None:
-            y = ops.gemm(out.view(b * t, d), wout_bf16, bias=b_out).view(b, t, d)
+            # output projection with post_attn_dropout (inverted-dropout keep mask) and the reversible residual in its epilogue
+            resid, resid_sub = ops.ResidualRequest.take(x.shape, x.device)
+            y = ops.gemm(out.view(b * t, d), wout_bf16, bias=b_out, resid=resid, resid_sub=resid_sub,
+                         keep_mask=None if keep is None else keep.view(b * t, d), keep_scale=keep_scale).view(b, t, d)
         else:
             y = out.float()
         ctx.cfg = cfg
@@ -84,7 +88,8 @@ class _LSHAttentionFn(torch.autograd.Function):
         g_wout = g_bout = None
         if ctx.has_out:
             g_bout = torch.zeros(d, dtype=torch.float32, device=dev)
-            dyb = ops.cast_bf16_colsum(dy2, g_bout)
+            keep = cfg.get("keep_mask")       # the forward's dropout mask: d(dropout(z)) = keep * scale * dy
+            dyb = ops.cast_bf16_colsum(dy2, g_bout, keep_mask=None if keep is None else keep.view(b * t, d), keep_scale=cfg.get("keep_scale", 1.0))
             g_wout = torch.zeros((d, d), dtype=torch.float32, device=dev)
             ops.gemm(dyb, out.view(b * t, d), a_mn_major=True, b_mn_major=True, out=g_wout, accumulate=True, split_k=_split_k(b * t, (d // 128) ** 2))
             dout = ops.gemm(dyb, wout_bf16, b_mn_major=True, out_dtype=torch.bfloat16).view(b, t, d)
@@ -179,8 +184,13 @@ class LSHSelfAttention(_LSHBase):
             rot = self.rot_override.to(device=x.device, dtype=torch.float32)
         cfg = dict(heads=self.heads, n_hashes=self.n_hashes, bucket_size=self.bucket_size, n_buckets=n_buckets, pad_bucket=False,
                    spec=LSHSpec.reformer_pytorch(d // self.heads, self.causal), eps=1e-5)
-        y = self._run(x, norm, self.toqk.weight, self.tov.weight, self.to_out.weight, self.to_out.bias, rot, input_mask, cfg)
-        return self.post_attn_dropout(y)
+        # post_attn_dropout (nn.Dropout after to_out): the keep mask is drawn here, at the point of the call order where nn.Dropout
+        # would draw it (so Deterministic's RNG replay reproduces it in the recompute), and applied in the to_out GEMM's epilogue
+        p_drop = self.post_attn_dropout.p
+        if self.training and p_drop > 0.:
+            cfg["keep_mask"] = torch.empty((b, t, d), dtype=torch.uint8, device=x.device).bernoulli_(1. - p_drop)
+            cfg["keep_scale"] = 1. / (1. - p_drop)
+        return self._run(x, norm, self.toqk.weight, self.tov.weight, self.to_out.weight, self.to_out.bias, rot, input_mask, cfg)
 
 
 class HFLSHSelfAttention(_LSHBase):

@@ -72,6 +72,11 @@ class LSHSelfAttentionWrapper(nn.Module):
             self.layer = HFLSHSelfAttention(dim, heads=kwargs["heads"], bucket_size=kwargs["bucket_size"],
                                             n_hashes=kwargs["n_hashes"], causal=causal, dropout=kwargs["dropout"])
 
+    @property
+    def takes_residual(self) -> bool:
+        """The RP layer ends in the to_out GEMM (dropout and residual go into its epilogue); the HF layer has no output projection."""
+        return self.implementation == "reformer_pytorch"
+
     def forward_with_norm(self, x, norm, input_mask: Optional[torch.Tensor] = None):
         if self.implementation == "reformer_pytorch":
             return self.layer(x, input_mask=input_mask, norm=norm)

@@ -280,9 +280,11 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_major: bool = False, bias=None, relu=False,
          gate=None, out_dtype=torch.float32, out: Optional[torch.Tensor] = None, accumulate: bool = False,
-         colsum: Optional[torch.Tensor] = None, split_k: int = 1, resid: Optional[torch.Tensor] = None, resid_sub: bool = False) -> torch.Tensor:
+         colsum: Optional[torch.Tensor] = None, split_k: int = 1, resid: Optional[torch.Tensor] = None, resid_sub: bool = False,
+         keep_mask: Optional[torch.Tensor] = None, keep_scale: float = 1.0) -> torch.Tensor:
     """C = epilogue(A . B^T) with bf16 operands.  A: [M,K] (or stored [K,M] when a_mn_major); B: [N,K] (or [K,N]).
-    ``resid`` (fp32 [M,N]): C = resid + result, or resid - result with ``resid_sub`` (fp32 output only)."""
+    ``resid`` (fp32 [M,N]): C = resid + result, or resid - result with ``resid_sub`` (fp32 output only).
+    ``keep_mask`` (uint8 [M,N], 1 = keep): inverted dropout on the result, ``keep * keep_scale * result`` (fp32 output only)."""
     _check(a, torch.bfloat16, "a")
     _check(b, torch.bfloat16, "b")
     assert a.dim() == 2 and b.dim() == 2
@@ -314,17 +316,32 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     if out is None:
         out = torch.empty((m, n), dtype=out_dtype, device=a.device)
     assert out.shape == (m, n) and out.stride(1) == 1
+    if keep_mask is not None:
+        _check(keep_mask, torch.uint8, "keep_mask")
+        assert keep_mask.shape == (m, n) and keep_mask.stride(1) == 1 and out.dtype == torch.float32 and not accumulate and colsum is None
+        _launch(_tag("gemm_bf16", locals()), "rtts_gemm_bf16_dropout", _ptr(a), a.stride(0), int(a_mn_major), _ptr(b), b.stride(0), int(b_mn_major),
+                _ptr(out), out.stride(0), _ptr(bias), _ptr(gate), 0 if gate is None else gate.stride(0), _ptr(colsum), _ptr(keep_mask),
+                keep_mask.stride(0), float(keep_scale), m, n, k, flags, split_k, _stream())
+        return out
     _launch(_tag("gemm_bf16", locals()), "rtts_gemm_bf16", _ptr(a), a.stride(0), int(a_mn_major), _ptr(b), b.stride(0), int(b_mn_major), _ptr(out),
               out.stride(0), _ptr(bias), _ptr(gate), 0 if gate is None else gate.stride(0), _ptr(colsum), m, n, k, flags, split_k,
               _stream())
     return out
 
 
-def cast_bf16_colsum(x: torch.Tensor, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """fp32 [rows, cols] -> bf16 copy; colsum (fp32 [cols]) += column sums."""
+def cast_bf16_colsum(x: torch.Tensor, colsum: Optional[torch.Tensor] = None, keep_mask: Optional[torch.Tensor] = None,
+                     keep_scale: float = 1.0) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 copy; colsum (fp32 [cols]) += column sums.  With ``keep_mask`` (uint8, x's shape) the inverted
+    dropout ``keep * keep_scale * x`` is applied first (backward of a GEMM whose epilogue applied the same mask)."""
     _check(x, torch.float32, "x")
     x = x.contiguous()
     cols = x.shape[-1]
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if keep_mask is not None:
+        _check(keep_mask, torch.uint8, "keep_mask")
+        assert keep_mask.is_contiguous() and keep_mask.numel() == x.numel()
+        _launch(_tag("cast_bf16_colsum", locals()), "rtts_cast_bf16_colsum_dropout", _ptr(x), _ptr(keep_mask), float(keep_scale), _ptr(y), _ptr(colsum),
+                x.numel() // cols, cols, _stream())
+        return y
     _launch(_tag("cast_bf16_colsum", locals()), "rtts_cast_bf16_colsum", _ptr(x), _ptr(y), _ptr(colsum), x.numel() // cols, cols, _stream())
     return y

@@ -160,6 +160,39 @@ def test_feed_forward_with_norm_equals_chunked_reference():
         assert rel_l2(g_ours[k], g_ref[k]) <= 6e-2, k
 
 
+def test_rp_layer_post_attn_dropout_in_the_gemm_epilogue():
+    """post_attn_dropout (nn.Dropout after to_out in reformer-pytorch's LSHSelfAttention, 0.15 / 0.1 in the reference configs) is
+    applied inside the to_out GEMM's epilogue from a keep mask drawn where nn.Dropout would draw it.  Check against the same layer
+    without dropout times the regenerated mask: outputs and every gradient."""
+    from reformer_tts_b200.lsh_attention import LSHSelfAttention
+    torch.manual_seed(9)
+    dim, heads, rounds, B, T, p = 128, 2, 4, 2, 256, 0.25
+    layer = LSHSelfAttention(dim, heads=heads, bucket_size=64, n_hashes=rounds, causal=True, post_attn_dropout=p).to(DEV).train()
+    layer.rot_override = torch.randn(1, dim // heads, rounds, (T // 64) // 2, device=DEV)
+    x, dy = torch.randn(B, T, dim, device=DEV), torch.randn(B, T, dim, device=DEV)
+    torch.manual_seed(123)
+    xg = x.clone().requires_grad_(True)
+    y = layer(xg)
+    y.backward(dy)
+    g_fused = _grads(layer)
+    # the layer draws its rotations first (replaced by rot_override afterwards), then the keep mask
+    torch.manual_seed(123)
+    torch.randn((1, dim // heads, rounds, (T // 64) // 2), device=DEV)
+    keep = torch.empty((B, T, dim), dtype=torch.uint8, device=DEV).bernoulli_(1 - p)
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    layer.eval()
+    layer.zero_grad()
+    xr = x.clone().requires_grad_(True)
+    yr = layer(xr) * keep * (1.0 / (1 - p))
+    yr.backward(dy)
+    g_ref = _grads(layer)
+    assert (y == 0).float().mean().item() > p - 0.02
+    assert rel_l2(y, yr) <= 1e-6 and rel_l2(xg.grad, xr.grad) <= 1e-5
+    assert set(g_fused) == set(g_ref)
+    for k in g_ref:
+        assert rel_l2(g_fused[k], g_ref[k]) <= 1e-5, k
+
+
 @pytest.mark.parametrize("pad", [False, True])
 def test_cross_attention_block_equals_multihead_attention(pad):
     """WithNorm(LayerNorm, MultiheadAttentionWrapper) (ref:reformer_tts/model/reformer.py:161-186 as built at :122-125) on the
