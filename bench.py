@@ -73,10 +73,19 @@ class ClockSampler:
     def __init__(self, index: int):
         self.path = f"/tmp/rtts_clocks_{os.getpid()}.csv"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+        self.first = 0
+
+    def mark(self):
+        """Samples taken from here on belong to the timed region (the sampler is started before the warm-up: nvidia-smi needs
+        ~100 ms to deliver its first line, longer than the timed region of the small configs)."""
+        try:
+            self.first = sum(1 for _ in open(self.path))
+        except OSError:
+            self.first = 0
 
     def stop(self):
         if self.proc is None:
@@ -84,7 +93,9 @@ class ClockSampler:
         self.proc.terminate()
         self.proc.wait()
         sm, mx, reasons = [], 0, set()
-        for line in open(self.path):
+        lines = open(self.path).readlines()
+        in_region = lines[self.first:]
+        for line in (in_region if len(in_region) >= 2 else lines):      # (a region shorter than two samples: warm-up samples, same load)
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7 or not f[0].isdigit():
                 continue
@@ -95,7 +106,8 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.path)
         busy = [c for c in sm if c > 0.5 * mx] or sm
-        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "samples_in_timed_region": len(in_region)}
 
 
 def lsh_layer_shapes(kwargs, batch):
@@ -215,14 +227,16 @@ def run_ours(args, kwargs, world, rank, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank) if rank == 0 else None      # running from the warm-up on; the timed region is marked below
     for _ in range(args.warmup):
         step.step(resident)
     sync()
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------------------------------
     shapes = lsh_layer_shapes(kwargs, batch_size)
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
+    if clocks:
+        clocks.mark()
     start.record()
     for _ in range(args.steps):
         step.step(resident)

@@ -124,6 +124,10 @@ int rtts_layernorm_fwd(const float* x, const float* gamma, const float* beta, vo
  * are ACCUMULATED (+=) so they can point at parameter .grad buffers. */
 int rtts_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                        float* dx, float* dgamma, float* dbeta, int rows, int dim, void* stream);
+/* Same, accumulated onto another gradient: dx = dx_add + (LayerNorm backward); dx_add fp32 [rows, dim], may be NULL or alias dx
+ * (the `dx2 += df` of the reversible blocks without a separate pass over the stream). */
+int rtts_layernorm_bwd_acc(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                           const float* dx_add, float* dx, float* dgamma, float* dbeta, int rows, int dim, void* stream);
 
 /* ---- GEMM with fused epilogue (projections rp R1, FeedForward ref:reformer_tts/model/modules.py:195-207) */
 

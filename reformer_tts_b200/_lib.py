@@ -36,6 +36,7 @@ SIGNATURES = {
     "rtts_lsh_grad_reduce": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
     "rtts_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
     "rtts_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "rtts_layernorm_bwd_acc": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "rtts_gemm_bf16": [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P],
     "rtts_cast_bf16_colsum": [_P, _P, _P, _I, _I, _P],
     "rtts_cast_bf16_colsum_dropout": [_P, _P, _F, _P, _P, _I, _I, _P],

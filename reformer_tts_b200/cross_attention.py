@@ -83,7 +83,7 @@ class _CrossAttentionFn(torch.autograd.Function):
         if ctx.has_ln:
             g_lnw = torch.zeros(d, dtype=torch.float32, device=dev)
             g_lnb = torch.zeros(d, dtype=torch.float32, device=dev)
-            dx = ops.layernorm_bwd(dxn, x2, ln_w, mean, rstd, g_lnw, g_lnb)
+            dx = ops.layernorm_bwd(dxn, x2, ln_w, mean, rstd, g_lnw, g_lnb, accumulate_request=True)
         else:
             dx = dxn
         return dx.view(b, t, d), g_lnw, g_lnb, dmem, g_win, g_bin, g_wo, g_bo, None, None, None, None, None

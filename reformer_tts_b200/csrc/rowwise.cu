@@ -64,9 +64,9 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_fwd_kernel(const float*
 template <int VEC>
 __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                                    const float* __restrict__ rstd, float* __restrict__ dx,
+                                                                    const float* __restrict__ rstd, float* dx,
                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
-                                                                    int rows_per_cta) {
+                                                                    int rows_per_cta, const float* dx_add) {
   constexpr int dim = VEC * 128;
   __shared__ float sg[dim], sb[dim];
   for (int i = threadIdx.x; i < dim; i += kRowThreads) { sg[i] = 0.f; sb[i] = 0.f; }
@@ -81,7 +81,16 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const float*
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<int64_t>(row) * dim);
     const float4* dr = reinterpret_cast<const float4*>(dy + static_cast<int64_t>(row) * dim);
     const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
-    float4 xh[VEC], gd[VEC];
+    float4 xh[VEC], gd[VEC], av[VEC];
+    // dx_add (nullable, may alias dx): the gradient this one is accumulated onto (dx2 += df of the reversible blocks) - its row is
+    // requested with the other loads and added in the store, instead of a separate pass over both tensors
+    if (dx_add != nullptr) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) av[i] = *(reinterpret_cast<const float4*>(dx_add + static_cast<int64_t>(row) * dim) + i * 32 + lane);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -99,8 +108,8 @@ __global__ void __launch_bounds__(kRowThreads) layernorm_bwd_kernel(const float*
     float4* out = reinterpret_cast<float4*>(dx + static_cast<int64_t>(row) * dim);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      out[i * 32 + lane] = make_float4(rs * (gd[i].x - s1 - xh[i].x * s2), rs * (gd[i].y - s1 - xh[i].y * s2),
-                                       rs * (gd[i].z - s1 - xh[i].z * s2), rs * (gd[i].w - s1 - xh[i].w * s2));
+      out[i * 32 + lane] = make_float4(av[i].x + rs * (gd[i].x - s1 - xh[i].x * s2), av[i].y + rs * (gd[i].y - s1 - xh[i].y * s2),
+                                       av[i].z + rs * (gd[i].z - s1 - xh[i].z * s2), av[i].w + rs * (gd[i].w - s1 - xh[i].w * s2));
     }
   }
 #pragma unroll
@@ -247,6 +256,11 @@ extern "C" int rtts_layernorm_fwd(const float* x, const float* gamma, const floa
 
 extern "C" int rtts_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                                   float* dx, float* dgamma, float* dbeta, int rows, int dim, void* stream) {
+  return rtts_layernorm_bwd_acc(dy, x, gamma, mean, rstd, nullptr, dx, dgamma, dbeta, rows, dim, stream);
+}
+
+extern "C" int rtts_layernorm_bwd_acc(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                                      const float* dx_add, float* dx, float* dgamma, float* dbeta, int rows, int dim, void* stream) {
   RTTS_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "rtts_layernorm_bwd: null pointer");
   RTTS_REQUIRE(rows > 0 && dim % 128 == 0 && dim <= kMaxDim, "rtts_layernorm_bwd: dim=%d must be a multiple of 128 and <= %d", dim, kMaxDim);
   // ~2 CTAs per SM; each walks a contiguous slab of rows so parameter-gradient atomics stay at 2*dim per CTA
@@ -255,10 +269,10 @@ extern "C" int rtts_layernorm_bwd(const float* dy, const float* x, const float* 
   const int blocks = (rows + rows_per_cta - 1) / rows_per_cta;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (dim / 128) {
-    case 1: layernorm_bwd_kernel<1><<<blocks, kRowThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, rows_per_cta); break;
-    case 2: layernorm_bwd_kernel<2><<<blocks, kRowThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, rows_per_cta); break;
-    case 4: layernorm_bwd_kernel<4><<<blocks, kRowThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, rows_per_cta); break;
-    case 8: layernorm_bwd_kernel<8><<<blocks, kRowThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, rows_per_cta); break;
+    case 1: layernorm_bwd_kernel<1><<<blocks, kRowThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, rows_per_cta, dx_add); break;
+    case 2: layernorm_bwd_kernel<2><<<blocks, kRowThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, rows_per_cta, dx_add); break;
+    case 4: layernorm_bwd_kernel<4><<<blocks, kRowThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, rows_per_cta, dx_add); break;
+    case 8: layernorm_bwd_kernel<8><<<blocks, kRowThreads, 0, s>>>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, rows_per_cta, dx_add); break;
     default: return fail(kErrUnsupported, "rtts_layernorm_bwd: dim=%d unsupported (128, 256, 512, 1024)", dim);
   }
   return check_launch("rtts_layernorm_bwd");

@@ -50,7 +50,7 @@ class _LNFeedForwardFn(torch.autograd.Function):
         if ctx.has_ln:
             g_lnw = torch.zeros(d, dtype=torch.float32, device=dev)
             g_lnb = torch.zeros(d, dtype=torch.float32, device=dev)
-            dx = ops.layernorm_bwd(dxn, x2, ln_w, mean, rstd, g_lnw, g_lnb)
+            dx = ops.layernorm_bwd(dxn, x2, ln_w, mean, rstd, g_lnw, g_lnb, accumulate_request=True)
         else:
             dx = dxn
         return dx.view(dy.shape), g_lnw, g_lnb, g_w1, g_b1, g_w2, g_b2, None, None, None

@@ -107,7 +107,7 @@ class _LSHAttentionFn(torch.autograd.Function):
         if ctx.has_ln:
             g_lnw = torch.zeros(d, dtype=torch.float32, device=dev)
             g_lnb = torch.zeros(d, dtype=torch.float32, device=dev)
-            dx = ops.layernorm_bwd(dxn, x.reshape(b * t, d), ln_w, mean, rstd, g_lnw, g_lnb).view(b, t, d)
+            dx = ops.layernorm_bwd(dxn, x.reshape(b * t, d), ln_w, mean, rstd, g_lnw, g_lnb, accumulate_request=True).view(b, t, d)
         else:
             dx = dxn.view(b, t, d)
         return dx, g_lnw, g_lnb, g_wqkv[:d], g_wqkv[d:], g_wout, g_bout, None, None, None, None, None

@@ -20,7 +20,7 @@ from torch import nn
 from torch.autograd.function import Function
 from torch.utils.checkpoint import get_device_states, set_device_states
 
-from ..residual import ResidualRequest
+from ..residual import GradAccumRequest, ResidualRequest
 
 
 class Deterministic(nn.Module):
@@ -94,11 +94,12 @@ def _takes_residual(fn) -> bool:
     return False
 
 
-def _grad_through(fn, inp, grad_out, y, **kwargs):
-    """Re-run ``fn`` on a detached copy of ``inp`` with grad enabled, push ``grad_out`` through it, and reconstruct the
-    block input ``y - fn(inp)``.  Returns (y - fn(inp), d loss / d inp).  Parameter gradients accumulate into ``.grad`` as
-    usual.  The subtraction is offered to the sub-network (``ResidualRequest``): a layer ending in one of this library's GEMMs
-    writes ``y - f`` from its epilogue and no separate pass over the residual stream is needed."""
+def _grad_through(fn, inp, grad_out, y, acc, **kwargs):
+    """Re-run ``fn`` on a detached copy of ``inp`` with grad enabled, push ``grad_out`` through it, reconstruct the block
+    input ``y - fn(inp)`` and add the input gradient onto ``acc``.  Returns (y - fn(inp), acc + d loss / d inp).  Parameter
+    gradients accumulate into ``.grad`` as usual.  Both elementwise passes are offered to the sub-network: a layer ending in
+    one of this library's GEMMs writes ``y - f`` from its epilogue (``ResidualRequest``), and one whose backward ends in the
+    LayerNorm-backward kernel adds ``acc`` there (``GradAccumRequest``)."""
     with torch.enable_grad():
         leaf = inp.detach().requires_grad_(True)
         if _takes_residual(fn):
@@ -107,9 +108,15 @@ def _grad_through(fn, inp, grad_out, y, **kwargs):
             fused = req.consumed
         else:
             out, fused = fn(leaf, set_rng=True, **kwargs), False
-        torch.autograd.backward(out, grad_out)
+        if _takes_residual(fn):
+            with GradAccumRequest(acc) as greq:
+                torch.autograd.backward(out, grad_out)
+            acc_fused = greq.consumed
+        else:
+            torch.autograd.backward(out, grad_out)
+            acc_fused = False
     out = out.detach()
-    return (out if fused else y - out), leaf.grad
+    return (out if fused else y - out), (leaf.grad if acc_fused else acc + leaf.grad)
 
 
 def _residual_forward(fn, x_res, inp, **kwargs):
@@ -136,12 +143,10 @@ class ReversibleBlock(nn.Module):
         return y1, y2
 
     def backward_halves(self, y1, y2, dy1, dy2, f_args={}, g_args={}):
-        x2, dg = _grad_through(self.g, y1, dy2, y2, **g_args)         # x2 = y2 - g(y1)
         with torch.no_grad():
-            dx1 = dy1 + dg
-        x1, df = _grad_through(self.f, x2, dx1, y1, **f_args)         # x1 = y1 - f(x2)
-        with torch.no_grad():
-            dx2 = dy2 + df
+            dy1, dy2 = dy1.contiguous(), dy2.contiguous()      # (halves of one tensor at the first block: views with a row stride)
+        x2, dx1 = _grad_through(self.g, y1, dy2, y2, dy1, **g_args)         # x2 = y2 - g(y1), dx1 = dy1 + dg
+        x1, dx2 = _grad_through(self.f, x2, dx1, y1, dy2, **f_args)         # x1 = y1 - f(x2), dx2 = dy2 + df
         return x1, x2, dx1, dx2
 
     def forward(self, x, f_args={}, g_args={}):
@@ -168,9 +173,9 @@ class ReversibleHalfResidual(nn.Module):
         return y1, x2
 
     def backward_halves(self, y1, x2, dy1, dx2, **f_args):
-        x1, df = _grad_through(self.f, x2, dy1, y1, **f_args)         # x1 = y1 - f(x2)
         with torch.no_grad():
-            dx2 = dx2 + df
+            dx2 = dx2.contiguous()
+        x1, dx2 = _grad_through(self.f, x2, dy1, y1, dx2, **f_args)         # x1 = y1 - f(x2), dx2 += df
         return x1, x2, dy1, dx2
 
     def forward(self, x, **f_args):

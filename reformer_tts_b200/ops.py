@@ -15,7 +15,7 @@ from . import _lib
 
 KEYNORM_L2, KEYNORM_RMS = 0, 1
 MASK_QUERY_AND_KEY, MASK_KEY_ONLY = 0, 1
-from .residual import ResidualRequest  # noqa: F401  (re-exported: layers call ops.ResidualRequest.take)
+from .residual import GradAccumRequest, ResidualRequest  # noqa: F401  (re-exported: layers call ops.ResidualRequest.take)
 
 EPI_BIAS, EPI_RELU, EPI_GATE, EPI_OUT_BF16, EPI_ATOMIC, EPI_COLSUM, EPI_RESID_ADD, EPI_RESID_SUB = 1, 2, 4, 8, 16, 32, 64, 128
 
@@ -267,14 +267,16 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta):
-    """dy, x fp32 [..., dim] -> dx fp32; dgamma / dbeta (fp32 [dim]) are accumulated in place."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, accumulate_request: bool = False):
+    """dy, x fp32 [..., dim] -> dx fp32; dgamma / dbeta (fp32 [dim]) are accumulated in place.  With ``accumulate_request`` a pending
+    ``GradAccumRequest`` of the same shape is taken: dx = request.base + (LayerNorm backward), one pass instead of two."""
     _check(dy, torch.float32, "dy")
     dy, x = dy.contiguous(), x.contiguous()
     dim = x.shape[-1]
     dx = torch.empty_like(x)
-    _launch(_tag("layernorm_bwd", locals()), "rtts_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(gamma.contiguous()), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma),
-              _ptr(dbeta), x.numel() // dim, dim, _stream())
+    add = GradAccumRequest.take(x.numel(), x.device) if accumulate_request else None
+    _launch(_tag("layernorm_bwd", locals()), "rtts_layernorm_bwd_acc", _ptr(dy), _ptr(x), _ptr(gamma.contiguous()), _ptr(mean), _ptr(rstd), _ptr(add),
+              _ptr(dx), _ptr(dgamma), _ptr(dbeta), x.numel() // dim, dim, _stream())
     return dx
 
 

@@ -38,3 +38,32 @@ class ResidualRequest:
             return None, False
         req.consumed = True
         return r.view(-1, shape[-1]), req.mode == "reconstruct"
+
+
+class GradAccumRequest:
+    """The backward-pass counterpart: a reversible block is about to back-propagate through a sub-network and will add the
+    resulting input gradient onto ``base`` (``dx2 = dx2 + df``).  A layer whose backward ends in this library's LayerNorm-backward
+    kernel takes the request and returns ``base + df`` as its input gradient; the block checks ``consumed``."""
+    current: Optional["GradAccumRequest"] = None
+
+    def __init__(self, base: torch.Tensor):
+        self.base, self.consumed = base, False
+
+    def __enter__(self):
+        self._prev, GradAccumRequest.current = GradAccumRequest.current, self
+        return self
+
+    def __exit__(self, *exc):
+        GradAccumRequest.current = self._prev
+        return False
+
+    @staticmethod
+    def take(numel, device):
+        req = GradAccumRequest.current
+        if req is None or req.consumed:
+            return None
+        b = req.base
+        if b.dtype != torch.float32 or b.device != device or b.numel() != numel or not b.is_contiguous():
+            return None
+        req.consumed = True
+        return b
