@@ -280,6 +280,14 @@ def test_gemm_residual_epilogue(ops, sub):
     inplace = resid.clone()
     got2 = ops.gemm(a, b, bias=bias, resid=inplace, resid_sub=sub, out=inplace)
     assert got2.data_ptr() == inplace.data_ptr() and torch.equal(got2, got)
+    # with the inverted-dropout keep mask in the same epilogue (rtts_gemm_bf16_dropout), and on its own
+    keep = (torch.rand(m, n, device=DEV) < 0.85).to(torch.uint8)
+    scale = 1.0 / 0.85
+    core = (a.float() @ b.float().t() + bias) * keep * scale
+    got3 = ops.gemm(a, b, bias=bias, resid=resid, resid_sub=sub, keep_mask=keep, keep_scale=scale)
+    assert rel_l2(got3, resid - core if sub else resid + core) <= TOL_FP32
+    got4 = ops.gemm(a, b, bias=bias, keep_mask=keep, keep_scale=scale)
+    assert rel_l2(got4, core) <= TOL_FP32 and bool((got4[keep == 0] == 0).all())
 
 
 def test_gemm_rejects_bad_shapes(ops):
@@ -305,6 +313,16 @@ def test_layernorm_forward_backward(ops, dim):
     dg, db = torch.ones(dim, device=DEV), torch.ones(dim, device=DEV)       # accumulate semantics: += on top of 1
     dx = ops.layernorm_bwd(dy, x, g, mean, rstd, dg, db)
     assert rel_l2(dx, xr.grad) <= 1e-5 and rel_l2(dg - 1, gr.grad) <= 1e-4 and rel_l2(db - 1, br.grad) <= 1e-4
+    # accumulate-onto variant (the reversible blocks' dx2 += df): a pending GradAccumRequest is added in the same kernel
+    from reformer_tts_b200.residual import GradAccumRequest
+    base = torch.randn_like(x)
+    dg2, db2 = torch.zeros(dim, device=DEV), torch.zeros(dim, device=DEV)
+    with GradAccumRequest(base) as req:
+        dx_acc = ops.layernorm_bwd(dy, x, g, mean, rstd, dg2, db2, accumulate_request=True)
+    assert req.consumed and rel_l2(dx_acc, base + xr.grad) <= 1e-5
+    with GradAccumRequest(base[:, : dim // 2]) as req:      # shape / contiguity mismatch: not taken, plain result
+        dx_plain = ops.layernorm_bwd(dy, x, g, mean, rstd, dg2, db2, accumulate_request=True)
+    assert not req.consumed and torch.equal(dx_plain, dx)
 
 
 def test_cast_colsum_and_delta(ops):
@@ -312,6 +330,12 @@ def test_cast_colsum_and_delta(ops):
     cs = torch.zeros(512, device=DEV)
     y = ops.cast_bf16_colsum(x, cs)
     assert torch.equal(y, x.bfloat16()) and rel_l2(cs, x.sum(0)) <= 1e-5
+    # inverted dropout applied first (backward of rtts_gemm_bf16_dropout)
+    keep = (torch.rand(1000, 512, device=DEV) < 0.8).to(torch.uint8)
+    cs2 = torch.zeros(512, device=DEV)
+    y2 = ops.cast_bf16_colsum(x, cs2, keep_mask=keep, keep_scale=1.25)
+    want2 = x * keep * 1.25
+    assert torch.equal(y2, want2.bfloat16()) and rel_l2(cs2, want2.sum(0)) <= 1e-5
     a = torch.randn(3, 256, 512, device=DEV).bfloat16()
     o = torch.randn(3, 256, 512, device=DEV).bfloat16()
     want = (a.float() * o.float()).view(3, 256, 8, 64).sum(-1).permute(0, 2, 1)
