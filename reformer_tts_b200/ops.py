@@ -86,6 +86,10 @@ def _launch(tag: str, name: str, *args):
     timer = _TIMER
     if timer is not None and timer.wants(tag):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # In an eager pass the host is the slow side: the GPU would reach event `a` idle and then wait for the launch to be enqueued,
+        # and that host latency (5-10 us) would be counted as kernel time.  A short device-side spin keeps the stream busy until the
+        # event, the kernel and the closing event are all queued.
+        torch.cuda._sleep(40000)
         a.record()
         _lib.call(name, *args)
         b.record()
