@@ -1,7 +1,9 @@
 """BASELINE.json configs[4]: LSH-attention long-sequence sweep, 1k-16k positions, 8 heads, 4 hash rounds, bucket 64.
 Times the LSH core (hash -> sort -> chunked attention -> merge, and its backward) and the whole LSHSelfAttention layer
 (LayerNorm + projections + core + output projection, forward + backward) on ONE GPU; (batch, head) units are independent, so
-multi-GPU scaling of this workload is plain replication.  Prints one JSON line per length."""
+multi-GPU scaling of this workload is plain replication: under torchrun every rank runs its own ~16k positions on its own
+GPU, no data-path collective; times are the maximum over ranks (bracketed by barriers) and rates are the sum over ranks.
+Prints one JSON line per length (rank 0).  python tools/sweep_lsh.py | torchrun --nproc-per-node N tools/sweep_lsh.py"""
 import json
 import os
 import sys
@@ -13,7 +15,12 @@ from reformer_tts_b200 import ops  # noqa: E402
 from reformer_tts_b200.lsh_attention import LSHSelfAttention  # noqa: E402
 
 H, R, bucket, D = 8, 4, 64, 512
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
 dev = "cuda"
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
 peak = 1396.7
 if os.path.exists("MEASURED_PEAKS.json"):
     peak = json.load(open("MEASURED_PEAKS.json"))["bf16_tflops_sustained"]
@@ -23,18 +30,26 @@ def timed(fn, iters=10):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters):
         fn()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters
+    ms = a.elapsed_time(b) / iters
+    if world > 1:      # slowest rank
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return ms
 
 
 for T in (1024, 2048, 4096, 8192, 16384):
     B = max(1, 16384 // T)          # keep ~16k positions in flight so every length fills the GPU
-    torch.manual_seed(0)
+    torch.manual_seed(rank)
     qkv = torch.randn(B, T, 2 * D, device=dev).bfloat16()
     qk, v = qkv[..., :D], qkv[..., D:]
     dout = torch.randn(B, T, D, device=dev).bfloat16()
@@ -71,6 +86,12 @@ for T in (1024, 2048, 4096, 8192, 16384):
 
     ms_l = timed(layer_step, iters=5)
     flops = 8.0 * B * R * T * bucket * D
-    print(json.dumps({"T": T, "batch": B, "heads": H, "rounds": R, "bucket": bucket, "core_fwd_ms": round(ms_f, 4), "core_bwd_ms": round(ms_b, 4),
+    if rank == 0:
+      print(json.dumps({"n_gpus": world, "T": T, "batch_per_gpu": B, "heads": H, "rounds": R, "bucket": bucket, "core_fwd_ms": round(ms_f, 4), "core_bwd_ms": round(ms_b, 4),
                       "attn_kernel_ms": round(ms_a, 4), "attn_kernel_tflops": round(flops / ms_a / 1e9, 1), "attn_kernel_frac_of_peak": round(flops / ms_a / 1e9 / peak, 4),
-                      "layer_fwd_bwd_ms": round(ms_l, 4), "positions_per_s_layer_fwd_bwd": round(B * T / ms_l * 1e3)}), flush=True)
+                      "layer_fwd_bwd_ms": round(ms_l, 4), "positions_per_s_layer_fwd_bwd": round(world * B * T / ms_l * 1e3),
+                      "positions_per_s_core_fwd_bwd": round(world * B * T / (ms_f + ms_b) * 1e3)}), flush=True)
+if world > 1:
+    torch.cuda.synchronize()
+    dist.barrier()
+    os._exit(0)
