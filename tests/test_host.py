@@ -134,6 +134,75 @@ def test_reversible_context_tensor_gets_summed_gradient():
     assert (gx - x.grad).abs().max().item() <= 1e-5 and (gk - key.grad).abs().max().item() <= 1e-5
 
 
+def test_reversible_blocks_offer_residual_and_gradient_accumulation():
+    """Host protocol of the fused residual stream (reformer_tts_b200/residual.py): a sub-network that advertises
+    ``takes_residual`` is offered the residual of the forward (``x + f``), of the reconstruction (``y - f``) and the gradient it is
+    accumulated onto (``dx += df``); one that takes the offers must give the same outputs and gradients as one that ignores them,
+    and a sub-network without the flag is never offered anything.  CPU stand-in for the GEMM / LayerNorm-backward epilogues."""
+    from reformer_tts_b200.model.reversible import ReversibleBlock, ReversibleHalfResidual, ReversibleSequence, ReversibleSwap
+    from reformer_tts_b200.residual import GradAccumRequest, ResidualRequest
+    seen = {"add": 0, "reconstruct": 0, "acc": 0}
+
+    class _TanhLinearFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w, fuse):
+            y = torch.tanh(x @ w.t())
+            ctx.save_for_backward(x, w, y)
+            ctx.fuse = fuse
+            resid, sub = ResidualRequest.take(x.shape, x.device) if fuse else (None, False)
+            if resid is None:
+                return y
+            seen["reconstruct" if sub else "add"] += 1
+            return (resid.view(x.shape) - y) if sub else (resid.view(x.shape) + y)
+
+        @staticmethod
+        def backward(ctx, dy):       # the incoming gradient is d loss / d f in every mode (see ResidualRequest)
+            x, w, y = ctx.saved_tensors
+            dz = dy * (1 - y * y)
+            dx = dz @ w
+            base = GradAccumRequest.take(dx.numel(), dx.device) if ctx.fuse else None
+            if base is not None:
+                seen["acc"] += 1
+                dx = base.view(dx.shape) + dx
+            return dx, dz.reshape(-1, dz.shape[-1]).t() @ x.reshape(-1, x.shape[-1]), None
+
+    class Layer(nn.Module):
+        def __init__(self, fuse, flag):
+            super().__init__()
+            self.w = nn.Parameter(torch.randn(8, 8) * 0.3)
+            self.fuse = fuse
+            if flag:
+                self.takes_residual = True
+
+        def forward(self, x):
+            return _TanhLinearFn.apply(x, self.w, self.fuse)
+
+    def run(fuse, flag):
+        torch.manual_seed(0)
+        nets = [Layer(fuse, flag) for _ in range(4)]
+        blocks = nn.ModuleList([ReversibleBlock(nets[0], nets[1]), ReversibleHalfResidual(nets[2]), ReversibleSwap(),
+                                ReversibleHalfResidual(nets[3]), ReversibleSwap()])
+        seq = ReversibleSequence(blocks).train()
+        torch.manual_seed(1)
+        x = torch.randn(2, 5, 16, requires_grad=True)
+        y = seq(x, kwargs_list=[{}] * 5)
+        (y * torch.linspace(-1, 1, y.numel()).view_as(y)).sum().backward()
+        return y.detach(), x.grad, [n.w.grad for n in nets]
+
+    y0, gx0, gw0 = run(fuse=False, flag=False)
+    assert seen == {"add": 0, "reconstruct": 0, "acc": 0}
+    y1, gx1, gw1 = run(fuse=True, flag=True)
+    # 4 sub-networks: every forward, reconstruction and gradient accumulation went through the requests (the first block's
+    # residuals are halves of one tensor, i.e. not contiguous: those two offers are declined and added by the block)
+    assert seen["reconstruct"] == 4 and seen["acc"] == 4 and 2 <= seen["add"] <= 4
+    assert (y0 - y1).abs().max().item() <= 1e-6 and (gx0 - gx1).abs().max().item() <= 1e-6
+    for a, b in zip(gw0, gw1):
+        assert (a - b).abs().max().item() <= 1e-6
+    before = dict(seen)
+    y2, gx2, _ = run(fuse=True, flag=False)          # would take offers, but does not advertise it: nothing is offered
+    assert seen == before and (y0 - y2).abs().max().item() <= 1e-6 and (gx0 - gx2).abs().max().item() <= 1e-6
+
+
 def test_chunk_and_withnorm_fuse_only_rowwise_functions():
     from reformer_tts_b200.model import Chunk, WithNorm
     calls = []
