@@ -1,6 +1,6 @@
 """One ReformerTTS training step as a callable: forward, TTSLoss, reversible backward, gradient averaging, optimiser update
 (ref:reformer_tts/training/wrappers.py:53-105 + the Lightning loop around it).  The whole step can be captured ONCE in a CUDA
-graph and replayed: at the reference configs a step is ~1700 kernel launches of 10-300 us, so eager launch overhead is as large
+graph and replayed: at the reference configs a step is ~1250 kernel launches of 2-420 us, so eager launch overhead is as large
 as the GPU time itself.  Capture needs static shapes (the collate pads to a fixed length) and capture-safe randomness
 (``Deterministic.use_private_generators``)."""
 from __future__ import annotations
@@ -13,6 +13,42 @@ from torch import nn
 
 from .lsh_attention import _WeightCache
 from .model.reversible import Deterministic
+
+
+NO_DECAY = ("bias", "norm.weight")      # ref:reformer_tts/training/wrappers.py:240 ("norm.weight only applies to nn.LayerNorm")
+
+
+def param_groups(model: nn.Module, weight_decay: float):
+    """The reference's two AdamW parameter groups (ref:reformer_tts/training/wrappers.py:240-250): every parameter whose NAME contains
+    "bias" or "norm.weight" is exempt from weight decay.  The rule keys on names, which is why the product modules keep the
+    reference's parameter names."""
+    decay = [p for n, p in model.named_parameters() if not any(nd in n for nd in NO_DECAY)]
+    no_decay = [p for n, p in model.named_parameters() if any(nd in n for nd in NO_DECAY)]
+    return [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}]
+
+
+def make_optimizer(model: nn.Module, learning_rate: float, weight_decay: float, fused: Optional[bool] = None) -> torch.optim.AdamW:
+    """AdamW over ``param_groups`` (ref:...wrappers.py:251-256).  ``fused`` defaults to True on CUDA parameters."""
+    if fused is None:
+        fused = next(model.parameters()).is_cuda
+    return torch.optim.AdamW(param_groups(model, weight_decay), lr=learning_rate, weight_decay=weight_decay, fused=fused)
+
+
+def warmup_lr(global_step: int, base_lr: float, warmup_steps: Optional[int]) -> float:
+    """Learning rate of optimiser step ``global_step`` (0-based) under the reference's linear warm-up
+    (ref:...wrappers.py:286-295): base_lr * min(1, (step + 1) / warmup_steps) while step < warmup_steps."""
+    if warmup_steps is None or global_step >= warmup_steps:
+        return base_lr
+    return min(1.0, float(global_step + 1) / warmup_steps) * base_lr
+
+
+def set_lr(optimizer: torch.optim.Optimizer, lr: float) -> None:
+    """Write ``lr`` into every parameter group; a tensor-valued ``lr`` (CUDA-graph captured optimisers) is updated in place."""
+    for group in optimizer.param_groups:
+        if isinstance(group["lr"], torch.Tensor):
+            group["lr"].fill_(lr)
+        else:
+            group["lr"] = lr
 
 
 def loss_of_batch(model, loss_fn, batch: Dict[str, torch.Tensor]) -> torch.Tensor:

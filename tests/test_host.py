@@ -203,6 +203,29 @@ def test_reversible_blocks_offer_residual_and_gradient_accumulation():
     assert seen == before and (y0 - y2).abs().max().item() <= 1e-6 and (gx0 - gx2).abs().max().item() <= 1e-6
 
 
+def test_optimizer_groups_and_warmup_follow_the_reference_rules():
+    """SURVEY.md 8(f) rank 2 (host logic only): AdamW parameter groups keyed on the substrings "bias" / "norm.weight"
+    (ref:reformer_tts/training/wrappers.py:240-250) and the linear learning-rate warm-up (ref:...wrappers.py:286-295)."""
+    from reformer_tts_b200.model import ReformerTTS, config as C
+    from reformer_tts_b200.training import make_optimizer, param_groups, set_lr, warmup_lr
+    model = ReformerTTS(**C.reference_model_kwargs("bucket-size-64-18-06"))
+    groups = param_groups(model, 1e-6)
+    names = dict(model.named_parameters())
+    want_no_decay = {n for n in names if "bias" in n or "norm.weight" in n}
+    got_no_decay = {n for n, p in names.items() if any(p is q for q in groups[1]["params"])}
+    assert got_no_decay == want_no_decay and groups[1]["weight_decay"] == 0.0 and groups[0]["weight_decay"] == 1e-6
+    assert len(groups[0]["params"]) + len(groups[1]["params"]) == len(names)
+    # every LayerNorm gain and every bias is exempt; projection / embedding weights are not
+    assert any(n.endswith("norm.weight") for n in got_no_decay) and all(not n.endswith("toqk.weight") for n in got_no_decay)
+    opt = make_optimizer(model, 3e-4, 1e-6, fused=False)
+    assert [g["weight_decay"] for g in opt.param_groups] == [1e-6, 0.0] and all(g["lr"] == 3e-4 for g in opt.param_groups)
+    # warm-up of config/bucket-size-64-18-06.yml: 320 steps to 3e-4
+    assert warmup_lr(0, 3e-4, 320) == pytest.approx(3e-4 / 320) and warmup_lr(159, 3e-4, 320) == pytest.approx(1.5e-4)
+    assert warmup_lr(319, 3e-4, 320) == pytest.approx(3e-4) and warmup_lr(320, 3e-4, 320) == 3e-4 and warmup_lr(5, 3e-4, None) == 3e-4
+    set_lr(opt, warmup_lr(0, 3e-4, 320))
+    assert all(g["lr"] == pytest.approx(3e-4 / 320) for g in opt.param_groups)
+
+
 def test_chunk_and_withnorm_fuse_only_rowwise_functions():
     from reformer_tts_b200.model import Chunk, WithNorm
     calls = []
