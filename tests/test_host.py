@@ -32,6 +32,23 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert rc != 0 and b"null pointer" in lib.rtts_last_error()
 
 
+def test_hash_tc_shape_rules_through_the_c_abi():
+    """Host-only entry points of the tensor-pipe hash (no CUDA call): which shapes it takes and how much workspace it wants."""
+    from reformer_tts_b200 import _lib
+    lib = _lib.load()
+    sup = lib.rtts_lsh_hash_tc_supported
+    # (T, dh, R, n_buckets): the four training configs and the sweep lengths
+    assert sup(1024, 64, 8, 16) and sup(256, 64, 8, 4) and sup(1024, 64, 8, 8) and sup(256, 64, 8, 8)
+    assert sup(16384, 64, 4, 256)          # 512 projections: two launches of two rounds (256 columns each)
+    assert not sup(384, 64, 8, 6)          # 24 projections: not a multiple of 16 -> fp32 FMA kernel
+    assert not sup(1000, 64, 8, 16) and not sup(1024, 32, 8, 16) and not sup(1024, 64, 8, 1024)
+    ws = lib.rtts_lsh_hash_tc_workspace_bytes
+    assert ws(1, 8, 16) == 3 * 64 * 64 * 2 and ws(8, 8, 16) == 8 * 3 * 64 * 64 * 2
+    assert ws(1, 4, 256) == 3 * 256 * 64 * 2      # one group of two rounds at a time
+    rc = lib.rtts_lsh_hash_tc(None, 0, None, 1, None, 0, None, None, None, 1, 128, 1, 64, 8, 4, None)
+    assert rc != 0 and b"null pointer" in lib.rtts_last_error()
+
+
 def test_product_modules_refuse_cpu_tensors():
     from reformer_tts_b200.lsh_attention import LSHSelfAttention
     with pytest.raises(RuntimeError, match="no CPU path"):
