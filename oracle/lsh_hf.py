@@ -40,12 +40,25 @@ class LSHSelfAttentionHF(nn.Module):
         self.num_buckets = None                               # hf:531-533: set on first call, then cached
         self.last = None
         self.inject_buckets = None
+        self.round_operands = False  # oracle/rounded.py: bf16 roundings at the CUDA path's operand boundaries
 
     def forward(self, x: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         b, t, _ = x.shape
         h, dh = self.heads, self.dim // self.heads
         if t <= self.chunk_len:
             raise NotImplementedError("hf:537-539 standard-attention fallback is outside the hot path")
+        if self.round_operands:
+            from . import rounded
+            if self.num_buckets is None:
+                self.num_buckets = auto_num_buckets(t, self.chunk_len)
+            nb = self.num_buckets
+            rot = torch.randn((h, dh, self.n_hashes, nb // 2), dtype=x.dtype, device=x.device)              # hf:717-719, same draw
+            pad_bucket = attention_mask is not None and not bool(attention_mask.all())
+            y, self.last = rounded.lsh_layer(x, self.query_key.weight, self.value.weight, None, None, self.inject_buckets, attention_mask,
+                                             h, self.chunk_len, self.n_hashes, LSHSpec.huggingface(dh, self.causal), rot=rot,
+                                             n_buckets=nb, pad_bucket=pad_bucket)
+            self.last["rot"] = rot
+            return y
         qk = self.query_key(x).view(b, t, h, dh).transpose(1, 2).reshape(b * h, t, dh)    # hf:511-524
         v = self.value(x).view(b, t, h, dh).transpose(1, 2).reshape(b * h, t, dh)
         if self.num_buckets is None:

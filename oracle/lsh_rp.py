@@ -41,11 +41,21 @@ class LSHSelfAttentionRP(nn.Module):
         self.post_attn_dropout = nn.Dropout(post_attn_dropout)
         self.last = None    # stage outputs of the latest forward (tests read them)
         self.inject_buckets = None   # tests may force the bucket ids (SURVEY.md 8(c) end-to-end check)
+        self.round_operands = False  # oracle/rounded.py: bf16 roundings at the CUDA path's operand boundaries
 
     def forward(self, x: torch.Tensor, input_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         b, t, _ = x.shape
         h, dh = self.heads, self.dim // self.heads
         assert t % (2 * self.bucket_size) == 0, "sequence must be a multiple of 2*bucket_size"
+        if self.round_operands:
+            from . import rounded
+            n_buckets = t // self.bucket_size
+            rot = torch.randn((1, dh, self.n_hashes, n_buckets // 2), dtype=x.dtype, device=x.device)      # R2, same draw
+            y, self.last = rounded.lsh_layer(x, self.toqk.weight, self.tov.weight, self.to_out.weight, self.to_out.bias, self.inject_buckets,
+                                             input_mask, h, self.bucket_size, self.n_hashes, LSHSpec.reformer_pytorch(dh, self.causal),
+                                             rot=rot, n_buckets=n_buckets)
+            self.last["rot"] = rot
+            return self.post_attn_dropout(y)
         qk = self.toqk(x).view(b, t, h, dh).transpose(1, 2).reshape(b * h, t, dh)      # R1 merge_heads
         v = self.tov(x).view(b, t, h, dh).transpose(1, 2).reshape(b * h, t, dh)
         mask = None if input_mask is None else input_mask.bool()[:, None, :].expand(b, h, t).reshape(b * h, t)

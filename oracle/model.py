@@ -25,8 +25,13 @@ class FeedForward(nn.Module):       # ref:reformer_tts/model/modules.py:195-207
     def __init__(self, dim=512, hidden=2048, dropout=0.):
         super().__init__()
         self.net = nn.Sequential(nn.Linear(dim, hidden), nn.ReLU(), nn.Dropout(dropout), nn.Linear(hidden, dim))
+        self.round_operands = False      # oracle/rounded.py
 
     def forward(self, x):
+        if self.round_operands:
+            from .rounded import FeedForwardFn
+            assert self.net[2].p == 0 or not self.training, "rounding mode: hidden dropout is 0 in every reference config"
+            return FeedForwardFn.apply(x, self.net[0].weight, self.net[0].bias, self.net[3].weight, self.net[3].bias)
         return self.net(x)
 
 
@@ -69,8 +74,14 @@ class CrossAttention(nn.Module):    # ref:reformer_tts/model/reformer.py:161-186
         super().__init__()
         self.layer = nn.MultiheadAttention(dim, **kwargs)
         self.attention_matrices_ = attention_matrices
+        self.round_operands = False      # oracle/rounded.py
 
     def forward(self, query, **kwargs):
+        if self.round_operands and self.training:
+            from .rounded import CrossAttentionFn
+            assert self.layer.dropout == 0, "rounding mode: attention dropout is 0 in every reference config"
+            return CrossAttentionFn.apply(query, kwargs["key"], self.layer.in_proj_weight, self.layer.in_proj_bias, self.layer.out_proj.weight,
+                                          self.layer.out_proj.bias, kwargs.get("key_padding_mask"), self.layer.num_heads)
         mem = kwargs["key"].transpose(0, 1)
         extra = {k: v for k, v in kwargs.items() if k not in ("key", "value")}
         out, w = self.layer(query.transpose(0, 1), mem, mem, **extra)

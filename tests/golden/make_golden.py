@@ -4,6 +4,9 @@
                       ref:reformer_tts/model/reformer.py:204-213, run through the reference's own
                       ``LSHSelfAttentionWrapper`` (imported from /root/reference with the 2.11-era module path aliased);
                       inputs, weights, rotations seed, bucket ids and hidden states.
+* hfgrad_*.npz      - the same class, forward AND backward (d/dx, d/dWqk, d/dWv), including the shapes of
+                      config/huggingface-lsh.yml (dim 512, 8 heads, 8 rounds; T=256 chunk 64 / T=1024 chunk 128); inputs are
+                      regenerated from the seed by the tests (``hf_inputs``), a checksum guards against generator drift.
 * reversible_ref.npz - gradients produced by the reference's own ref:reformer_tts/model/reversible.py
                       (ReversibleSequence of ReversibleBlock / ReversibleHalfResidual / ReversibleSwap) on small MLP
                       sub-networks, plus the plain-autograd gradients through its IrreversibleBlock.
@@ -20,6 +23,8 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, "/root/reference")
+sys.path.insert(0, os.path.dirname(HERE))
+from _util import hf_inputs  # noqa: E402  (tests/_util.py: the tests regenerate the same inputs from the seed)
 import transformers  # noqa: E402
 import transformers.models.reformer.modeling_reformer as _mr  # noqa: E402
 
@@ -46,6 +51,28 @@ def hf_case(name, dim, heads, bucket, n_hashes, causal, T, B, pad, seed):
                         mask=np.zeros(0) if mask is None else mask.numpy(), hidden=out.hidden_states.detach().numpy(),
                         buckets=out.buckets.numpy().astype(np.int16), meta=np.array([dim, heads, bucket, n_hashes, int(causal), seed + 1]))
     print(name, "hidden", tuple(out.hidden_states.shape), "buckets", tuple(out.buckets.shape))
+
+
+def hf_grad_case(name, dim, heads, bucket, n_hashes, causal, T, B, pad, seed, stride):
+    """Forward AND backward of the real transformers class at a reference-config shape (config/huggingface-lsh.yml: dim 512,
+    8 heads, 8 hash rounds; encoder chunk 64 at T=256, decoder chunk 128 at T=1024): hidden states, bucket ids, d/dx, d/dWqk,
+    d/dWv.  Row-strided copies keep the fixture small (weight gradients sum over every token, so they pin all rows anyway)."""
+    wrapper = ref_reformer.LSHSelfAttentionWrapper(dim, causal, implementation="huggingface_transformers", heads=heads,
+                                                   bucket_size=bucket, n_hashes=n_hashes, dropout=0.).train()
+    wqk, wv, x, dy, mask, checksum = hf_inputs(dim, T, B, pad, seed)
+    with torch.no_grad():
+        wrapper.layer.query_key.weight.copy_(wqk)
+        wrapper.layer.value.weight.copy_(wv)
+    x.requires_grad_(True)
+    torch.manual_seed(seed + 1)     # state right before the rotations are drawn
+    out = wrapper.layer(x, attention_mask=mask)
+    out.hidden_states.backward(dy)
+    np.savez_compressed(os.path.join(HERE, f"hfgrad_{name}.npz"),
+                        hidden=out.hidden_states.detach().numpy()[:, ::stride], dx=x.grad.numpy()[:, ::stride],
+                        dwqk=wrapper.layer.query_key.weight.grad.numpy()[::stride], dwv=wrapper.layer.value.weight.grad.numpy()[::stride],
+                        buckets=out.buckets.numpy().astype(np.int16), checksum=np.array([checksum]),
+                        meta=np.array([dim, heads, bucket, n_hashes, int(causal), T, B, int(pad), seed, stride]))
+    print(name, "hidden", tuple(out.hidden_states.shape), "dx", tuple(x.grad.shape))
 
 
 def mlp(d, seed):
@@ -107,5 +134,8 @@ if __name__ == "__main__":
     hf_case("enc_pad", 128, 2, 64, 4, False, 256, 2, True, 200)
     hf_case("dec_causal", 128, 2, 128, 2, True, 512, 2, False, 300)
     hf_case("dec_causal_pad", 128, 2, 128, 2, True, 512, 2, True, 400)
+    hf_grad_case("small_dec", 128, 2, 64, 4, True, 256, 2, True, 500, 1)
+    hf_grad_case("cfg3_enc", 512, 8, 64, 8, False, 256, 1, True, 600, 2)
+    hf_grad_case("cfg3_dec", 512, 8, 128, 8, True, 1024, 1, True, 700, 4)
     reversible_case()
     state_dict_keys()

@@ -1,9 +1,9 @@
 """Module-level (drop-in boundary) parity: the product layers / stacks / model against the CPU oracle with the same
 weights.  Because the product projects in bf16, whole-model bucket ids cannot equal a pure-fp32 run at every position
 (SURVEY.md 8(c)); the end-to-end checks therefore inject OUR bucket ids into the oracle and then compare activations and
-gradients.  Tolerances: a layer is a chain of 5-6 bf16-stored intermediates (LayerNorm output, qk|v, P, per-round o, merged
-out, and the same again for gradients), each worth 1.1e-3 relative L2, so layers are compared at 1e-2 (measured values are
-recorded in DESIGN.md); stage-wise tolerances are in tests/test_kernels_gpu.py."""
+gradients.  The oracle runs in its OPERAND-ROUNDING mode (oracle/rounded.py: the reference arithmetic in fp32 with a bf16
+rounding exactly where the CUDA path stores a bf16 operand), so every output and every gradient is asserted at the 1e-3
+of BASELINE.json north_star; the distance to the exact fp32 oracle (which measures bf16 storage rounding) is printed."""
 import copy
 import glob
 import os
@@ -13,11 +13,11 @@ import pytest
 import torch
 from torch import nn
 
-from _util import rel_l2
+from _util import TOL, rel_l2, report
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-TOL_LAYER = 1e-2
+TOL_LAYER = TOL
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -39,8 +39,11 @@ def test_rp_layer_forward_backward(causal, pad, bucket):
     from reformer_tts_b200.lsh_attention import LSHSelfAttention
     torch.manual_seed(0)
     dim, heads, R, B, T = 128, 2, 4, 2, 512
+    from oracle.rounded import set_round_operands
     ref = LSHSelfAttentionRP(dim, heads=heads, bucket_size=bucket, n_hashes=R, causal=causal)
     _round_weights_to_bf16(ref)
+    exact = copy.deepcopy(ref)
+    set_round_operands(ref)
     ours = LSHSelfAttention(dim, heads=heads, bucket_size=bucket, n_hashes=R, causal=causal).to(DEV)
     ours.load_state_dict(ref.state_dict())
     norm_ref = nn.LayerNorm(dim)
@@ -55,24 +58,30 @@ def test_rp_layer_forward_backward(causal, pad, bucket):
     xg = x.to(DEV).requires_grad_(True)
     y = ours(xg, input_mask=None if mask is None else mask.to(DEV), norm=norm)
     y.backward(dy.to(DEV))
-    ref.inject_buckets = ours.last_buckets.cpu()
+    ref.inject_buckets = exact.inject_buckets = ours.last_buckets.cpu()
     xr = x.clone().requires_grad_(True)
     yr = ref(norm_ref(xr), input_mask=mask)
     yr.backward(dy)
-    assert rel_l2(y, yr) <= TOL_LAYER
-    assert rel_l2(xg.grad, xr.grad) <= TOL_LAYER
-    g_ours, g_ref = _grads(ours), _grads(ref)
+    norm_x = copy.deepcopy(norm_ref)
+    norm_x.zero_grad()
+    xe = x.clone().requires_grad_(True)
+    ye = exact(norm_x(xe), input_mask=mask)                 # exact fp32 oracle: information only
+    ye.backward(dy)
+    assert report("rp layer y", y, yr, ye) <= TOL_LAYER
+    assert report("rp layer dx", xg.grad, xr.grad, xe.grad) <= TOL_LAYER
+    g_ours, g_ref, g_x = _grads(ours), _grads(ref), _grads(exact)
     for k in g_ref:
-        assert rel_l2(g_ours[k], g_ref[k]) <= TOL_LAYER, k
-    assert rel_l2(norm.weight.grad, norm_ref.weight.grad) <= TOL_LAYER and rel_l2(norm.bias.grad, norm_ref.bias.grad) <= TOL_LAYER
-    # our own hash on our own bf16 qk agrees with the oracle's fp32 hash of ITS qk almost everywhere (bf16 projections flip <2 %)
-    ref.inject_buckets = None
-    torch.manual_seed(0)
-    ref2_rot = ours.rot_override
+        assert report("rp layer d" + k, g_ours[k], g_ref[k], g_x[k]) <= TOL_LAYER, k
+    assert report("rp layer dnorm.weight", norm.weight.grad, norm_ref.weight.grad) <= TOL_LAYER
+    assert report("rp layer dnorm.bias", norm.bias.grad, norm_ref.bias.grad) <= TOL_LAYER
+    # bucket ids.  The rounded oracle hashes the same bf16 qk values we do (only fp32 accumulation-order ties can differ); the
+    # exact oracle hashes fp32 projections, and bf16 projections flip < 2 % of the ids relative to it.
     from oracle import lsh_core
-    b_ref = lsh_core.hash_buckets(ref.last["qk"].detach(), ref2_rot, R, T // bucket)
-    agree = (b_ref == ours.last_buckets.cpu().view(B * heads, -1).long()).float().mean().item()
-    assert agree >= 0.97, agree
+    mine = ours.last_buckets.cpu().view(B * heads, -1).long()
+    agree_r = (lsh_core.hash_buckets(ref.last["qk"].detach(), ours.rot_override, R, T // bucket) == mine).float().mean().item()
+    agree_x = (lsh_core.hash_buckets(exact.last["qk"].detach(), ours.rot_override, R, T // bucket) == mine).float().mean().item()
+    print(f"[parity] bucket ids equal to the rounded oracle's own hash: {agree_r:.5f}; to the exact fp32 oracle's: {agree_x:.4f}")
+    assert agree_r >= 0.999 and agree_x >= 0.97
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "hf_lsh_*.npz"))), ids=os.path.basename)
@@ -97,67 +106,104 @@ def test_hf_layer_against_real_transformers_golden(path):
     agree = (ours.last_buckets.cpu().long() == golden_b).float().mean().item()
     assert agree >= 0.97, f"bucket agreement with transformers {agree}"     # bf16 projections flip ~0.5 % of ids
     # activations: oracle (pinned to the golden vectors in test_oracle.py) with OUR buckets injected
+    from oracle.rounded import set_round_operands
     ref = LSHSelfAttentionHF(dim, heads, bucket, R, bool(causal))
     ref.query_key.weight.data, ref.value.weight.data = torch.from_numpy(z["wqk"]), torch.from_numpy(z["wv"])
     ref.inject_buckets = ours.last_buckets.cpu()
     with torch.no_grad():
-        yr = ref(x, attention_mask=mask)
-    assert rel_l2(y, yr) <= TOL_LAYER
+        y_exact = ref(x, attention_mask=mask)
+        yr = set_round_operands(ref)(x, attention_mask=mask)
+    assert report("hf layer y", y, yr, y_exact) <= TOL_LAYER
     # and against transformers' own fp32 output.  One flipped bucket id shifts every later slot of that round by one, so chunk
     # membership changes for tokens near chunk boundaries: outputs agree closely but not to rounding level.  Sanity bound only.
     assert rel_l2(y, torch.from_numpy(z["hidden"])) <= 0.35
 
 
-def test_feed_forward_equals_chunked_reference():
-    """FeedForward stage fed the oracle's input (bf16-representable rows): Chunk(100, FF) on the oracle side, one fused
-    call on ours.  Both sides then see identical pre-activation signs, so gradients agree to bf16-operand level."""
-    from oracle.model import Chunk, FeedForward as RefFF
-    from reformer_tts_b200.model import Chunk as OurChunk, FeedForward
-    torch.manual_seed(1)
-    dim, hidden, B, T = 128, 512, 2, 384
-    ref = Chunk(100, RefFF(dim, hidden), along_dim=-2)
-    _round_weights_to_bf16(ref)
-    ours = OurChunk(100, FeedForward(dim, hidden), along_dim=-2).to(DEV)
-    ours.load_state_dict(ref.state_dict())
-    x, dy = torch.randn(B, T, dim).bfloat16().float(), torch.randn(B, T, dim)
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "hfgrad_*.npz"))), ids=os.path.basename)
+def test_hf_layer_forward_backward_at_config_shapes(path):
+    """The HF-API layer, forward and backward, on the gradient fixtures of the REAL transformers class (``hf_grad_case`` in
+    tests/golden/make_golden.py; cfg3_* are the shapes of config/huggingface-lsh.yml: dim 512, 8 heads, 8 rounds, T=256 chunk 64 /
+    T=1024 chunk 128).  tests/test_oracle.py pins the oracle to those vectors (buckets bit-equal, gradients 1e-5); here the
+    rounded oracle gets OUR bucket ids and every output / gradient must agree at 1e-3."""
+    from _util import hf_inputs
+    from oracle.lsh_hf import LSHSelfAttentionHF
+    from oracle.rounded import set_round_operands
+    from reformer_tts_b200.lsh_attention import HFLSHSelfAttention
+    z = np.load(path)
+    dim, heads, bucket, R, causal, T, B, pad, seed, stride = [int(v) for v in z["meta"]]
+    wqk, wv, x, dy, mask, checksum = hf_inputs(dim, T, B, bool(pad), seed)
+    assert abs(checksum - float(z["checksum"][0])) <= 1e-6 * abs(checksum)
+    ours = HFLSHSelfAttention(dim, heads, bucket, R, bool(causal)).to(DEV)
+    with torch.no_grad():
+        ours.query_key.weight.copy_(wqk)
+        ours.value.weight.copy_(wv)
+    nb = 2 ** ((2 * (T // bucket)).bit_length() - 1)
+    torch.manual_seed(seed + 1)
+    ours.rot_override = torch.randn(heads, dim // heads, R, nb // 2)       # the draw transformers made (hf:717-719)
     xg = x.to(DEV).requires_grad_(True)
-    y = ours(xg)
+    y = ours(xg, attention_mask=None if mask is None else mask.to(DEV))
     y.backward(dy.to(DEV))
+    golden_b = torch.from_numpy(z["buckets"]).long().view(B, heads, -1)
+    agree = (ours.last_buckets.cpu().long() == golden_b).float().mean().item()
+    print(f"[parity] bucket ids equal to transformers': {agree:.4f}")
+    assert agree >= 0.97
+    ref = set_round_operands(LSHSelfAttentionHF(dim, heads, bucket, R, bool(causal)))
+    ref.query_key.weight.data, ref.value.weight.data = wqk.clone(), wv.clone()
+    ref.inject_buckets = ours.last_buckets.cpu()
     xr = x.clone().requires_grad_(True)
-    yr = ref(xr)
+    yr = ref(xr, attention_mask=mask)
     yr.backward(dy)
-    assert rel_l2(y, yr) <= 3e-3 and rel_l2(xg.grad, xr.grad) <= 5e-3
-    g_ours, g_ref = _grads(ours), _grads(ref)
-    assert set(g_ours) == set(g_ref)
-    for k in g_ref:
-        assert rel_l2(g_ours[k], g_ref[k]) <= 5e-3, k
+    assert report("hf y", y, yr) <= TOL
+    assert report("hf dx", xg.grad, xr.grad) <= TOL
+    assert report("hf dWqk", ours.query_key.weight.grad, ref.query_key.weight.grad) <= TOL
+    assert report("hf dWv", ours.value.weight.grad, ref.value.weight.grad) <= TOL
+    # sanity against transformers' own numbers (different bucket ids at a fraction of the positions: not a rounding-level check)
+    assert rel_l2(y[:, ::stride], torch.from_numpy(z["hidden"])) <= 0.35
 
 
-def test_feed_forward_with_norm_equals_chunked_reference():
-    """Chunk(100, WithNorm(LayerNorm, FeedForward)) as the reference builds it (ref:reformer_tts/model/reformer.py:69-75).
-    Here the oracle's LayerNorm output is fp32 and ours is bf16, so a fraction ~1e-3 of the ReLU pre-activations that sit at
-    rounding distance from zero change sign; each flips one element of dh completely, which bounds the gradient agreement at
-    sqrt(fraction) ~ 3e-2 for ANY bf16-operand implementation.  Forward is unaffected (the flipped activations are ~0)."""
+def _ffn_parity(with_norm):
     from oracle.model import Chunk, FeedForward as RefFF, WithNorm as RefWithNorm
+    from oracle.rounded import set_round_operands
     from reformer_tts_b200.model import Chunk as OurChunk, FeedForward, WithNorm
     torch.manual_seed(1)
     dim, hidden, B, T = 128, 512, 2, 384
-    ref = Chunk(100, RefWithNorm(nn.LayerNorm, dim, RefFF(dim, hidden)), along_dim=-2)
+    if with_norm:
+        ref = Chunk(100, RefWithNorm(nn.LayerNorm, dim, RefFF(dim, hidden)), along_dim=-2)
+        ours = OurChunk(100, WithNorm(nn.LayerNorm, dim, FeedForward(dim, hidden)), along_dim=-2).to(DEV)
+    else:
+        ref = Chunk(100, RefFF(dim, hidden), along_dim=-2)
+        ours = OurChunk(100, FeedForward(dim, hidden), along_dim=-2).to(DEV)
     _round_weights_to_bf16(ref)
-    ours = OurChunk(100, WithNorm(nn.LayerNorm, dim, FeedForward(dim, hidden)), along_dim=-2).to(DEV)
     ours.load_state_dict(ref.state_dict())
+    exact = copy.deepcopy(ref)
+    set_round_operands(ref)
     x, dy = torch.randn(B, T, dim), torch.randn(B, T, dim)
     xg = x.to(DEV).requires_grad_(True)
     y = ours(xg)
     y.backward(dy.to(DEV))
     xr = x.clone().requires_grad_(True)
-    yr = ref(xr)
+    yr = ref(xr)                       # real chunking (ref:reformer_tts/model/reformer.py:36-45) around the rounded FeedForward
     yr.backward(dy)
-    assert rel_l2(y, yr) <= 5e-3 and rel_l2(xg.grad, xr.grad) <= 6e-2
-    g_ours, g_ref = _grads(ours), _grads(ref)
+    xe = x.clone().requires_grad_(True)
+    ye = exact(xe)
+    ye.backward(dy)
+    assert report("ffn y", y, yr, ye) <= TOL and report("ffn dx", xg.grad, xr.grad, xe.grad) <= TOL
+    g_ours, g_ref, g_x = _grads(ours), _grads(ref), _grads(exact)
     assert set(g_ours) == set(g_ref)
     for k in g_ref:
-        assert rel_l2(g_ours[k], g_ref[k]) <= 6e-2, k
+        assert report("ffn d" + k, g_ours[k], g_ref[k], g_x[k]) <= TOL, k
+
+
+def test_feed_forward_equals_chunked_reference():
+    """FeedForward: Chunk(100, FF) with real chunking on the oracle side (operand-rounded), one fused call on ours."""
+    _ffn_parity(False)
+
+
+def test_feed_forward_with_norm_equals_chunked_reference():
+    """Chunk(100, WithNorm(LayerNorm, FeedForward)) as the reference builds it (ref:reformer_tts/model/reformer.py:69-75).  Against
+    the EXACT oracle the gradients of any bf16-operand implementation differ by ~3e-2 (the bf16 LayerNorm output flips ~1e-3 of the
+    ReLU masks - printed); the rounded oracle rounds the LayerNorm output like the kernel does, sees the same masks, and 1e-3 holds."""
+    _ffn_parity(True)
 
 
 def test_rp_layer_post_attn_dropout_in_the_gemm_epilogue():
@@ -196,9 +242,11 @@ def test_rp_layer_post_attn_dropout_in_the_gemm_epilogue():
 @pytest.mark.parametrize("pad", [False, True])
 def test_cross_attention_block_equals_multihead_attention(pad):
     """WithNorm(LayerNorm, MultiheadAttentionWrapper) (ref:reformer_tts/model/reformer.py:161-186 as built at :122-125) on the
-    kernel path (row-wise LayerNorm + tcgen05 projections, hand-written backward) against LayerNorm + stock ``nn.MultiheadAttention``
-    in fp32 on the CPU: output, input / memory gradients and every parameter gradient.  bf16 hops: LN out, q|kv, P, o, and the same
-    number on the way back, so the layer tolerance (1e-2) applies."""
+    kernel path against LayerNorm + ``nn.MultiheadAttention`` arithmetic on the CPU in the oracle's operand-rounding mode
+    (oracle/rounded.py ``CrossAttentionFn``; tests/test_oracle.py checks that function against stock nn.MultiheadAttention):
+    output, input / memory gradients and every parameter gradient at 1e-3; the stock fp32 module's numbers are printed."""
+    from oracle.model import CrossAttention, WithNorm as RefWithNorm
+    from oracle.rounded import set_round_operands
     from reformer_tts_b200.model.reformer import MultiheadAttentionWrapper, WithNorm
     torch.manual_seed(3)
     dim, heads, B, T, S = 128, 2, 2, 256, 128
@@ -209,9 +257,9 @@ def test_cross_attention_block_equals_multihead_attention(pad):
         ours.norm.bias.normal_(0, 0.1)
         ours.fn.layer.in_proj_bias.normal_(0, 0.1)
         ours.fn.layer.out_proj.bias.normal_(0, 0.1)
-    ref_norm, ref_mha = nn.LayerNorm(dim), nn.MultiheadAttention(dim, num_heads=heads)
-    ref_norm.load_state_dict(ours.norm.state_dict())
-    ref_mha.load_state_dict(ours.fn.layer.state_dict())
+    exact = RefWithNorm(nn.LayerNorm, dim, CrossAttention(dim, None, num_heads=heads)).train()
+    exact.load_state_dict({k: v.cpu() for k, v in ours.state_dict().items()})
+    ref = set_round_operands(copy.deepcopy(exact))
     x, mem, dy = torch.randn(B, T, dim), torch.randn(B, S, dim), torch.randn(B, T, dim)
     kpm = None
     if pad:
@@ -222,18 +270,21 @@ def test_cross_attention_block_equals_multihead_attention(pad):
     assert ours.fn._kernel_path_ok(xg, mg)
     y = ours(xg, key=mg, value=mg, key_padding_mask=None if kpm is None else kpm.to(DEV))
     y.backward(dy.to(DEV))
-    xr, mr = x.clone().requires_grad_(True), mem.clone().requires_grad_(True)
-    yr, _ = ref_mha(ref_norm(xr).transpose(0, 1), mr.transpose(0, 1), mr.transpose(0, 1), key_padding_mask=kpm)
-    yr = yr.transpose(0, 1)
-    yr.backward(dy)
-    assert rel_l2(y, yr) <= TOL_LAYER
-    assert rel_l2(xg.grad, xr.grad) <= TOL_LAYER and rel_l2(mg.grad, mr.grad) <= TOL_LAYER
+
+    def run(mod):
+        xr, mr = x.clone().requires_grad_(True), mem.clone().requires_grad_(True)
+        yr = mod(xr, key=mr, value=mr, key_padding_mask=kpm)
+        yr.backward(dy)
+        return yr, xr.grad, mr.grad, _grads(mod)
+
+    yr, dxr, dmr, g_ref = run(ref)
+    ye, dxe, dme, g_x = run(exact)
+    assert report("cross y", y, yr, ye) <= TOL_LAYER
+    assert report("cross dx", xg.grad, dxr, dxe) <= TOL_LAYER and report("cross dmem", mg.grad, dmr, dme) <= TOL_LAYER
     g_ours = _grads(ours)
-    g_ref = {"norm." + k: v for k, v in _grads(ref_norm).items()}
-    g_ref.update({"fn.layer." + k: v for k, v in _grads(ref_mha).items()})
     assert set(g_ours) == set(g_ref)
     for k in g_ref:
-        assert rel_l2(g_ours[k], g_ref[k]) <= TOL_LAYER, k
+        assert report("cross d" + k, g_ours[k], g_ref[k], g_x[k]) <= TOL_LAYER, k
 
 
 def _small_kwargs(impl="reformer_pytorch", depth=2):
@@ -257,12 +308,15 @@ def test_full_model_training_step_matches_oracle(impl):
     """ReformerTTS forward + loss + backward on the product stack vs the oracle stack (reversible recompute on both sides),
     same weights, our buckets injected into the oracle layer by layer."""
     from oracle.model import ReformerTTSOracle
+    from oracle.rounded import set_round_operands
     from reformer_tts_b200.model import ReformerTTS
     from reformer_tts_b200.model.loss import TTSLoss
     torch.manual_seed(2)
+    torch.backends.cudnn.allow_tf32 = False        # pre / post nets (stock convolutions, outside the hot path) in true fp32 like the CPU side
     kw = _small_kwargs(impl)
     ref = ReformerTTSOracle(**kw).train()
     _round_weights_to_bf16(ref)
+    set_round_operands(ref)
     ours = ReformerTTS(**kw).to(DEV).train()
     ours.load_state_dict(ref.state_dict())
     B, Lp, Lm = 2, 100, 200
@@ -287,11 +341,14 @@ def test_full_model_training_step_matches_oracle(impl):
     for lo, lr in zip(_lsh_layers(ours), _lsh_layers(ref)):
         lr.inject_buckets = lo.last_buckets.cpu()
     loss_ref, out_ref = step(ref, "cpu")
-    assert abs(loss_ours - loss_ref) <= 1e-2 * abs(loss_ref), (loss_ours, loss_ref)
-    assert rel_l2(out_ours[0], out_ref[0]) <= 2e-2
+    assert abs(loss_ours - loss_ref) <= TOL * abs(loss_ref), (loss_ours, loss_ref)
+    assert report("model mel out", out_ours[0], out_ref[0]) <= TOL
     g_ours, g_ref = _grads(ours), _grads(ref)
     assert set(g_ours) == set(g_ref)
-    bad = {k: rel_l2(g_ours[k], g_ref[k]) for k in g_ref if g_ref[k].norm() > 1e-6 and rel_l2(g_ours[k], g_ref[k]) > 3e-2}
+    errs = {k: rel_l2(g_ours[k], g_ref[k]) for k in g_ref if g_ref[k].norm() > 1e-6}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    print("[parity] full model, worst parameter gradients vs rounded oracle:", [(k, f"{v:.2e}") for k, v in worst])
+    bad = {k: v for k, v in errs.items() if v > TOL}
     assert not bad, bad
 
 

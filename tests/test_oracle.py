@@ -186,3 +186,163 @@ def test_kat6_chunked_ffn_equals_unchunked():
     x = torch.randn(2, 1024, 64)
     assert len(x.chunk(100, dim=-2)) == 94 and len(torch.randn(1, 256, 4).chunk(100, dim=-2)) == 86
     assert (Chunk(100, ff, along_dim=-2)(x) - ff(x)).abs().max().item() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- operand-rounding mode
+def _rounded_case(impl, causal, pad, bucket, dtype, seed=0, N=3, T=256, R=2):
+    torch.manual_seed(seed)
+    qk = torch.randn(N, T, 64).bfloat16().to(dtype)
+    v = torch.randn(N, T, 64).bfloat16().to(dtype)
+    nb = T // bucket
+    buckets = (torch.randint(0, nb, (N, R, T)) + nb * torch.arange(R).view(1, R, 1)).view(N, R * T)
+    mask = None
+    if pad:
+        mask = torch.ones(N, T, dtype=torch.bool)
+        mask[0, -50:] = False
+        mask[1, -1:] = False
+    spec = (LSHSpec.reformer_pytorch if impl == "rp" else LSHSpec.huggingface)(64, causal)
+    return qk, v, buckets, mask, spec
+
+
+@pytest.mark.parametrize("bucket", [64, 128])
+@pytest.mark.parametrize("impl", ["rp", "hf"])
+@pytest.mark.parametrize("causal,pad", [(False, False), (True, False), (False, True), (True, True)])
+def test_rounded_oracle_without_rounding_equals_the_exact_oracle_and_its_autograd(bucket, impl, causal, pad):
+    """oracle/lsh_rounded.py restates forward AND the analytic backward; with the roundings switched off it must reproduce
+    lsh_core.lsh_attention and autograd through it (fp64), so the only thing the rounding mode adds is the roundings."""
+    from oracle import lsh_rounded
+    qk, v, buckets, mask, spec = _rounded_case(impl, causal, pad, bucket, torch.float64)
+    R, T = 2, qk.shape[1]
+    q = qk.clone().requires_grad_(True)
+    vv = v.clone().requires_grad_(True)
+    ref = lsh_core.lsh_attention(q, vv, buckets, bucket, R, spec, mask)
+    dout = torch.randn_like(qk)
+    (ref["out"] * dout).sum().backward()
+    got = lsh_rounded.forward(qk, v, ref["sticker"], ref["undo"], bucket, R, spec, mask, round_operands=False)
+    assert (got["out"] - ref["out"]).abs().max().item() <= 1e-10
+    assert (got["o_rounds"] - ref["o_rounds"]).abs().max().item() <= 1e-10
+    fin = torch.isfinite(ref["lse_rounds"])
+    assert (got["lse_rounds"] - ref["lse_rounds"])[fin].abs().max().item() <= 1e-8
+    dqk, dv = lsh_rounded.backward(qk, v, ref["sticker"], ref["undo"], bucket, R, spec, mask, dout, got["out"], got["lse"], round_operands=False)
+    assert (dv - vv.grad).abs().max().item() <= 1e-9 * max(1.0, vv.grad.abs().max().item())
+    assert (dqk - q.grad).abs().max().item() <= 1e-9 * max(1.0, q.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("bucket", [64, 128])
+def test_rounded_oracle_rounding_error_is_storage_rounding(bucket):
+    """The rounding mode moves results by about one bf16 storage rounding (1e-3 relative), not more: that is the part of the
+    kernel-vs-exact-oracle difference which is NOT a kernel property."""
+    from oracle import lsh_rounded
+    qk, v, buckets, mask, spec = _rounded_case("rp", True, True, bucket, torch.float32, seed=3)
+    R, T = 2, qk.shape[1]
+    sticker, undo = lsh_core.sort_buckets(buckets, T)
+    exact = lsh_rounded.forward(qk, v, sticker, undo, bucket, R, spec, mask, round_operands=False)
+    rnd = lsh_rounded.forward(qk, v, sticker, undo, bucket, R, spec, mask, round_operands=True)
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    assert 2e-4 <= rel(rnd["out"], exact["out"]) <= 3e-3
+    assert torch.equal(rnd["out"], rnd["out"].bfloat16().float()) and torch.equal(rnd["o_rounds"], rnd["o_rounds"].bfloat16().float())
+    dout = torch.randn_like(qk).bfloat16().float()
+    ge = lsh_rounded.backward(qk, v, sticker, undo, bucket, R, spec, mask, dout, exact["out"], exact["lse"], round_operands=False)
+    gr = lsh_rounded.backward(qk, v, sticker, undo, bucket, R, spec, mask, dout, rnd["out"], rnd["lse"], round_operands=True)
+    for a, b in zip(gr, ge):
+        assert 2e-4 <= rel(a, b) <= 5e-3
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("impl", ["rp", "hf"])
+def test_rounded_layer_functions_track_the_exact_oracle(impl):
+    """oracle/rounded.py (hand-written forward / backward with bf16 roundings) against the exact oracle modules with the same
+    weights and bucket ids: a formula error would show as O(1); what is left must be bf16 storage noise (a few 1e-3)."""
+    from oracle.model import CrossAttention, FeedForward
+    from oracle.rounded import set_round_operands
+    import copy
+    torch.manual_seed(4)
+    dim, heads, T, B = 128, 2, 256, 2
+    layer = (LSHSelfAttentionRP(dim, heads=heads, bucket_size=64, n_hashes=2, causal=True) if impl == "rp"
+             else LSHSelfAttentionHF(dim, heads, 64, 2, True))
+    x = torch.randn(B, T, dim)
+    mask = torch.ones(B, T, dtype=torch.bool)
+    mask[1, -20:] = False
+    dy = torch.randn(B, T, dim)
+    kw = {"input_mask": mask} if impl == "rp" else {"attention_mask": mask}
+
+    def run(mod, inp):
+        mod.zero_grad()
+        xi = inp.clone().requires_grad_(True)
+        y = mod(xi, **kw)
+        y.backward(dy)
+        return y.detach(), xi.grad, {k: p.grad.clone() for k, p in mod.named_parameters()}
+
+    torch.manual_seed(7)
+    y0, dx0, g0 = run(layer, x)
+    exact_buckets = layer.last["buckets"].clone()
+    layer.last = None
+    layer.inject_buckets = exact_buckets
+    rounded_layer = set_round_operands(copy.deepcopy(layer))
+    y1, dx1, g1 = run(rounded_layer, x)
+    assert 1e-4 <= _rel(y1, y0) <= 1e-2 and _rel(dx1, dx0) <= 1e-2
+    for k in g0:
+        assert _rel(g1[k], g0[k]) <= 1e-2, k
+    # without injected buckets the rounded layer hashes its own bf16 qk with the same rotation draw: nearly the same ids
+    rounded_layer.inject_buckets = None
+    torch.manual_seed(7)
+    rounded_layer(x, **kw)
+    assert (rounded_layer.last["buckets"] == exact_buckets).float().mean().item() >= 0.97
+
+    # FeedForward: bf16-representable input and weights, so both sides see the same ReLU pre-activation signs (an fp32 input
+    # rounded to bf16 flips ~1e-3 of them, which moves gradients by sqrt(1e-3) for ANY bf16-operand implementation)
+    ff = FeedForward(dim, 4 * dim)
+    with torch.no_grad():
+        for p_ in ff.parameters():
+            if p_.dim() == 2:
+                p_.copy_(p_.bfloat16().float())
+    kw = {}
+    xb = x.bfloat16().float()
+    y0, dx0, g0 = run(ff, xb)
+    y1, dx1, g1 = run(set_round_operands(copy.deepcopy(ff)), xb)
+    assert 1e-4 <= _rel(y1, y0) <= 1e-2 and _rel(dx1, dx0) <= 1e-2
+    for k in g0:
+        assert _rel(g1[k], g0[k]) <= 1e-2, k
+
+    ca = CrossAttention(dim, None, num_heads=heads).train()
+    mem = torch.randn(B, 64, dim)
+    kpm = torch.zeros(B, 64, dtype=torch.bool)
+    kpm[0, 50:] = True
+    kw = dict(key=mem, value=mem, key_padding_mask=kpm)
+    y0, dx0, g0 = run(ca, x)
+    ca_r = set_round_operands(copy.deepcopy(ca))
+    memr = mem.clone().requires_grad_(True)
+    kw = dict(key=memr, value=memr, key_padding_mask=kpm)
+    y1, dx1, g1 = run(ca_r, x)
+    mem0 = mem.clone().requires_grad_(True)
+    kw = dict(key=mem0, value=mem0, key_padding_mask=kpm)
+    run(ca, x)
+    assert 1e-4 <= _rel(y1, y0) <= 1e-2 and _rel(dx1, dx0) <= 1e-2 and _rel(memr.grad, mem0.grad) <= 1e-2
+    for k in g0:
+        assert _rel(g1[k], g0[k]) <= 1e-2, k
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "hfgrad_*.npz"))), ids=os.path.basename)
+def test_hf_restatement_gradients_match_real_transformers_golden(path):
+    """Forward AND backward of the restatement against what the real transformers class produced (tests/golden/make_golden.py
+    ``hf_grad_case``), including the shapes of config/huggingface-lsh.yml (dim 512, 8 heads, 8 rounds, T=256 chunk 64 and
+    T=1024 chunk 128): bucket ids bit-equal, hidden states, d/dx, d/dWqk, d/dWv to fp32 rounding."""
+    from _util import hf_inputs
+    z = np.load(path)
+    dim, heads, bucket, n_hashes, causal, T, B, pad, seed, stride = [int(v) for v in z["meta"]]
+    wqk, wv, x, dy, mask, checksum = hf_inputs(dim, T, B, bool(pad), seed)
+    assert abs(checksum - float(z["checksum"][0])) <= 1e-6 * abs(checksum), "torch's CPU generator no longer reproduces the fixture inputs"
+    layer = LSHSelfAttentionHF(dim, heads, bucket, n_hashes, bool(causal)).train()
+    layer.query_key.weight.data, layer.value.weight.data = wqk, wv
+    x.requires_grad_(True)
+    torch.manual_seed(seed + 1)
+    hidden = layer(x, attention_mask=mask)
+    hidden.backward(dy)
+    assert torch.equal(layer.last["buckets"].view(B, heads, n_hashes, -1), torch.from_numpy(z["buckets"]).long()), "bucket ids must be bit-equal"
+    assert _rel(hidden.detach()[:, ::stride], torch.from_numpy(z["hidden"])) <= 1e-5
+    assert _rel(x.grad[:, ::stride], torch.from_numpy(z["dx"])) <= 1e-5
+    assert _rel(layer.query_key.weight.grad[::stride], torch.from_numpy(z["dwqk"])) <= 1e-5
+    assert _rel(layer.value.weight.grad[::stride], torch.from_numpy(z["dwv"])) <= 1e-5
