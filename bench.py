@@ -26,7 +26,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NCU_DRAM_BYTES_FWD_DEC_CFG2 = 63_337_472 + 121_166_336      # profiles/r1_attn_v3_ncu_full.txt (read + write), B=20 T=1024 R=8 bucket 64
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram__bytes of `ncu --set full` captures, keyed by kernel + shape + source hash
 DEFAULT_CONFIG = "bucket-size-64-18-06"       # BASELINE.json configs[1]: the configuration the metric is quoted on
 PHONEMES, FRAMES, N_MELS = 200, 800, 80       # "~200 phonemes -> ~800x80 mel frames" (BASELINE.json configs[0])
 
@@ -119,6 +119,35 @@ def lsh_layer_shapes(kwargs, batch):
             "dec": (batch, tm, d["self_attn_kwargs"]["n_hashes"], d["self_attn_kwargs"]["bucket_size"], kwargs["embedding_dim"], d["depth"])}
 
 
+def workload_config(args, kwargs, world):
+    """The workload both arms are measured on (the reference arm times a bounded sample of it: ``cpu_baseline.sample``)."""
+    pad = kwargs["pad_base"]
+    return {"workload": f"ReformerTTS config/{args.config}.yml training step (fwd + loss + reversible bwd + AdamW)",
+            "per_gpu_batch": args.batch, "global_batch": args.batch * world, "phonemes": PHONEMES, "mel_frames": FRAMES,
+            "padded_lengths": [-(-PHONEMES // pad) * pad, -(-FRAMES // pad) * pad], "parallelism": f"dp{world}"}
+
+
+def ncu_traffic(kernel: str, shape: str, sources):
+    """DRAM bytes per launch from the committed ncu capture of this kernel at this shape - only if the kernel's source files
+    still hash to what was profiled (otherwise the number is stale: None)."""
+    from reformer_tts_b200.csrc.build import source_hash
+    try:
+        entry = json.load(open(NCU_TRAFFIC_FILE)).get(f"{kernel}|{shape}")
+    except (OSError, ValueError):
+        return None, None
+    if not entry or entry.get("source_hash") != source_hash(sources):
+        return None, None
+    return entry["dram_bytes"], entry.get("profile")
+
+
+CPU_SAMPLE_FRAMES, CPU_SAMPLE_PHONEMES = 800, 200      # ONE protocol for both CPU legs: one full-length utterance per step
+
+
+def cpu_sample_description(steps, warmup, cores):
+    return (f"1 utterance x {CPU_SAMPLE_FRAMES} mel frames ({CPU_SAMPLE_PHONEMES} phonemes) per step (the workload's batch is "
+            f"per_gpu_batch such utterances), {warmup} warm-up + {steps} timed steps, fp32 CPU oracle (oracle/model.py), torch {torch.__version__}, {cores} threads")
+
+
 # ------------------------------------------------------------------------------------------------------------------ arms
 def run_reference(args, kwargs, world, rank):
     """CPU arm: oracle restatement of the reference path, all host threads, bounded sample of the same workload."""
@@ -132,36 +161,27 @@ def run_reference(args, kwargs, world, rank):
     model = ReformerTTSOracle(**kwargs).train()
     loss_fn = TTSLoss(torch.tensor(5.))
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
-    # bounded sample: ONE utterance; shorten it (fewer mel frames, same phoneme/frame ratio) until the whole run fits ~4 minutes
-    frames, budget = FRAMES, 240.0
-    total_steps = args.steps + args.warmup
-    while True:
-        batch = synthetic_batch(1, frames=frames, phonemes=max(8, frames // 4))
-        t0 = time.perf_counter()
-        train_step(model, loss_fn, opt, batch)
-        t_probe = time.perf_counter() - t0
-        if t_probe * total_steps <= budget or frames <= 100:
-            break
-        frames //= 2
-    for _ in range(max(0, args.warmup - 1)):
+    # bounded sample of the workload: ONE full-length utterance per step (same protocol as the in-line cpu_baseline leg)
+    frames = CPU_SAMPLE_FRAMES
+    batch = synthetic_batch(1, frames=frames, phonemes=CPU_SAMPLE_PHONEMES)
+    for _ in range(args.warmup):
         train_step(model, loss_fn, opt, batch)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         train_step(model, loss_fn, opt, batch)
     dt = time.perf_counter() - t0
     value = frames * args.steps / dt
-    sample = f"1 utterance x {frames} mel frames ({max(8, frames // 4)} phonemes) per step, {args.steps} steps, fp32, torch {torch.__version__} CPU"
+    sample = cpu_sample_description(args.steps, args.warmup, cores)
     line = {"impl": "reference", "metric": "train_mel_frames_per_sec", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"ReformerTTS config/{args.config}.yml training step (fwd + loss + reversible bwd + AdamW)", "bounded_sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, kwargs, world),
             "cpu_baseline": {"value": value, "unit": "mel-frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg(kwargs, seconds_budget=40.0):
-    """Rank-0, N=1 only: the oracle port timed beside the GPU number on a bounded sample (one short utterance, one step)."""
+def cpu_baseline_leg(kwargs):
+    """Rank-0, N=1 only: the oracle port timed beside the GPU number, same bounded sample as ``--impl reference`` (1 warm-up + 2 steps)."""
     from oracle.model import ReformerTTSOracle
     from reformer_tts_b200.model.loss import TTSLoss
     cores = os.cpu_count() or 1
@@ -170,15 +190,13 @@ def cpu_baseline_leg(kwargs, seconds_budget=40.0):
     model = ReformerTTSOracle(**kwargs).train()
     loss_fn = TTSLoss(torch.tensor(5.))
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
-    frames = 200
-    batch = synthetic_batch(1, frames=frames, phonemes=50)
+    batch = synthetic_batch(1, frames=CPU_SAMPLE_FRAMES, phonemes=CPU_SAMPLE_PHONEMES)
     train_step(model, loss_fn, opt, batch)            # warm-up (first-call overheads)
     t0 = time.perf_counter()
     for _ in range(2):
         train_step(model, loss_fn, opt, batch)
     dt = (time.perf_counter() - t0) / 2
-    return {"value": frames / dt, "unit": "mel-frames/s", "cores": cores, "kind": "port",
-            "sample": f"1 utterance x {frames} mel frames (50 phonemes) per step, 1 warm-up + 2 timed steps, fp32 CPU oracle (oracle/model.py), {cores} threads"}
+    return {"value": CPU_SAMPLE_FRAMES / dt, "unit": "mel-frames/s", "cores": cores, "kind": "port", "sample": cpu_sample_description(2, 1, cores)}
 
 
 def run_ours(args, kwargs, world, rank, local_rank):
@@ -187,7 +205,7 @@ def run_ours(args, kwargs, world, rank, local_rank):
     from reformer_tts_b200.distributed import GradientAverager
     from reformer_tts_b200.model import ReformerTTS
     from reformer_tts_b200.model.loss import TTSLoss
-    from reformer_tts_b200.training import TrainStep, param_groups
+    from reformer_tts_b200.training import TrainStep, make_optimizer, set_lr, warmup_lr
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     _lib.load()
@@ -213,15 +231,22 @@ def run_ours(args, kwargs, world, rank, local_rank):
     model = ReformerTTS(**kwargs).to(dev).train()
     torch.manual_seed(42 + rank)                        # ref:reformer_tts/training/train.py:16 seeds 42; ranks draw different rotations / dropout
     loss_fn = TTSLoss(torch.tensor(5.)).to(dev)
-    # the reference's two parameter groups (no weight decay on biases / LayerNorm gains, ref:reformer_tts/training/wrappers.py:240-250)
-    opt = torch.optim.AdamW(param_groups(model, 1e-6), lr=1e-4, weight_decay=1e-6, fused=True, capturable=not args.no_cuda_graph)
-    averager = GradientAverager(model) if world > 1 else None
+    # the reference's trainer rules (ref:config/bucket-size-64-18-06.yml:26-32, ref:reformer_tts/training/wrappers.py:240-297): two AdamW
+    # parameter groups (no weight decay on biases / LayerNorm gains), lr 3e-4 with a 320-step linear warm-up, global-norm clip 1.0
+    base_lr, warmup_steps, grad_clip = 3e-4, 320, 1.0
+    opt = make_optimizer(model, base_lr, 1e-6, fused=True, capturable=True)
+    averager = GradientAverager(model, overlap=not args.no_overlap) if world > 1 else None
     batch_size = args.batch
     host = synthetic_batch(batch_size, seed=42 + rank, pin=True)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     # the public training-step API of the package; captures the step in a CUDA graph unless --no-cuda-graph
-    step = TrainStep(model, loss_fn, opt, host, use_cuda_graph=not args.no_cuda_graph, averager=averager, seed=1234 + rank)
+    step = TrainStep(model, loss_fn, opt, host, use_cuda_graph=not args.no_cuda_graph, averager=averager, seed=1234 + rank,
+                     grad_clip=grad_clip, accumulate_grad_batches=args.accumulate)
     resident = step.static                              # device-resident copy of the batch
+
+    def train(batch):
+        set_lr(opt, warmup_lr(step.optimizer_steps, base_lr, warmup_steps))      # tensor-valued lr: reaches the replayed graph
+        return step.step(batch)
 
     def sync():
         if world > 1:
@@ -230,7 +255,7 @@ def run_ours(args, kwargs, world, rank, local_rank):
 
     clocks = ClockSampler(local_rank) if rank == 0 else None      # running from the warm-up on; the timed region is marked below
     for _ in range(args.warmup):
-        step.step(resident)
+        train(resident)
     sync()
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------------------------------
     shapes = lsh_layer_shapes(kwargs, batch_size)
@@ -240,7 +265,7 @@ def run_ours(args, kwargs, world, rank, local_rank):
         clocks.mark()
     start.record()
     for _ in range(args.steps):
-        step.step(resident)
+        train(resident)
     end.record()
     sync()
     ms = start.elapsed_time(end)
@@ -249,7 +274,7 @@ def run_ours(args, kwargs, world, rank, local_rank):
     sync()
     start.record()
     for _ in range(args.steps):
-        loss_host = step.step(host).item()
+        loss_host = train(host).item()
     end.record()
     sync()
     ms_e2e = start.elapsed_time(end)
@@ -290,10 +315,10 @@ def run_ours(args, kwargs, world, rank, local_rank):
             roofline["avg_launch_ms"] = fwd_ms
             roofline["launches_timed"] = kernel_ms[key_fwd]["count"]
             roofline["algorithmic_flop_per_launch"] = flops_fwd
-            # DRAM bytes of one launch from the committed `ncu --set full` capture of this kernel at the benched shape
-            # (profiles/r1_attn_v2_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum); algorithmic minimum beside it
-            if (b, t, r, bucket) == (20, 1024, 8, 64):
-                roofline["traffic"] = NCU_DRAM_BYTES_FWD_DEC_CFG2
+            # DRAM bytes of one launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of
+            # this kernel at this shape; null when the kernel's sources have changed since that capture.  Algorithmic minimum beside it.
+            roofline["traffic"], roofline["traffic_source"] = ncu_traffic(f"lsh_attn_fwd_kernel<{bucket}>", f"B={b},T={t},H=8,R={r}",
+                                                                         ["lsh_attn_fwd.cu", "common.cuh"])
             roofline["algorithmic_min_bytes"] = 2 * b * t * d * 2 + r * b * t * d * 2 + r * b * 8 * t * 4
         if bwd_ms:
             roofline["bwd_kernel"] = {"kernel": f"lsh_attn_bwd_kernel<{bucket}> (decoder shape)", "avg_launch_ms": bwd_ms,
@@ -305,13 +330,16 @@ def run_ours(args, kwargs, world, rank, local_rank):
         cpu = cpu_baseline_leg(kwargs) if world == 1 and not args.no_cpu_baseline else None
         line = {"metric": "train_mel_frames_per_sec", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"ReformerTTS config/{args.config}.yml training step (fwd + loss + reversible bwd + AdamW)",
-                           "per_gpu_batch": batch_size, "global_batch": batch_size * world, "phonemes": PHONEMES, "mel_frames": FRAMES,
-                           "padded_lengths": [shapes["enc"][1], shapes["dec"][1]], "parallelism": f"dp{world}",
-                           "precision": "bf16 MMA operands, fp32 accumulate, fp32 residual stream / master weights; non-hot-path torch modules fp32 storage + TF32",
-                           "l2": "no flush: one step streams several GB of activations (>> 126 MB L2) through HBM",
-                           "optimizer": "torch AdamW(fused=True) over the reference's two parameter groups, inside the timed region",
-                           "cuda_graph": step.graph is not None, "cuda_graph_error": step.graph_error, "eager_ms_per_step": eager_ms},
+                "config": workload_config(args, kwargs, world),
+                "run": {"precision": "bf16 MMA operands, fp32 accumulate, fp32 residual stream / master weights; non-hot-path torch modules fp32 storage + TF32",
+                        "l2": "no flush: one step streams several GB of activations (>> 126 MB L2) through HBM",
+                        "trainer": f"torch AdamW(fused, capturable, tensor lr) over the reference's two parameter groups, lr {base_lr} with {warmup_steps}-step "
+                                   f"linear warm-up set every step, global-norm clip {grad_clip} after the all-reduce, accumulate_grad_batches "
+                                   f"{args.accumulate} - all inside the timed region",
+                        "gradient_allreduce": None if world == 1 else ("per reversible block, overlapped with the reversible backward, inside the captured graph"
+                                                                      if averager.overlap else "one flat all-reduce after backward"),
+                        "cuda_graph": step.graph is not None, "cuda_graph_error": step.graph_error, "eager_ms_per_step": eager_ms,
+                        "build_id": _lib.build_id()},
                 "e2e": {"value": e2e, "unit": "mel-frames/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "last_loss": loss_host},
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step, "clocks": clock_info, "roofline": roofline}
@@ -338,6 +366,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the reference config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the step eagerly instead of replaying a captured CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one flat gradient all-reduce after backward instead of per-block overlapped ones")
+    ap.add_argument("--accumulate", type=int, default=1, help="accumulate_grad_batches (the reference YAMLs use 3-5; 1 = every step reduces and updates)")
     args = ap.parse_args()
     from reformer_tts_b200.model import config as C
     kwargs = C.reference_model_kwargs(args.config)

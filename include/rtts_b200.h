@@ -41,6 +41,8 @@ typedef struct rtts_lsh_spec {
 
 const char* rtts_last_error(void);
 int rtts_abi_version(void);
+/* Hash of the sources this binary was built from (csrc/build.py source_hash); "unknown" for a build outside build.py. */
+const char* rtts_build_id(void);
 
 /* ---- LSH bucketing --------------------------------------------------------------------------- */
 

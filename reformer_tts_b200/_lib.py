@@ -59,6 +59,8 @@ def load() -> ctypes.CDLL:
         lib.rtts_last_error.argtypes = []
         lib.rtts_abi_version.restype = c_int
         lib.rtts_abi_version.argtypes = []
+        lib.rtts_build_id.restype = c_char_p
+        lib.rtts_build_id.argtypes = []
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError here = header / library mismatch: fail loudly
             fn.restype = RESTYPES.get(name, c_int)
@@ -72,3 +74,8 @@ def call(name: str, *args) -> None:
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.rtts_last_error().decode()}")
+
+
+def build_id() -> str:
+    """Hash of the sources the loaded binary was built from (csrc/build.py ``source_hash``)."""
+    return load().rtts_build_id().decode()

@@ -1,6 +1,7 @@
 """Build libreformer_b200.so in-tree with nvcc for sm_100a (no torch headers: the library is a plain C ABI)."""
 from __future__ import annotations
 
+import hashlib
 import os
 import subprocess
 import sys
@@ -16,6 +17,18 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-li
 FLAGS += os.environ.get("RTTS_DEFS", "").split()      # experiment builds only (e.g. RTTS_DEFS="-DRTTS_TIME_LD"), use with -f
 
 
+def source_hash(names=None) -> str:
+    """sha256 (16 hex digits) over the library's sources (all of them, or the given file names): what rtts_build_id() reports."""
+    if names is None:
+        files = sorted([*HERE.glob("*.cu"), *HERE.glob("*.cuh"), *HERE.glob("*.h"), ROOT / "include" / "rtts_b200.h"], key=lambda p: p.name)
+    else:
+        files = [HERE / n for n in names]
+    h = hashlib.sha256()
+    for f in files:
+        h.update(f.name.encode() + b"\0" + f.read_bytes() + b"\0")
+    return h.hexdigest()[:16]
+
+
 def _stale(obj: Path, src: Path) -> bool:
     if not obj.exists():
         return True
@@ -26,6 +39,9 @@ def _stale(obj: Path, src: Path) -> bool:
 def build(verbose: bool = False, force: bool = False) -> Path:
     objs = []
     procs = []
+    build_id = source_hash()
+    id_file = HERE / "build" / "build_id.txt"
+    id_changed = not id_file.exists() or id_file.read_text() != build_id
     for name in SOURCES:
         src = HERE / name
         if not src.exists():
@@ -33,8 +49,9 @@ def build(verbose: bool = False, force: bool = False) -> Path:
         obj = HERE / "build" / (name + ".o")
         obj.parent.mkdir(exist_ok=True)
         objs.append(obj)
-        if force or _stale(obj, src):
-            cmd = [NVCC, *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", str(src), "-o", str(obj)]
+        if force or _stale(obj, src) or (name == "api.cu" and id_changed):
+            extra = [f'-DRTTS_BUILD_ID="{build_id}"'] if name == "api.cu" else []
+            cmd = [NVCC, *FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-c", str(src), "-o", str(obj)]
             procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for name, proc in procs:
@@ -46,6 +63,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
         raise RuntimeError("nvcc failed")
     if procs or not LIB.exists():
         subprocess.check_call([NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"])
+    id_file.write_text(build_id)
     return LIB
 
 

@@ -1,14 +1,22 @@
 """Batch-sharded data parallelism for the ReformerTTS step: one process per GPU, model replicated, gradients
 averaged with NCCL all-reduce over NVLink 5 / NVSwitch (the reference is single-GPU; this is new).
 
-The reversible backward finishes a block's parameter gradients long before the step ends
+Gradient storage.  ``GradientBuckets`` owns ONE flat fp32 buffer; every parameter's ``.grad`` is a view into it, laid out
+bucket by bucket: one bucket per reversible block (in the order the reversible backward finishes them) and one for
+everything outside the reversible stacks.  Autograd accumulates into the views in place, so a bucket is ready for the
+collective the moment its block's backward returns - no ``cat`` into a staging buffer and no copy back - and global-norm
+clipping / zeroing are one kernel over the flat buffer.
+
+Overlap.  The reversible backward finishes a block's parameter gradients long before the step ends
 (ref:reformer_tts/model/reversible.py:127-128 is the point), so ``GradientAverager`` hooks
-``ReversibleSequence.on_block_done`` and launches one flat all-reduce per block on a side stream while the next
-block recomputes; everything outside the reversible stacks goes in one last bucket.  Works with any
-``torch.distributed`` backend (``gloo`` on CPU for the tests)."""
+``ReversibleSequence.on_block_done`` and issues one asynchronous all-reduce per bucket (NCCL: on the process group's own
+stream, ordered after the producing kernels by an event) while the next block recomputes; ``finish()`` issues the last bucket
+and makes the compute stream wait for all of them.  Everything is stream / event ordered, so the same code is captured into
+the training step's CUDA graph (``reformer_tts_b200.training.TrainStep``) with the collectives as parallel graph branches.
+Works with any ``torch.distributed`` backend (``gloo`` on CPU for the tests)."""
 from __future__ import annotations
 
-from typing import List
+from typing import Dict, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -16,78 +24,126 @@ from torch import nn
 
 from .model.reversible import ReversibleSequence
 
+_ALIGN = 64      # elements (256 B): every bucket starts on a 256-byte boundary
 
-class GradientAverager:
-    def __init__(self, model: nn.Module, overlap: bool = True):
-        self.model = model
-        self.world = dist.get_world_size() if dist.is_initialized() else 1
-        self.overlap = overlap and self.world > 1
-        self._pending = []          # (work handle or stream event, flat buffer, params)
-        self._stream = None
-        self._block_params = {}     # id(block) -> params
-        self._in_blocks = set()
+
+class GradientBuckets:
+    """One flat fp32 gradient buffer; ``p.grad`` of every trainable parameter is a view into it."""
+
+    def __init__(self, model: nn.Module):
+        params = [p for p in model.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError("GradientBuckets: the model has no trainable parameters")
+        if any(p.dtype != torch.float32 for p in params):
+            raise ValueError("GradientBuckets: master weights (and their gradients) are fp32")
+        self.device = params[0].device
+        seen = set()
+        groups: List[List[nn.Parameter]] = []
+        self._block_bucket: Dict[int, int] = {}      # id(block) -> bucket index
         for seq in [m for m in model.modules() if isinstance(m, ReversibleSequence)]:
             for block in seq.blocks:
-                params = [p for p in block.parameters() if p.requires_grad]
-                self._block_params[id(block)] = params
-                self._in_blocks.update(id(p) for p in params)
-            if self.overlap:
-                seq.on_block_done = self._on_block_done
-        self._rest = [p for p in model.parameters() if p.requires_grad and id(p) not in self._in_blocks]
+                own = [p for p in block.parameters() if p.requires_grad and id(p) not in seen]
+                seen.update(id(p) for p in own)
+                if own:
+                    self._block_bucket[id(block)] = len(groups)
+                    groups.append(own)
+        rest = [p for p in params if id(p) not in seen]
+        self.rest_bucket: Optional[int] = None
+        if rest:
+            self.rest_bucket = len(groups)
+            groups.append(rest)
+        self.groups = groups
+        bounds, total = [], 0
+        for g in groups:
+            start = total
+            for p in g:
+                total += p.numel()
+            total = (total + _ALIGN - 1) // _ALIGN * _ALIGN
+            bounds.append((start, total))
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.bounds = bounds
+        for g, (start, _) in zip(groups, bounds):
+            off = start
+            for p in g:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+
+    def bucket(self, index: int) -> torch.Tensor:
+        start, end = self.bounds[index]
+        return self.flat[start:end]
+
+    def bucket_of_block(self, block) -> Optional[int]:
+        return self._block_bucket.get(id(block))
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def attached(self) -> bool:
+        """True while every parameter's ``.grad`` still is its view (``zero_grad(set_to_none=True)`` would detach them)."""
+        base = self.flat.untyped_storage().data_ptr()
+        return all(p.grad is not None and p.grad.untyped_storage().data_ptr() == base for g in self.groups for p in g)
+
+
+class GradientAverager:
+    """Averages the gradients of a ``GradientBuckets`` over the ranks; per-bucket and overlapped with the reversible
+    backward when ``overlap`` (the default).  ``sync_enabled = False`` turns a backward pass into a local accumulation
+    (non-boundary micro-batches of gradient accumulation, ref:reformer_tts/training/train.py:77-89)."""
+
+    def __init__(self, model: nn.Module, overlap: bool = True, buckets: Optional[GradientBuckets] = None):
+        self.model = model
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.buckets = buckets if buckets is not None else GradientBuckets(model)
+        self.overlap = overlap and self.world > 1
+        self.sync_enabled = True
+        self._works = []
+        self._done = set()
+        # NCCL averages inside the collective; gloo (CPU tests) sums and the flat buffer is divided once
+        self._avg_in_collective = self.world > 1 and dist.get_backend() == "nccl"
+        for seq in [m for m in model.modules() if isinstance(m, ReversibleSequence)]:
+            seq.on_block_done = self._on_block_done
 
     # -- internals -------------------------------------------------------------------------------------------------
-    def _launch(self, params: List[torch.Tensor]):
-        params = [p for p in params if p.grad is not None]
-        if not params or self.world == 1:
+    def _reduce(self, index: int, async_op: bool):
+        if index in self._done:
             return
-        flat = torch.cat([p.grad.reshape(-1) for p in params])
-        if not self.overlap:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            self._pending.append((None, flat, params))
-            return
-        if flat.is_cuda:
-            if self._stream is None:
-                self._stream = torch.cuda.Stream()
-            self._stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self._stream):
-                work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
-            flat.record_stream(self._stream)
-        else:
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
-        self._pending.append((work, flat, params))
+        self._done.add(index)
+        op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+        work = dist.all_reduce(self.buckets.bucket(index), op=op, async_op=async_op)
+        if async_op:
+            self._works.append(work)
 
     def _on_block_done(self, index, block):
-        if self.overlap:
-            self._launch(self._block_params.get(id(block), []))
+        if not (self.overlap and self.sync_enabled and self.world > 1):
+            return
+        bucket = self.buckets.bucket_of_block(block)
+        if bucket is not None:
+            self._reduce(bucket, async_op=True)
 
     def enable_overlap(self):
         self.overlap = self.world > 1
 
     def disable_overlap(self):
-        """One flat all-reduce after backward on the current stream (what a CUDA-graph capture of the step records)."""
+        """One flat all-reduce after backward on the current stream instead of per-bucket collectives during it."""
         self.overlap = False
 
     # -- API -------------------------------------------------------------------------------------------------------
     def finish(self):
-        """Call after ``loss.backward()``: reduces what is left and writes the averaged gradients back."""
-        if self.world == 1:
+        """Call after ``loss.backward()``: reduces what is left and orders the compute stream after every collective."""
+        if self.world == 1 or not self.sync_enabled:
+            self._done.clear()
             return
         if self.overlap:
-            self._launch(self._rest)
+            for index in range(len(self.buckets.groups)):      # the non-block bucket, and any block the hook did not see
+                self._reduce(index, async_op=True)
+            for work in self._works:
+                work.wait()       # CUDA: the current stream waits for the collective's stream (no host blocking)
+            self._works.clear()
         else:
-            self._launch([p for p in self.model.parameters() if p.requires_grad])
-        for work, flat, params in self._pending:
-            if work is not None:
-                work.wait()
-                if flat.is_cuda:
-                    torch.cuda.current_stream().wait_stream(self._stream)
-            flat.div_(self.world)
-            offset = 0
-            for p in params:
-                n = p.grad.numel()
-                p.grad.copy_(flat[offset:offset + n].view_as(p.grad))
-                offset += n
-        self._pending.clear()
+            op = dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+            dist.all_reduce(self.buckets.flat, op=op)
+        self._done.clear()
+        if not self._avg_in_collective:
+            self.buckets.flat.div_(self.world)
 
 
 def shard_batch(batch_size: int, rank: int, world: int):

@@ -127,6 +127,8 @@ def _split_k(tokens: int, out_tiles: int = 64) -> int:
 
 
 class _LSHBase(nn.Module):
+    _last = (None, None, 1)      # (bucket ids, padding mask if the extra bucket was used, rounds) of the latest forward
+
     def _run(self, x, norm, w_qk, w_v, w_out, b_out, rot, mask, cfg):
         if not x.is_cuda:
             raise RuntimeError("reformer_tts_b200 LSH attention runs on sm_100a CUDA only; there is no CPU path")
@@ -138,8 +140,20 @@ class _LSHBase(nn.Module):
             ln_w, ln_b = norm.weight, norm.bias
             cfg = dict(cfg, eps=norm.eps)
         y = _LSHAttentionFn.apply(x.float(), ln_w, ln_b, w_qk, w_v, w_out, b_out, wqkv, wout, rot, mask_u8, cfg)
-        self.last_buckets = cfg.pop("_last_buckets", None)      # int32 [B,H,R*T] of this forward (parity tests read it)
+        self._last = (cfg.pop("_last_buckets", None), mask_u8 if cfg["pad_bucket"] else None, cfg["n_hashes"])
         return y
+
+    @property
+    def last_buckets(self):
+        """int32 [B,H,R*T] bucket ids of the latest forward in the numbering of the third-party class (parity tests read it).
+        The HF layer always hashes with the extra padding bucket when a mask is supplied (round stride nb + 1); transformers does
+        so only if the mask actually masks something (hf:740-747) - the sort order is the same either way, the ids are converted
+        here, on demand, off the hot path."""
+        buckets, pad_mask, rounds = self._last
+        if buckets is not None and pad_mask is not None and bool(pad_mask.all()):
+            t = buckets.shape[-1] // rounds
+            buckets = buckets - torch.arange(rounds, device=buckets.device, dtype=buckets.dtype).repeat_interleave(t)
+        return buckets
 
 
 class LSHSelfAttention(_LSHBase):
@@ -211,7 +225,7 @@ class HFLSHSelfAttention(_LSHBase):
         self.num_buckets = None      # hf:531-533 set lazily on the first call, then kept
         self._wqkv_cache, self._wout_cache = _WeightCache(), _WeightCache()
         self.rot_override = None
-        self._pad_bucket_cached = True
+        self.max_position_embeddings = 4096      # ReformerConfig default; the reference does not set it (ref:...reformer.py:204-212)
 
     def forward(self, x, attention_mask=None, norm: Optional[nn.LayerNorm] = None, **kwargs):
         b, t, d = x.shape
@@ -222,20 +236,19 @@ class HFLSHSelfAttention(_LSHBase):
         if self.num_buckets is None:
             self.num_buckets = 2 ** ((2 * (t // self.bucket_size)).bit_length() - 1)      # hf:781-785
         nb = self.num_buckets
-        if nb > 1024:
-            raise NotImplementedError("factorised bucket hashing (hf:788-793) is not built")
+        # hf:788-793: above this limit transformers switches to FACTORISED buckets [2^(n//2), 2^(n - n//2)] (different rotation
+        # shape, RNG consumption and ids): 128 buckets at chunk 64, 256 at chunk 128, i.e. T >= 8192 / 32768.  Not built.
+        limit = 2 * max(int((self.max_position_embeddings // self.bucket_size) ** 0.5), self.bucket_size)
+        if nb > limit:
+            raise NotImplementedError(f"HFLSHSelfAttention: {nb} buckets exceed transformers' limit of {limit} for chunk length "
+                                      f"{self.bucket_size}; the factorised bucket hashing it switches to (hf:788-793) is not built")
         rot = torch.randn((self.heads, d // self.heads, self.n_hashes, nb // 2), dtype=torch.float32, device=x.device)  # hf:717-719
         if self.rot_override is not None:
             rot = self.rot_override.to(device=x.device, dtype=torch.float32)
-        # hf:740-747: extra padding bucket only if some token is actually masked (a host sync in the reference too).  While a
-        # CUDA graph is being captured no host read is possible: the decision of the latest eager call (same batch layout) is kept.
-        if attention_mask is None:
-            pad_bucket = False
-        elif x.is_cuda and torch.cuda.is_current_stream_capturing():
-            pad_bucket = bool(self._pad_bucket_cached)
-        else:
-            pad_bucket = not bool(attention_mask.all())
-            self._pad_bucket_cached = pad_bucket
+        # hf:740-747 sends padded tokens to an extra bucket if the mask masks anything (a host sync in the reference).  Here the
+        # extra bucket is used whenever a mask is supplied: empty, it changes nothing but the round stride of the ids (same sort
+        # order, same attention), so there is no host decision to read - nothing a CUDA-graph capture could freeze wrongly.
+        pad_bucket = attention_mask is not None
         cfg = dict(heads=self.heads, n_hashes=self.n_hashes, bucket_size=self.bucket_size, n_buckets=nb, pad_bucket=pad_bucket,
                    spec=LSHSpec.huggingface(d // self.heads, self.causal), eps=1e-5)
         return self._run(x, norm, self.query_key.weight, self.value.weight, None, None, rot, attention_mask, cfg)

@@ -68,6 +68,11 @@ class Deterministic(nn.Module):
 
     def forward(self, *args, record_rng=False, set_rng=False, **kwargs):
         if self._private is not None and (record_rng or set_rng):
+            if record_rng and not torch.cuda.is_current_stream_capturing():
+                # a forward without a matching recompute (no_grad evaluation in train mode, an exception, a skipped step) must not
+                # leave the pair out of step for good: the recompute generator restarts where this forward starts.  (Generator
+                # state is host-side bookkeeping: no device sync.  Inside a capture every forward has its backward.)
+                self._private[2].set_state(self._private[1].get_state())
             return self._run_private(self._private[2] if set_rng else self._private[1], *args, **kwargs)
         if record_rng:
             self.record_rng(*args)

@@ -25,8 +25,11 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
-    assert declared - {"rtts_last_error", "rtts_abi_version"} == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
+    assert declared - {"rtts_last_error", "rtts_abi_version", "rtts_build_id"} == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
     assert lib.rtts_abi_version() == 1
+    # the binary was built from exactly the sources that are checked out (a stale prebuilt .so must not pass for HEAD)
+    from reformer_tts_b200.csrc.build import source_hash
+    assert _lib.build_id() == source_hash(), "libreformer_b200.so is stale: run python reformer_tts_b200/csrc/build.py"
     # argument validation happens before any CUDA call: a bad head size is reported, not launched
     rc = lib.rtts_lsh_hash(None, 0, None, 1, None, 0, None, None, 1, 128, 1, 64, 1, 2, None)
     assert rc != 0 and b"null pointer" in lib.rtts_last_error()
@@ -295,19 +298,33 @@ net = Net()
 data = torch.randn(6, 5, 8)
 lo, hi = shard_batch(6, dist.get_rank(), 2)
 avg = GradientAverager(net, overlap=(sys.argv[4] == "1"))
-(net(data[lo:hi]) / (hi - lo)).backward()
+assert avg.buckets.attached() and len(avg.buckets.groups) == 4       # three reversible blocks + everything else
+# micro-batch 1 of 2: local accumulation only (no collective), micro-batch 2: reduce
+avg.sync_enabled = False
+(0.5 * net(data[lo:hi]) / (hi - lo)).backward()
 avg.finish()
+local = avg.buckets.flat.clone()
+avg.sync_enabled = True
+(0.5 * net(data[lo:hi]) / (hi - lo)).backward()
+avg.finish()
+assert avg.buckets.attached()
 if dist.get_rank() == 0:
     ref = Net(); ref.load_state_dict(net.state_dict())
     (0.5 * (ref(data[:3]) / 3 + ref(data[3:]) / 3)).backward()
     err = max((p.grad - q.grad).abs().max().item() for p, q in zip(net.parameters(), ref.parameters()))
-    print("MAXERR", err)
+    half = Net(); half.load_state_dict(net.state_dict())
+    (0.5 * half(data[:3]) / 3).backward()
+    err_local = max((a - q.grad.reshape(-1)).abs().max().item() for a, q in
+                    zip([local[o:o + p.numel()] for o, p in [(p.grad.storage_offset(), p) for p in net.parameters()]], half.parameters()))
+    print("MAXERR", max(err, err_local))
 dist.destroy_process_group()
 """
 
 
 @pytest.mark.parametrize("overlap", ["0", "1"])
 def test_data_parallel_gradient_average_gloo_world2(tmp_path, overlap):
+    """World size 2 on CPU (gloo): flat gradient buckets (one per reversible block + the rest), per-bucket all-reduce from the
+    reversible backward's block hook (overlap) or one flat all-reduce, and a non-boundary micro-batch that must stay local."""
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
     port = str(29500 + (os.getpid() % 400) + (50 if overlap == "1" else 0))
@@ -317,3 +334,108 @@ def test_data_parallel_gradient_average_gloo_world2(tmp_path, overlap):
     assert all(p.returncode == 0 for p in procs), outs
     err = float(re.search(r"MAXERR ([0-9.e+-]+)", outs[0][0]).group(1))
     assert err <= 1e-5, err
+
+
+# ---------------------------------------------------------------------------------------------- trainer rules (host logic, CPU)
+class _ToyTTS(nn.Module):
+    """Smallest module with the ReformerTTS call signature (phonemes, spectrogram, mask) -> (raw, post, stop, attention): a
+    reversible stack between two linear layers, so TrainStep's bucket / accumulation / clipping logic runs on the CPU."""
+
+    def __init__(self):
+        super().__init__()
+        from reformer_tts_b200.model.reversible import ReversibleBlock, ReversibleSequence
+        mlp = lambda: nn.Sequential(nn.LayerNorm(16), nn.Linear(16, 32), nn.ReLU(), nn.Linear(32, 16))
+        self.inp = nn.Linear(80, 16)
+        self.layers = ReversibleSequence(nn.ModuleList([ReversibleBlock(mlp(), mlp()) for _ in range(2)]))
+        self.mel = nn.Linear(16, 80)
+        self.stop = nn.Linear(16, 1)
+
+    def forward(self, phonemes, spectrogram, mask):
+        h = self.inp(spectrogram)
+        y = self.layers(torch.cat([h, h], -1), kwargs_list=[{}] * 2)
+        h = torch.stack(y.chunk(2, dim=-1)).sum(0)
+        mel = self.mel(h)
+        return mel, mel + 0.1 * torch.tanh(mel), self.stop(h), None
+
+
+def _toy_batch(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    frames = 12
+    spec = torch.randn(n, frames + 1, 80, generator=g) * 3
+    stop = torch.zeros(n, frames)
+    stop[:, -1] = 1
+    return {"phonemes": torch.ones(n, 4, dtype=torch.long), "spectrogram": spec, "stop_tokens": stop, "loss_mask": torch.ones(n, frames, 80)}
+
+
+def test_train_step_accumulation_clipping_and_warmup_follow_the_reference_rules():
+    """ref:reformer_tts/training/train.py:77-89 (Lightning: accumulate_grad_batches, gradient_clip_val) and
+    ref:reformer_tts/training/wrappers.py:284-297 (warm-up) against a plain-PyTorch statement of the same rules:
+    k micro-batches of loss / k == one batch k times the size; clip_grad_norm_(1.0) before the update; lr set per optimiser step."""
+    import copy
+    from reformer_tts_b200.model.loss import TTSLoss
+    from reformer_tts_b200.training import TrainStep, make_optimizer, set_lr, warmup_lr
+    torch.manual_seed(0)
+    base = _ToyTTS()
+    loss_fn = TTSLoss(torch.tensor(5.))
+    micro = [_toy_batch(2, s) for s in (1, 2, 3)]
+    big = {k: torch.cat([m[k] for m in micro]) for k in micro[0]}
+
+    # reference rules, stated with stock torch
+    ref = copy.deepcopy(base)
+    opt_r = make_optimizer(ref, 1e-2, 1e-6, fused=False)
+    set_lr(opt_r, warmup_lr(0, 1e-2, 4))
+    spec = big["spectrogram"]
+    raw, post, stop, _ = ref(big["phonemes"], spec[:, :-1], big["loss_mask"].mean(-1))
+    loss_r = loss_fn(raw, post, stop.view(6, -1), spec[:, 1:], big["stop_tokens"], big["loss_mask"])[0]
+    loss_r.backward()
+    norm_r = torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+    assert norm_r > 1.0, "the case must actually clip"
+    opt_r.step()
+
+    ours = copy.deepcopy(base)
+    opt = make_optimizer(ours, 1e-2, 1e-6, fused=False)
+    step = TrainStep(ours, loss_fn, opt, micro[0], use_cuda_graph=False, grad_clip=1.0, accumulate_grad_batches=3)
+    set_lr(opt, warmup_lr(step.optimizer_steps, 1e-2, 4))
+    before = [p.detach().clone() for p in ours.parameters()]
+    losses = [step.step(micro[0]), step.step(micro[1])]
+    assert step.optimizer_steps == 0 and all(torch.equal(a, b) for a, b in zip(before, ours.parameters())), "no update before the boundary"
+    losses.append(step.step(micro[2]))
+    assert step.optimizer_steps == 1
+    assert torch.allclose(torch.stack(losses).mean(), loss_r, rtol=1e-5)
+    assert torch.allclose(step.grad_norm, norm_r, rtol=1e-4)
+    for a, b in zip(ours.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+    assert float(step.buckets.flat.abs().max()) == 0.0 and step.buckets.attached()      # zeroed in place, still the parameters' .grad
+    # a second optimiser step runs at the next warm-up rate
+    set_lr(opt, warmup_lr(step.optimizer_steps, 1e-2, 4))
+    assert opt.param_groups[0]["lr"] == pytest.approx(2 * 1e-2 / 4)
+
+
+def test_train_step_refuses_to_capture_an_optimizer_whose_lr_would_be_baked_in():
+    """a float lr (or a non-capturable optimiser) must not reach CUDA-graph capture, where warm-up would silently stop working."""
+    from reformer_tts_b200.model.loss import TTSLoss
+    from reformer_tts_b200.training import TrainStep, make_optimizer
+    model = _ToyTTS()
+    opt = make_optimizer(model, 1e-3, 1e-6, fused=False, capturable=False)
+    with pytest.raises(ValueError, match="capturable"):
+        TrainStep(model, TTSLoss(torch.tensor(5.)), opt, _toy_batch(2, 0), use_cuda_graph=True)
+
+
+def test_gradient_buckets_layout():
+    from reformer_tts_b200.distributed import GradientBuckets
+    model = _ToyTTS()
+    model.stop.weight.requires_grad_(False)
+    b = GradientBuckets(model)
+    assert len(b.groups) == 3 and b.rest_bucket == 2                     # two reversible blocks, then everything else
+    assert all(start % 64 == 0 for start, _ in b.bounds) and b.flat.numel() % 64 == 0
+    n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    assert sum(p.numel() for g in b.groups for p in g) == n_train and model.stop.weight.grad is None
+    for i, blk in enumerate(model.layers.blocks):
+        assert b.bucket_of_block(blk) == i
+        lo, hi = b.bounds[i]
+        for p in blk.parameters():
+            assert lo <= p.grad.storage_offset() and p.grad.storage_offset() + p.numel() <= hi
+    model(torch.ones(1, 4, dtype=torch.long), torch.randn(1, 12, 80), None)[0].sum().backward()
+    assert b.attached() and float(b.flat.abs().sum()) > 0
+    b.zero()
+    assert all(float(p.grad.abs().sum()) == 0 for g in b.groups for p in g)
