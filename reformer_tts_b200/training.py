@@ -86,7 +86,7 @@ class TrainStep:
 
     def __init__(self, model: nn.Module, loss_fn: nn.Module, optimizer: torch.optim.Optimizer, example_batch: Dict[str, torch.Tensor],
                  use_cuda_graph: bool = True, averager=None, warmup_steps: int = 3, seed: int = 1234, grad_clip: Optional[float] = None,
-                 accumulate_grad_batches: int = 1):
+                 accumulate_grad_batches: int = 1, private_rng: Optional[bool] = None):
         self.model, self.loss_fn, self.optimizer, self.averager = model, loss_fn, optimizer, averager
         self.grad_clip, self.accumulate = grad_clip, int(accumulate_grad_batches)
         assert self.accumulate >= 1
@@ -100,8 +100,15 @@ class TrainStep:
         self.grad_norm: Optional[torch.Tensor] = None                  # global gradient norm of the latest boundary step (before clipping)
         self.optimizer_steps = 0
         self._micro_index = 0
+        self._generators = []
+        # capture-safe randomness of the reversible recompute (mandatory under capture, optional in eager mode - the default there is
+        # the reference's record / replay of the global generator state)
         if use_cuda_graph:
             self._check_capturable()
+        if use_cuda_graph or private_rng:
+            for i, mod in enumerate(m for m in self.model.modules() if isinstance(m, Deterministic)):
+                self._generators.append(mod.use_private_generators(seed + i, self.device))
+        if use_cuda_graph:
             rng_before = torch.cuda.get_rng_state(self.device)
             try:
                 self._capture(warmup_steps, seed)
@@ -113,6 +120,7 @@ class TrainStep:
                 for mod in self.model.modules():
                     if isinstance(mod, Deterministic):
                         mod._private = None
+                self._generators = []
                 torch.cuda.set_rng_state(rng_before, self.device)
                 self.buckets.zero()
 
@@ -174,10 +182,15 @@ class TrainStep:
                     g["lr"] = lr
         self.buckets.zero()
 
+    def reseed(self, seed: int) -> None:
+        """Restart the private generator pairs (sub-network i: seed + i).  Two TrainSteps over equal models, reseeded alike, draw
+        the same rotations and dropout masks whether they replay a graph or run eagerly."""
+        for i, (fwd, rec) in enumerate(self._generators):
+            fwd.manual_seed(seed + i)
+            rec.manual_seed(seed + i)
+
     def _capture(self, warmup_steps: int, seed: int):
-        generators = []
-        for i, mod in enumerate(m for m in self.model.modules() if isinstance(m, Deterministic)):
-            generators += mod.use_private_generators(seed + i, self.device)
+        generators = [g for pair in self._generators for g in pair]
         # Warm-up on a side stream (allocator, cuDNN / NCCL initialisation, lazily created optimiser state).  It runs real
         # optimiser updates on the example batch, so weights, buffers, optimiser state and learning rate are put back afterwards:
         # constructing a TrainStep does not train.

@@ -1,0 +1,157 @@
+"""The CUDA-graph training step (reformer_tts_b200.training.TrainStep) - the code path every bench number comes from:
+graph replay against the same step run eagerly (same seeds: rotations and dropout masks of the forward AND of the reversible
+recompute must coincide), learning-rate warm-up reaching the replayed graph, gradient accumulation, clipping, and the
+data-parallel all-reduce inside the graph (2 GPUs).  ref:reformer_tts/training/wrappers.py:234-297, ref:reformer_tts/training/train.py:77-89."""
+import copy
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from _util import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _kwargs(post_attn_dropout=0.2, cross_dropout=0.1):
+    from reformer_tts_b200.model import config as C
+    attn = {"implementation": "reformer_pytorch", "heads": 2, "n_hashes": 2, "post_attn_dropout": post_attn_dropout}
+    return C.model_kwargs({"num_mel_coeffs": 80, "dict_size": 76, "embedding_dim": 128, "pad_base": 128, "scp_encoding_dropout": 0.,
+                           "enc_prenet_kwargs": {"dropout": 0.}, "dec_prenet_kwargs": {"hidden_size": 64, "dropout": 0.},
+                           "enc_reformer_kwargs": {"depth": 2, "attn_kwargs": dict(attn), "ff_kwargs": {"hidden": 256}},
+                           "dec_reformer_kwargs": {"depth": 2, "attn_kwargs": {"num_heads": 2, "dropout": cross_dropout},
+                                                   "self_attn_kwargs": dict(attn), "ff_kwargs": {"hidden": 256}},
+                           "postnet_kwargs": {"depth": 2, "dropout": 0.}})
+
+
+def _batch(n, seed, frames=200, phonemes=100):
+    g = torch.Generator().manual_seed(seed)
+    spec = torch.randn(n, frames + 1, 80, generator=g)
+    stop = torch.zeros(n, frames)
+    stop[:, -1] = 1
+    return {"phonemes": torch.randint(1, 77, (n, phonemes), generator=g), "spectrogram": spec, "stop_tokens": stop,
+            "loss_mask": torch.ones(n, frames, 80)}
+
+
+def _make(kw, lr=1e-3):
+    from reformer_tts_b200.model import ReformerTTS
+    from reformer_tts_b200.model.loss import TTSLoss
+    from reformer_tts_b200.training import make_optimizer
+    torch.manual_seed(0)
+    model = ReformerTTS(**kw).to(DEV).train()
+    return model, TTSLoss(torch.tensor(5.)).to(DEV), make_optimizer(model, lr, 1e-6)
+
+
+def test_graph_replay_equals_eager_steps_with_dropout_and_changing_batches():
+    """N graph-replayed steps against N eager steps, post_attn_dropout and cross-attention dropout > 0, a different
+    batch every step.  If the recompute of the replayed graph saw other rotations / masks than its forward, x = y - f(x) and every
+    gradient would be wrong while the step time looked fine."""
+    from reformer_tts_b200.training import TrainStep, set_lr
+    kw = _kwargs()
+    model_g, loss_fn, opt_g = _make(kw)
+    model_e = copy.deepcopy(model_g)
+    from reformer_tts_b200.training import make_optimizer
+    opt_e = make_optimizer(model_e, 1e-3, 1e-6)
+    before = {k: v.clone() for k, v in model_g.state_dict().items()}
+    graph = TrainStep(model_g, loss_fn, opt_g, _batch(2, 0), use_cuda_graph=True, seed=11, grad_clip=1.0)
+    assert graph.graph is not None, graph.graph_error
+    # constructing the step (3 warm-up updates on the example batch) must not have trained the model
+    for k, v in model_g.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    assert all(float(st["step"]) == 0 and float(st["exp_avg"].abs().max()) == 0 for st in opt_g.state.values())
+    eager = TrainStep(model_e, loss_fn, opt_e, _batch(2, 0), use_cuda_graph=False, private_rng=True, seed=11, grad_clip=1.0)
+    graph.reseed(5)
+    eager.reseed(5)
+    for i in range(3):
+        b = _batch(2, 100 + i)
+        lg, le = graph.step(b), eager.step(b)
+        assert abs(lg.item() - le.item()) <= 1e-4 * abs(le.item()), (i, lg.item(), le.item())
+    for (k, a), c in zip(model_g.named_parameters(), model_e.parameters()):
+        assert rel_l2(a, c) <= 1e-4, k       # split-K weight gradients are summed with atomics: bits differ run to run, values do not
+    # the reference's warm-up reaches the replayed graph: a zero rate leaves the weights alone, the next rate moves them
+    w = {k: v.detach().clone() for k, v in model_g.named_parameters()}
+    set_lr(opt_g, 0.0)
+    graph.step(_batch(2, 7))
+    assert all(torch.equal(v, w[k]) for k, v in model_g.named_parameters() if "bias" in k), "lr = 0 must not move un-decayed parameters"
+    set_lr(opt_g, 1e-3)
+    graph.step(_batch(2, 8))
+    assert any(not torch.equal(v, w[k]) for k, v in model_g.named_parameters())
+
+
+def test_three_accumulated_micro_batches_equal_one_batch_of_three_times_the_size():
+    """accumulate_grad_batches (ref:reformer_tts/training/train.py:77-89) through the two captured graphs.  Dropout off and
+    BatchNorm layers frozen (batch statistics of a micro-batch differ from those of the big batch - in the reference too)."""
+    from reformer_tts_b200.training import TrainStep, make_optimizer
+    kw = _kwargs(0., 0.)
+    model_a, loss_fn, opt_a = _make(kw)
+    for m in model_a.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.eval()
+    model_b = copy.deepcopy(model_a)
+    opt_b = make_optimizer(model_b, 1e-3, 1e-6)
+    micro = [_batch(2, 30 + i) for i in range(3)]
+    big = {k: torch.cat([m[k] for m in micro]) for k in micro[0]}
+    acc = TrainStep(model_a, loss_fn, opt_a, micro[0], use_cuda_graph=True, seed=3, grad_clip=1.0, accumulate_grad_batches=3)
+    assert acc.graph is not None and acc.graph_micro is not None, acc.graph_error
+    one = TrainStep(model_b, loss_fn, opt_b, big, use_cuda_graph=True, seed=3, grad_clip=1.0)
+    # same rotations on both sides: the draw does not depend on the batch size (shared across the batch, rp R2)
+    acc.reseed(9)
+    one.reseed(9)
+    losses = []
+    for i, b in enumerate(micro):
+        acc.reseed(9)                      # every micro-batch re-draws what the big batch drew once
+        losses.append(acc.step(b).item())
+    big_loss = one.step(big).item()
+    assert acc.optimizer_steps == 1 and one.optimizer_steps == 1
+    assert abs(sum(losses) / 3 - big_loss) <= 1e-4 * abs(big_loss)
+    assert rel_l2(acc.grad_norm, one.grad_norm) <= 1e-3
+    for (k, a), c in zip(model_a.named_parameters(), model_b.parameters()):
+        assert rel_l2(a, c) <= 2e-4, k
+
+
+_DDP_WORKER = r"""
+import os, sys, copy, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from test_training_gpu import _kwargs, _batch, _make
+from reformer_tts_b200.distributed import GradientAverager
+from reformer_tts_b200.training import TrainStep, make_optimizer
+rank = int(os.environ["RANK"]); torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+kw = _kwargs()
+model_g, loss_fn, opt_g = _make(kw)
+model_e = copy.deepcopy(model_g); opt_e = make_optimizer(model_e, 1e-3, 1e-6)
+g = TrainStep(model_g, loss_fn, opt_g, _batch(2, rank), use_cuda_graph=True, averager=GradientAverager(model_g), seed=20 + rank, grad_clip=1.0)
+assert g.graph is not None, g.graph_error
+e = TrainStep(model_e, loss_fn, opt_e, _batch(2, rank), use_cuda_graph=False, private_rng=True, averager=GradientAverager(model_e), seed=20 + rank, grad_clip=1.0)
+g.reseed(40 + rank); e.reseed(40 + rank)
+for i in range(3):
+    b = _batch(2, 10 * i + rank)            # every rank its own shard
+    lg, le = g.step(b), e.step(b)
+    assert abs(lg.item() - le.item()) <= 1e-4 * abs(le.item()), (i, lg.item(), le.item())
+err = max(((a - c).norm() / c.norm().clamp_min(1e-20)).item() for a, c in zip(model_g.parameters(), model_e.parameters()))
+flat = torch.cat([p.detach().reshape(-1) for p in model_g.parameters()])
+other = flat.clone(); dist.all_reduce(other, op=dist.ReduceOp.MAX)
+same = float((flat - other).abs().max())      # replicas stay identical: every rank applied the same averaged gradient
+print("DDP_RESULT", rank, err, same, float(g.grad_norm), float(e.grad_norm), flush=True)
+torch.cuda.synchronize(); dist.barrier(); os._exit(0)
+"""
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_data_parallel_graph_replay_equals_eager_overlapped_path_on_two_gpus(tmp_path):
+    """The per-block all-reduce overlapped with the reversible backward, INSIDE the captured graph, on 2 ranks over NCCL: three
+    replayed steps against three eager steps (same shards, same seeds), replicas identical afterwards."""
+    script = tmp_path / "ddp_worker.py"
+    script.write_text(_DDP_WORKER)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29611", str(script), ROOT], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    results = [l.split() for l in out.stdout.splitlines() if l.startswith("DDP_RESULT")]
+    assert len(results) == 2
+    for _, rank, err, same, gn_g, gn_e in results:
+        assert float(err) <= 1e-4 and float(same) == 0.0, results
+        assert abs(float(gn_g) - float(gn_e)) <= 1e-3 * float(gn_e)
