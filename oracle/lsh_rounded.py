@@ -37,7 +37,7 @@ LN2 = 0.6931471805599453
 EXACT_BOUND = 60.0        # lsh_attn_fwd.cu kExactBound
 # True: the forward kernel's softmax normaliser is the sum of the bf16-ROUNDED P (it comes out of the same tensor-core
 # contraction as O = P V: a ones block appended to V); False: the fp32 sum of the unrounded terms.
-KERNEL_SUM_ROUNDED = False
+KERNEL_SUM_ROUNDED = True
 
 
 def bf16r(x: torch.Tensor) -> torch.Tensor:

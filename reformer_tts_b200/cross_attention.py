@@ -44,6 +44,7 @@ class _CrossAttentionFn(torch.autograd.Function):
         y = ops.gemm(o2, wo_bf16, bias=b_out, resid=resid, resid_sub=resid_sub).view(b, t, d)
         ctx.inner = (ql, kl, vl, o) if need_grad else None
         ctx.has_ln = ln_w is not None
+        ctx.params = (ln_w, ln_b, w_in, w_out, b_out)
         ctx.dims = (b, t, s, d, h)
         ctx.save_for_backward(x2, ln_w, mean, rstd, xn, memb, o2, wq_bf16, wkv_bf16, wo_bf16)
         return y
@@ -58,10 +59,19 @@ class _CrossAttentionFn(torch.autograd.Function):
         dev = x2.device
         rows_q, rows_kv = b * t, b * s
         tiles = (d // 128) ** 2
+        p_lnw, p_lnb, p_win, p_wout, p_bout = ctx.params
+        ctx.params = None
+
+        def target(shape, param):
+            """The parameter's own .grad inside the flat gradient buffer (then None is returned for it), else a zero-filled temporary
+            that autograd adds (reformer_tts_b200.residual.grad_sink)."""
+            sink = ops.grad_sink(param)
+            return (sink, True) if sink is not None else (torch.zeros(shape, dtype=torch.float32, device=dev), False)
+
         # output projection
-        g_bo = torch.zeros(d, dtype=torch.float32, device=dev)
+        g_bo, s_bo = target((d,), p_bout)
         dyb = ops.cast_bf16_colsum(dy.reshape(rows_q, d), g_bo)
-        g_wo = torch.zeros((d, d), dtype=torch.float32, device=dev)
+        g_wo, s_wo = target((d, d), p_wout)
         ops.gemm(dyb, o2, a_mn_major=True, b_mn_major=True, out=g_wo, accumulate=True, split_k=_split_k(rows_q, tiles))
         do = ops.gemm(dyb, wo_bf16, b_mn_major=True, out_dtype=torch.bfloat16)            # [B*T, D]
         # attention core (vendor kernel, saved inner graph)
@@ -71,7 +81,7 @@ class _CrossAttentionFn(torch.autograd.Function):
             dq = dq.contiguous()
         dkv = torch.stack((dk4.transpose(1, 2), dv4.transpose(1, 2)), dim=2).reshape(rows_kv, 2 * d)
         # input projections: weights [3D, D] = [Wq; Wk; Wv]
-        g_win = torch.zeros((3 * d, d), dtype=torch.float32, device=dev)
+        g_win, s_win = target((3 * d, d), p_win)
         g_bin = torch.empty(3 * d, dtype=torch.float32, device=dev)
         torch.sum(dq, dim=0, dtype=torch.float32, out=g_bin[:d])
         torch.sum(dkv, dim=0, dtype=torch.float32, out=g_bin[d:])
@@ -80,13 +90,16 @@ class _CrossAttentionFn(torch.autograd.Function):
         dxn = ops.gemm(dq, wq_bf16, b_mn_major=True)                                        # fp32 [B*T, D]
         dmem = ops.gemm(dkv, wkv_bf16, b_mn_major=True).view(b, s, d)                       # fp32 [B, S, D]
         g_lnw = g_lnb = None
+        s_g = s_bt = False
         if ctx.has_ln:
-            g_lnw = torch.zeros(d, dtype=torch.float32, device=dev)
-            g_lnb = torch.zeros(d, dtype=torch.float32, device=dev)
+            g_lnw, s_g = target((d,), p_lnw)
+            g_lnb, s_bt = target((d,), p_lnb)
             dx = ops.layernorm_bwd(dxn, x2, ln_w, mean, rstd, g_lnw, g_lnb, accumulate_request=True)
         else:
             dx = dxn
-        return dx.view(b, t, d), g_lnw, g_lnb, dmem, g_win, g_bin, g_wo, g_bo, None, None, None, None, None
+        drop = lambda g, sunk: None if sunk else g
+        return (dx.view(b, t, d), drop(g_lnw, s_g), drop(g_lnb, s_bt), dmem, drop(g_win, s_win), g_bin, drop(g_wo, s_wo), drop(g_bo, s_bo),
+                None, None, None, None, None)
 
 
 def cross_attention(x, norm, memory, layer, caches, key_padding_mask):

@@ -18,6 +18,7 @@
 //   O = P V            tcgen05.mma with A = P from TMEM, B = the gathered V block used MN-major -> TMEM
 //   epilogue           O / rowsum -> bf16, scatter-stored at the UNSORTED slot (r*T + pos); lse too.
 #include <cfloat>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -46,6 +47,7 @@ struct AttnFwdParams {
   float score_scale_log2;  // score_scale * log2(e)
   float mask_value_log2, self_value_log2;
   int key_norm, mask_mode, causal;
+  int pos16;          // T <= 2048: positions are exact in fp16, the position mask is evaluated two keys per instruction
 };
 
 // Persistent, warp-specialised pipeline; CTA c owns tiles [c*N/grid, (c+1)*N/grid) of the (row, tile-in-row) order.
@@ -106,13 +108,16 @@ struct AttnFwdSmem {
   static constexpr int kOffK = 0;                                    // per slot (1024-B aligned): [ K block | V block ]
   static constexpr int kOffV = kTileBytes;
   static constexpr int kSlotBytes = 2 * kTileBytes;
-  static constexpr int kOffMeta = kSlots * kSlotBytes;               // per slot: float scale[128], int pos[128], int exact_tag (+pad)
+  static constexpr int kOffOnes = kSlots * kSlotBytes;               // 8 rows x 128 B of bf16 1.0 (1024-B aligned): B operand of the row-sum MMA (P . 1)
+  static constexpr int kOffMeta = kOffOnes + 1024;                   // per slot: float scale[128], int pos[128], int exact_tag (+pad), half pos16[128]
   static constexpr int kMetaScale = 0, kMetaPos = kQRows * 4, kMetaTag = 2 * kQRows * 4;
   static constexpr int kMetaGeo = kMetaTag + 16;                     // int4 {row_bh, base_main (round * T), round_start, -}: written by the loader
-  static constexpr int kMetaBytes = 2 * kQRows * 4 + 32;
-  static constexpr int kOffPart = kOffMeta + kSlots * kMetaBytes;    // float[2 tile parities][2 phases][kParts][128 rows] partial row sums (bit 31: duplicate seen) / maxima
-  // per (tile parity, phase): what the epilogue needs besides the partial sums: float max[128], int slot[128], int row_bh (+pad)
-  static constexpr int kOffFin = kOffPart + 4 * kMaxParts * kQRows * 4;
+  static constexpr int kMetaPos16 = 2 * kQRows * 4 + 32;             // fp16 position per row (+inf for a padded token): packed position mask
+  static constexpr int kMetaBytes = 2 * kQRows * 4 + 32 + kQRows * 2;
+  static constexpr int kOffPart = kOffMeta + kSlots * kMetaBytes;    // float[2 softmax groups][kParts][128 rows]: row maxima of the exact two-pass mode (exchange inside one tile)
+  static constexpr int kOffDup = kOffPart + 2 * kMaxParts * kQRows * 4;   // uint[2 tile parities][2 phases][128 rows]: bit 31 = the query's own token also sits in its look-back chunk
+  // per (tile parity, phase): what the epilogue needs: float max[128], int slot[128], int4 {row_bh, round_start, -, -}
+  static constexpr int kOffFin = kOffDup + 4 * kQRows * 4;
   static constexpr int kFinMax = 0, kFinSlot = kQRows * 4, kFinRow = 2 * kQRows * 4;
   static constexpr int kFinBytes = 2 * kQRows * 4 + 16;
   static constexpr int kOffStage = kOffFin + 4 * kFinBytes;          // epilogue staging: 4 warps x 32 rows x 128 B (swizzled) for coalesced stores
@@ -120,6 +125,7 @@ struct AttnFwdSmem {
   static constexpr int kOffTmem = kOffBar + (2 * kSlots + 8) * 8;
   static constexpr int kTotal = kOffTmem + 8;
   static constexpr int kDynamic = kTotal;                            // no static shared memory in the kernel: the dynamic segment starts 1024-B aligned (checked)
+  static_assert(kTotal <= 232448, "shared memory budget of one CTA (227 KB)");
 };
 
 #ifdef RTTS_TRACE      // timeline build (tools/trace_fwd.py): RTTS_DEFS=-DRTTS_TRACE python reformer_tts_b200/csrc/build.py -f
@@ -199,6 +205,42 @@ __device__ __forceinline__ void soft_chunk(uint32_t* r, uint32_t a_pos, uint32_t
   for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
 }
 
+// The same chunk with the masks applied AFTER the exponentials, on the packed bf16 pairs, two keys per instruction: positions
+// below 2048 are exact in fp16 (a padded key holds +inf), so `key position > query limit` is one HSET2 producing a 0xffff / 0
+// mask per key and clearing P is one LOP3 - a quarter of the ISETP + FSEL pairs of the fp32 form.  The query's own column is a
+// fixed column of the tile (key column BUCKET + row), found by comparing the constant column indices with `self_col` (the own
+// column relative to this chunk; anything outside 0..15 never matches).  No row sum here: it comes out of the tensor pipe (P . 1).
+template <bool MASK, bool SELF>
+__device__ __forceinline__ void soft_chunk_packed(uint32_t* r, uint32_t a_pos16, uint32_t a_scale, float neg_m, uint32_t q_limit2, int self_col, uint32_t* pk) {
+  float* x = reinterpret_cast<float*>(r);
+  {
+    uint4 s[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[q] = lds128(a_scale + q * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {      // packed fp32 FMA: two scores per instruction
+      ffma2(x[q * 4 + 0], x[q * 4 + 1], x[q * 4 + 0], x[q * 4 + 1], __uint_as_float(s[q].x), __uint_as_float(s[q].y), neg_m, neg_m);
+      ffma2(x[q * 4 + 2], x[q * 4 + 3], x[q * 4 + 2], x[q * 4 + 3], __uint_as_float(s[q].z), __uint_as_float(s[q].w), neg_m, neg_m);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = exp2f(x[i]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
+  if (MASK) {
+    const uint4 k0 = lds128(a_pos16), k1 = lds128(a_pos16 + 16);
+    const uint32_t kp[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    const __half2 ql = *reinterpret_cast<const __half2*>(&q_limit2);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pk[i] &= ~__hgt2_mask(*reinterpret_cast<const __half2*>(&kp[i]), ql);      // exp2(mask_value - m) == 0
+  }
+  if (SELF) {
+    const __half2 sc = __half2half2(__int2half_rn(self_col));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pk[i] &= ~__heq2_mask(__floats2half2_rn(2.f * i, 2.f * i + 1.f), sc);       // exp2(self_value - m) == 0
+  }
+}
+
 // Row maximum of one 16-column chunk with the reference's fill values (exact mode, first pass).
 __device__ __forceinline__ float chunk_max(const uint32_t* r, uint32_t a_pos, uint32_t a_scale, int q_limit, int q_enc, float mv, float sv, float mx) {
 #pragma unroll
@@ -225,6 +267,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
   constexpr int kTail = kQRows - BUCKET;  // first look-back row inside the previous block
   constexpr uint32_t kColO = BUCKET == 64 ? 192 : 64;
   constexpr bool kAliasO = BUCKET == 128; // bucket 128: S fills all 256 columns of the region, O reuses columns S no longer needs
+  // Row sums of P come out of the tensor pipe: one more accumulator, D2 = P . 1 (16 identical columns), in S columns that are
+  // dead once the softmax has consumed them - the second half of P block 0 (bucket 64) / the tail of the region (bucket 128).
+  // It is the sum of the bf16-ROUNDED P, i.e. exactly the normaliser of the O = P V the same instruction stream accumulates.
+  constexpr uint32_t kColSum = BUCKET == 64 ? 16 : 192;
   constexpr uint32_t kTmemCols = 512;
 #ifndef RTTS_PARTS64
 #define RTTS_PARTS64 4
@@ -287,6 +333,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
     fence_mbar_init();
   }
   if (tid < kSlots) *reinterpret_cast<int*>(smem + L::kOffMeta + tid * L::kMetaBytes + L::kMetaTag) = 0;
+  for (int i = tid; i < 256; i += kFwdThreads) reinterpret_cast<uint32_t*>(smem + L::kOffOnes)[i] = 0x3F803F80u;      // bf16 1.0 pairs
+  for (int i = tid; i < 4 * kQRows; i += kFwdThreads) reinterpret_cast<uint32_t*>(smem + L::kOffDup)[i] = 0u;
+  fence_proxy_async_smem();          // the ones tile is read by the tensor-core (async) proxy
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
@@ -312,9 +361,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
         mbar_wait(full + st, (k / kSlots) & 1);       // a fresh tile's look-back rows are part of this (the loader waits for PV(k-1))
         RTTS_STAMP(0, k, 0);
         if (k >= 2) {
-          // S(k) overwrites the S/P columns PV(k-2) reads (and, bucket 128, the O columns its epilogue reads)
-          if (kAliasO) mbar_wait(o_free + g, ((k >> 1) & 1) ^ 1);
-          else mbar_wait(o_full + g, ((k >> 1) & 1) ^ 1);
+          // S(k) overwrites the S/P columns PV(k-2) reads and the row-sum columns (bucket 128: also the O columns) its epilogue reads
+          mbar_wait(o_free + g, ((k >> 1) & 1) ^ 1);
         }
         tc_fence_after_sync();
         const uint32_t q_lo = k_lo0 + st * kSlotLo, lb_lo = k_lo0 + sp * kSlotLo + kTailLo;
@@ -331,8 +379,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
     // ================================================= MMA issuer: O = P V =========================================
     if (elect_one()) {
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, kDh, false, true);
+      constexpr uint32_t idesc_sum = umma_idesc_bf16(128, 16, false, false);
       constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+      constexpr uint32_t hi_ones = umma_desc_hi_sw128(0);                     // 8-row group stride 0: the 16 rows of B alias one 1 KB atom of ones
       const uint32_t v_lo0 = umma_desc_lo(smem_u32(smem + L::kOffV), 0);      // MN-major operand (V rows)
+      const uint32_t ones_lo = umma_desc_lo(smem_u32(smem + L::kOffOnes), 16);
       constexpr uint32_t kSlotLo = L::kSlotBytes >> 4, kTailLo = (kTail * 128) >> 4;
       int t_in_next = (g0 + 1) % p.tiles_per_row;     // tile-in-row of tile m + 1 (fresh when 0)
       for (int m = 0; m < my_tiles; ++m) {
@@ -349,6 +400,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           const uint32_t b_lo = (j * 16 < BUCKET) ? v_lb + j * (2048 >> 4) : v_main + (j * 16 - BUCKET) * (128 >> 4);
           umma_ts_lo(t_reg + kColO, t_reg + p_col<BUCKET>(j >> 1) + (j & 1) * 8, b_lo, hi, idesc_o, j > 0);
         }
+#pragma unroll
+        for (int j = 0; j < kKeyRows / 16; ++j)      // row sums: D2 = P . 1 (N = 16, the narrowest shape of an M = 128 MMA)
+          umma_ts_lo(t_reg + kColSum, t_reg + p_col<BUCKET>(j >> 1) + (j & 1) * 8, ones_lo, hi_ones, idesc_sum, j > 0);
         RTTS_STAMP(0, m, 6);
         umma_commit(o_full + g);
         // S(m) (issued by the other warp) completed before the softmax of tile m started, so everything that reads the previous
@@ -375,19 +429,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       // PV(k+2) waits for this role's o_free(k).
       mbar_wait_relaxed(o_full + g, ph, 40);
       tc_fence_after_sync();
-      const uint32_t a_part = smem_u32(smem + L::kOffPart) + (g * 2 + ph) * kMaxParts * kQRows * 4;
-      float row_sum = 0.f;
+      uint32_t rs;
+      tmem_ld1(t_lane + g * 256 + kColSum, &rs);                   // row sum of the (bf16) P row, from the tensor pipe
+      const uint4 fin = lds128(a_fin + L::kFinRow);                // {row_bh, first tile of a hash round, -, -}
+      const int row_bh = static_cast<int>(fin.x);
       uint32_t dup = 0;
-#pragma unroll
-      for (int q = 0; q < kParts; ++q) {
-        const uint32_t u = lds32(a_part + (q * kQRows + m) * 4);
-        row_sum += __uint_as_float(u & 0x7fffffffu);
-        dup |= u;
+      if (fin.y != 0) {                                           // only there can the own token sit in the look-back chunk a second time
+        const uint32_t a_dup = smem_u32(smem + L::kOffDup) + ((g * 2 + ph) * kQRows + m) * 4;
+        dup = lds32(a_dup);
+        if (dup != 0) sts32(a_dup, 0u);                          // (this role owns the row's flag once o_full has fired)
       }
       float row_max = __uint_as_float(lds32(a_fin + L::kFinMax + m * 4));
-      const int row_bh = static_cast<int>(lds32(a_fin + L::kFinRow));
       const int64_t row_base = static_cast<int64_t>(row_bh) * RT;
       const int own_slot = static_cast<int>(lds32(a_fin + L::kFinSlot + m * 4));
+      tmem_ld_wait();
+      float row_sum = __uint_as_float(rs);
       // all terms exactly zero: the row sees only itself (see the softmax role); exact-mode rows always have a positive sum
       const bool lonely = !(row_sum > 0.f);
       if (lonely) {
@@ -584,6 +640,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           const int j = kTail + (c + 8 * q) * kGroups + grp;
           reinterpret_cast<float*>(meta_p + L::kMetaScale)[j] = key_scale_of(ssq);
           reinterpret_cast<int*>(meta_p + L::kMetaPos)[j] = valid ? my_pos : (my_pos | kPadFlag);
+          reinterpret_cast<__half*>(meta_p + L::kMetaPos16)[j] = valid ? __int2half_rn(my_pos) : __ushort_as_half(0x7c00);      // padded: +inf
         }
       }
       wait_free(st_i);
@@ -607,6 +664,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           const float ks = key_scale_of(ssq_cur[q]);
           reinterpret_cast<float*>(meta + L::kMetaScale)[my_row] = ks;
           reinterpret_cast<int*>(meta + L::kMetaPos)[my_row] = valid_cur[q] ? my_pos : (my_pos | kPadFlag);
+          reinterpret_cast<__half*>(meta + L::kMetaPos16)[my_row] = valid_cur[q] ? __int2half_rn(my_pos) : __ushort_as_half(0x7c00);
           // a query whose score bound could push a visible key below the exp2 underflow: the pair runs this tile in exact mode
           if (p.score_scale_log2 * p.score_scale_log2 / ks * 1.001f >= kExactBound) *reinterpret_cast<volatile int*>(meta + L::kMetaTag) = k + 1;
         }
@@ -663,12 +721,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const int wg = k & 1;                         // TMEM region / barrier set of this tile
       const uint32_t ph = (k >> 1) & 1;
       const uint32_t t_row = t_lane + wg * 256;
-      const uint32_t a_part = smem_u32(smem + L::kOffPart) + (wg * 2 + ph) * kMaxParts * kQRows * 4;      // float [kParts][128 rows] of this tile
+      const uint32_t a_part = smem_u32(smem + L::kOffPart) + grp_id * kMaxParts * kQRows * 4;      // float [kParts][128 rows]: exact-mode row maxima
       const int sp_i = st_i == 0 ? kSlots - 1 : st_i - 1;
       const uint32_t a_meta = a_meta0 + st_i * L::kMetaBytes, a_meta_p = a_meta0 + sp_i * L::kMetaBytes;
       // key column j of the tile: j < BUCKET -> look-back row kTail + j of the previous slot, else main row j - BUCKET
       const uint32_t a_scale_lb = a_meta_p + L::kMetaScale + kTail * 4, a_pos_lb = a_meta_p + L::kMetaPos + kTail * 4;
       const uint32_t a_scale_mn = a_meta + L::kMetaScale - BUCKET * 4, a_pos_mn = a_meta + L::kMetaPos - BUCKET * 4;
+      const uint32_t a_p16_lb = a_meta_p + L::kMetaPos16 + kTail * 2, a_p16_mn = a_meta + L::kMetaPos16 - BUCKET * 2;
       if (m == 0 && part == 0) RTTS_STAMP(2, k, 0);
       // (sleeping waits: 16 polling warps would starve the loader warps they are waiting for of issue slots)
       mbar_wait_relaxed_a(a_full0 + st_i * 8, full_par, 100);      // metadata of this tile (and of its look-back rows) is visible
@@ -682,6 +741,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       int q_limit = p.causal ? (q_enc & ~kPadFlag) : (kPadFlag - 1);
       if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && (q_enc & kPadFlag)) q_limit = -1;   // padded query: all masked
       const bool exact = static_cast<int>(lds32(a_meta + L::kMetaTag)) == k + 1;
+      // packed position mask: the query's limit as an fp16 pair (causal: its own position; otherwise the largest finite value, which
+      // only a padded key's +inf exceeds; a fully masked query: -1)
+      uint32_t q_limit2;
+      {
+        const __half qh = q_limit < 0 ? __float2half_rn(-1.f) : (p.causal ? __int2half_rn(q_limit) : __ushort_as_half(0x7bff));
+        const __half2 q2 = __half2half2(qh);
+        q_limit2 = *reinterpret_cast<const uint32_t*>(&q2);
+      }
+      const bool packed = p.pos16 != 0 && !exact;
       // stabiliser: |q_i| * score_scale * log2(e) = score_scale_log2^2 / key_scale[own row] for both key-norm variants ...
       // (key_scale = score_scale_log2 / |x| up to the norm's epsilon), times (1 + 2^-10) so rounding cannot push a score above it
       const float row_bound = p.score_scale_log2 * p.score_scale_log2 / __uint_as_float(lds32(a_meta + L::kMetaScale + m * 4)) * 1.001f;
@@ -733,6 +801,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
             soft_chunk<true, true, false, true>(r0, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk, &dup);
             tmem_st8(t_p, pk);
             soft_chunk<true, true, false, true>(r1, a_pos + 64, a_scale + 64, neg_m, q_limit, q_enc, mv, sv, sum4, pk, &dup);
+          } else if (packed) {
+            // (everything but the look-back block of a round's first tile, where the own token may sit a second time at an unknown column)
+            const uint32_t a_p16 = (col < BUCKET ? a_p16_lb : a_p16_mn) + col * 2;
+            const int own = col == diag_col ? (m & 31) : -1;        // own column relative to this 32-column block
+            if (own >= 0) {
+              if (need_mask) {
+                soft_chunk_packed<true, true>(r0, a_p16, a_scale, neg_m, q_limit2, own, pk);
+                tmem_st8(t_p, pk);
+                soft_chunk_packed<true, true>(r1, a_p16 + 32, a_scale + 64, neg_m, q_limit2, own - 16, pk);
+              } else {
+                soft_chunk_packed<false, true>(r0, a_p16, a_scale, neg_m, q_limit2, own, pk);
+                tmem_st8(t_p, pk);
+                soft_chunk_packed<false, true>(r1, a_p16 + 32, a_scale + 64, neg_m, q_limit2, own - 16, pk);
+              }
+            } else if (need_mask) {
+              soft_chunk_packed<true, false>(r0, a_p16, a_scale, neg_m, q_limit2, 0, pk);
+              tmem_st8(t_p, pk);
+              soft_chunk_packed<true, false>(r1, a_p16 + 32, a_scale + 64, neg_m, q_limit2, 0, pk);
+            } else {
+              soft_chunk_packed<false, false>(r0, a_p16, a_scale, neg_m, q_limit2, 0, pk);
+              tmem_st8(t_p, pk);
+              soft_chunk_packed<false, false>(r1, a_p16 + 32, a_scale + 64, neg_m, q_limit2, 0, pk);
+            }
           } else if (self_chunk) {
             soft_chunk<true, true, false>(r0, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
             tmem_st8(t_p, pk);
@@ -764,6 +855,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
 #endif
             if (exact) soft_chunk<true, true, true>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
             else if (self_chunk && col < BUCKET) soft_chunk<true, true, false, true>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk, &dup);
+            else if (packed) {
+              const uint32_t a_p16 = (col < BUCKET ? a_p16_lb : a_p16_mn) + col * 2;
+              const int own = BUCKET + m - col;      // own column relative to this chunk (matches only inside 0..15)
+              if (self_chunk && need_mask) soft_chunk_packed<true, true>(r, a_p16, a_scale, neg_m, q_limit2, own, pk);
+              else if (self_chunk) soft_chunk_packed<false, true>(r, a_p16, a_scale, neg_m, q_limit2, own, pk);
+              else if (need_mask) soft_chunk_packed<true, false>(r, a_p16, a_scale, neg_m, q_limit2, 0, pk);
+              else soft_chunk_packed<false, false>(r, a_p16, a_scale, neg_m, q_limit2, 0, pk);
+            }
             else if (self_chunk) soft_chunk<true, true, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
             else if (need_mask) soft_chunk<true, false, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
             else soft_chunk<false, false, false>(r, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
@@ -792,15 +891,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       // only itself (with bound < 60 a visible key cannot underflow: s - bound >= -2*bound > -126): its P row stays zero and the
       // epilogue substitutes the exact result (rp R8 "except when no other targets are available": softmax uniform over the self
       // columns, all of which hold the query's own token, so out = v[own position], lse = self_value + log(#self columns)).
-      const float row_sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      sts32(a_part + (part * kQRows + m) * 4, __float_as_uint(row_sum) | (win0 == 0 ? dup : 0u));
+      // No exchange between the parts of a row and no row sum here: the sum of the bf16 P row comes out of the tensor pipe (P . 1,
+      // issued with PV) and is read by the epilogue.  A row whose terms are all exactly zero sees only itself (with bound < 60 a
+      // visible key cannot underflow: s - bound >= -2*bound > -126): its P row stays zero and the epilogue substitutes the exact
+      // result (rp R8 "except when no other targets are available": softmax uniform over the self columns, all of which hold the
+      // query's own token, so out = v[own position], lse = self_value + log(#self columns)); `dup` tells it about a second self column.
+      if (round_start && win0 == 0 && dup != 0) sts32(smem_u32(smem + L::kOffDup) + ((wg * 2 + ph) * kQRows + m) * 4, dup);
       if (part == 0) {
-        // (buffers are per (tile parity, phase): tile k+4 writes the same ones, and its S is issued only after PV(k+2) has waited
-        // for epilogue(k))
+        // (buffers are per (tile parity, phase): tile k+4 writes the same ones, and its S is issued only after epilogue(k+2) - hence
+        // epilogue(k) - has signalled o_free)
         const uint32_t a_fin = smem_u32(smem + L::kOffFin) + (wg * 2 + ph) * L::kFinBytes;
         sts32(a_fin + L::kFinMax + m * 4, __float_as_uint(row_max));
         sts32(a_fin + L::kFinSlot + m * 4, static_cast<uint32_t>(base_main + (q_enc & ~kPadFlag)));      // unsorted slot = round * T + position
-        if (m == 0) sts32(a_fin + L::kFinRow, static_cast<uint32_t>(row_bh));
+        if (m == 0) sts128(a_fin + L::kFinRow, make_uint4(static_cast<uint32_t>(row_bh), round_start ? 1u : 0u, 0u, 0u));
       }
       tmem_st_wait();
       tc_fence_before_sync();       // this thread's TMEM reads of S / writes of P precede the MMAs that consume / overwrite the region
@@ -845,6 +948,10 @@ __global__ void __launch_bounds__(256) lsh_merge_fwd_kernel(const __nv_bfloat16*
     acc[4] = fmaf(w, bf16_lo(u.z), acc[4]); acc[5] = fmaf(w, bf16_hi(u.z), acc[5]);
     acc[6] = fmaf(w, bf16_lo(u.w), acc[6]); acc[7] = fmaf(w, bf16_hi(u.w), acc[7]);
   };
+  // Weights as the reference forms them (rp R11 / hf:626-645): probs = exp(lse_r - logsumexp_r lse_r) with the total rounded to
+  // fp32 FIRST.  For a row that sees only itself in every round lse_r = self_value (-5e4 / -1e5, fp32 spacing 4e-3 / 8e-3), the
+  // rounded total is off by up to half a spacing and the reference's weights then sum to 1 +- 4e-3: reproduced, not "fixed".
+  float tot;
   if (RC > 0) {
     float lv[RC > 0 ? RC : 1];
     uint4 ov[RC > 0 ? RC : 1];
@@ -855,18 +962,15 @@ __global__ void __launch_bounds__(256) lsh_merge_fwd_kernel(const __nv_bfloat16*
 #pragma unroll
     for (int r = 0; r < RC; ++r) mx = fmaxf(mx, lv[r]);
 #pragma unroll
-    for (int r = 0; r < RC; ++r) {
-      lv[r] = __expf(lv[r] - mx);
-      den += lv[r];
-    }
-    const float inv_den = 1.f / den;
+    for (int r = 0; r < RC; ++r) den += __expf(lv[r] - mx);
+    tot = mx + __logf(den);
 #pragma unroll
-    for (int r = 0; r < RC; ++r) add_row(lv[r] * inv_den, ov[r]);
+    for (int r = 0; r < RC; ++r) add_row(__expf(lv[r] - tot), ov[r]);
   } else {
     for (int r = 0; r < R; ++r) mx = fmaxf(mx, l[static_cast<int64_t>(r) * T]);
     for (int r = 0; r < R; ++r) den += __expf(l[static_cast<int64_t>(r) * T] - mx);
-    const float inv_den = 1.f / den;
-    for (int r = 0; r < R; ++r) add_row(__expf(l[static_cast<int64_t>(r) * T] - mx) * inv_den, __ldg(o + r * o_step));
+    tot = mx + __logf(den);
+    for (int r = 0; r < R; ++r) add_row(__expf(l[static_cast<int64_t>(r) * T] - tot), __ldg(o + r * o_step));
   }
   const int64_t b = bh / H;
   const int h = static_cast<int>(bh - b * H);
@@ -874,7 +978,7 @@ __global__ void __launch_bounds__(256) lsh_merge_fwd_kernel(const __nv_bfloat16*
   u.x = pack_bf16(acc[0], acc[1]); u.y = pack_bf16(acc[2], acc[3]);
   u.z = pack_bf16(acc[4], acc[5]); u.w = pack_bf16(acc[6], acc[7]);
   reinterpret_cast<uint4*>(out + (b * T + t) * ld_out + h * kDh)[c] = u;
-  if (c == 0) lse[row] = mx + __logf(den);
+  if (c == 0) lse[row] = tot;
 }
 
 static long long* g_fwd_trace = nullptr;   // debug only (rtts_debug_set_fwd_trace)
@@ -924,6 +1028,7 @@ extern "C" int rtts_lsh_attn_fwd(const void* qk, const void* v, int64_t ld, cons
   p.mask_value_log2 = fmaxf(spec->mask_value * kLog2e, -3.0e38f);
   p.self_value_log2 = spec->self_value * kLog2e;
   p.key_norm = spec->key_norm; p.mask_mode = spec->mask_mode; p.causal = spec->causal;
+  p.pos16 = T <= 2048;       // integers up to 2048 are exact in fp16
   const int64_t ctas = static_cast<int64_t>(B) * H * p.tiles_per_row;
   RTTS_REQUIRE(ctas > 0 && ctas < (1ll << 31), "rtts_lsh_attn_fwd: bad grid");
   cudaStream_t s = static_cast<cudaStream_t>(stream);

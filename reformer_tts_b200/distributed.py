@@ -23,6 +23,7 @@ import torch.distributed as dist
 from torch import nn
 
 from .model.reversible import ReversibleSequence
+from .residual import register_grad_storage
 
 _ALIGN = 64      # elements (256 B): every bucket starts on a 256-byte boundary
 
@@ -61,6 +62,7 @@ class GradientBuckets:
             total = (total + _ALIGN - 1) // _ALIGN * _ALIGN
             bounds.append((start, total))
         self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        register_grad_storage(self.flat)      # the fused layers' weight-gradient kernels accumulate into it directly (residual.grad_sink)
         self.bounds = bounds
         for g, (start, _) in zip(groups, bounds):
             off = start

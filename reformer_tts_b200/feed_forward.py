@@ -26,6 +26,7 @@ class _LNFeedForwardFn(torch.autograd.Function):
         hid = ops.gemm(xn, w1_bf16, bias=b1, relu=True, out_dtype=torch.bfloat16)
         y = ops.gemm(hid, w2_bf16, bias=b2, resid=resid, resid_sub=resid_sub)
         ctx.has_ln = ln_w is not None
+        ctx.params = (ln_w, ln_b, w1, b1, w2, b2)
         ctx.save_for_backward(x2, ln_w, mean, rstd, xn, hid, w1_bf16, w2_bf16)
         return y.view(shape)
 
@@ -36,24 +37,36 @@ class _LNFeedForwardFn(torch.autograd.Function):
         f = hid.shape[1]
         dev = x2.device
         sk = _split_k(rows, (d // 128) * (f // 128))
-        g_b2 = torch.zeros(d, dtype=torch.float32, device=dev)
+        p_lnw, p_lnb, p_w1, p_b1, p_w2, p_b2 = ctx.params
+        ctx.params = None
+
+        def target(shape, param):
+            """The parameter's own .grad inside the flat gradient buffer (the Function then returns None for it), else a zero-filled
+            temporary that autograd adds (reformer_tts_b200.residual.grad_sink)."""
+            sink = ops.grad_sink(param)
+            return (sink, True) if sink is not None else (torch.zeros(shape, dtype=torch.float32, device=dev), False)
+
+        g_b2, s_b2 = target((d,), p_b2)
         dyb = ops.cast_bf16_colsum(dy.reshape(rows, d), g_b2)
-        g_w2 = torch.zeros((d, f), dtype=torch.float32, device=dev)
+        g_w2, s_w2 = target((d, f), p_w2)
         ops.gemm(dyb, hid, a_mn_major=True, b_mn_major=True, out=g_w2, accumulate=True, split_k=sk)
-        g_b1 = torch.zeros(f, dtype=torch.float32, device=dev)
+        g_b1, s_b1 = target((f,), p_b1)
         # dh = (dy W2) * 1[h > 0]; W2 is [d, f] = [K, N] row-major -> MN-major B, no transposed copy
         dh = ops.gemm(dyb, w2_bf16, b_mn_major=True, gate=hid, colsum=g_b1, out_dtype=torch.bfloat16)
-        g_w1 = torch.zeros((f, d), dtype=torch.float32, device=dev)
+        g_w1, s_w1 = target((f, d), p_w1)
         ops.gemm(dh, xn, a_mn_major=True, b_mn_major=True, out=g_w1, accumulate=True, split_k=sk)
         dxn = ops.gemm(dh, w1_bf16, b_mn_major=True)
         g_lnw = g_lnb = None
+        s_g = s_bt = False
         if ctx.has_ln:
-            g_lnw = torch.zeros(d, dtype=torch.float32, device=dev)
-            g_lnb = torch.zeros(d, dtype=torch.float32, device=dev)
+            g_lnw, s_g = target((d,), p_lnw)
+            g_lnb, s_bt = target((d,), p_lnb)
             dx = ops.layernorm_bwd(dxn, x2, ln_w, mean, rstd, g_lnw, g_lnb, accumulate_request=True)
         else:
             dx = dxn
-        return dx.view(dy.shape), g_lnw, g_lnb, g_w1, g_b1, g_w2, g_b2, None, None, None
+        drop = lambda g, sunk: None if sunk else g
+        return (dx.view(dy.shape), drop(g_lnw, s_g), drop(g_lnb, s_bt), drop(g_w1, s_w1), drop(g_b1, s_b1), drop(g_w2, s_w2), drop(g_b2, s_b2),
+                None, None, None)
 
 
 def ln_feed_forward(x, norm, lin1, lin2, cache1, cache2):

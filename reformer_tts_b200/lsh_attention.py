@@ -73,6 +73,7 @@ class _LSHAttentionFn(torch.autograd.Function):
             y = out.float()
         ctx.cfg = cfg
         ctx.has_ln, ctx.has_out = ln_w is not None, wout_bf16 is not None
+        ctx.params = (ln_w, ln_b, w_qk, w_v, w_out, b_out)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, sticker, undo, out, lse, mask_u8, wqkv_bf16, wout_bf16, sumsq)
         cfg["_last_buckets"] = buckets
         return y
@@ -85,14 +86,24 @@ class _LSHAttentionFn(torch.autograd.Function):
         h, r, bucket, spec = cfg["heads"], cfg["n_hashes"], cfg["bucket_size"], cfg["spec"]
         dev = x.device
         dy2 = dy.reshape(b * t, d)
+        p_lnw, p_lnb, p_wqk, p_wv, p_wout, p_bout = ctx.params
+        ctx.params = None
+
+        def target(shape, *params):
+            """Where a parameter gradient is accumulated: the parameters' own .grad inside the flat gradient buffer (then the
+            Function returns None for them) or a zero-filled temporary that autograd adds."""
+            sink = ops.grad_sink(*params)
+            return (sink, True) if sink is not None else (torch.zeros(shape, dtype=torch.float32, device=dev), False)
+
         g_wout = g_bout = None
         if ctx.has_out:
-            g_bout = torch.zeros(d, dtype=torch.float32, device=dev)
+            g_bout, sunk_b = target((d,), p_bout)
             keep = cfg.get("keep_mask")       # the forward's dropout mask: d(dropout(z)) = keep * scale * dy
             dyb = ops.cast_bf16_colsum(dy2, g_bout, keep_mask=None if keep is None else keep.view(b * t, d), keep_scale=cfg.get("keep_scale", 1.0))
-            g_wout = torch.zeros((d, d), dtype=torch.float32, device=dev)
+            g_wout, sunk_w = target((d, d), p_wout)
             ops.gemm(dyb, out.view(b * t, d), a_mn_major=True, b_mn_major=True, out=g_wout, accumulate=True, split_k=_split_k(b * t, (d // 128) ** 2))
             dout = ops.gemm(dyb, wout_bf16, b_mn_major=True, out_dtype=torch.bfloat16).view(b, t, d)
+            g_bout, g_wout = (None if sunk_b else g_bout), (None if sunk_w else g_wout)
         else:
             dout = ops.cast_bf16_colsum(dy2).view(b, t, d)
         delta = ops.lsh_delta(dout, out, h)
@@ -100,17 +111,19 @@ class _LSHAttentionFn(torch.autograd.Function):
         dqkv = torch.empty((b, t, 2 * d), dtype=torch.bfloat16, device=dev)
         ops.lsh_attn_bwd(qk, v, sticker, undo, mask_u8, spec, dout, lse, delta, h, r, bucket, out_dqk=dqkv[..., :d], out_dv=dqkv[..., d:], sumsq=sumsq)
         dqkv2 = dqkv.view(b * t, 2 * d)
-        g_wqkv = torch.zeros((2 * d, d), dtype=torch.float32, device=dev)
+        g_wqkv, sunk_qkv = target((2 * d, d), p_wqk, p_wv)
         ops.gemm(dqkv2, xn, a_mn_major=True, b_mn_major=True, out=g_wqkv, accumulate=True, split_k=_split_k(b * t, 2 * (d // 128) ** 2))
+        g_wqk, g_wv = (None, None) if sunk_qkv else (g_wqkv[:d], g_wqkv[d:])
         dxn = ops.gemm(dqkv2, wqkv_bf16, b_mn_major=True)
         g_lnw = g_lnb = None
         if ctx.has_ln:
-            g_lnw = torch.zeros(d, dtype=torch.float32, device=dev)
-            g_lnb = torch.zeros(d, dtype=torch.float32, device=dev)
+            g_lnw, sunk_g = target((d,), p_lnw)
+            g_lnb, sunk_bt = target((d,), p_lnb)
             dx = ops.layernorm_bwd(dxn, x.reshape(b * t, d), ln_w, mean, rstd, g_lnw, g_lnb, accumulate_request=True).view(b, t, d)
+            g_lnw, g_lnb = (None if sunk_g else g_lnw), (None if sunk_bt else g_lnb)
         else:
             dx = dxn.view(b, t, d)
-        return dx, g_lnw, g_lnb, g_wqkv[:d], g_wqkv[d:], g_wout, g_bout, None, None, None, None, None
+        return dx, g_lnw, g_lnb, g_wqk, g_wv, g_wout, g_bout, None, None, None, None, None
 
 
 def _split_k(tokens: int, out_tiles: int = 64) -> int:

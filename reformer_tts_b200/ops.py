@@ -15,7 +15,7 @@ from . import _lib
 
 KEYNORM_L2, KEYNORM_RMS = 0, 1
 MASK_QUERY_AND_KEY, MASK_KEY_ONLY = 0, 1
-from .residual import GradAccumRequest, ResidualRequest  # noqa: F401  (re-exported: layers call ops.ResidualRequest.take)
+from .residual import GradAccumRequest, ResidualRequest, grad_sink  # noqa: F401  (re-exported: layers call ops.ResidualRequest.take)
 
 EPI_BIAS, EPI_RELU, EPI_GATE, EPI_OUT_BF16, EPI_ATOMIC, EPI_COLSUM, EPI_RESID_ADD, EPI_RESID_SUB = 1, 2, 4, 8, 16, 32, 64, 128
 

@@ -1,4 +1,6 @@
-"""The reversible residual offered to a sub-network's last GEMM epilogue (no kernels here: importable without the CUDA library)."""
+"""Hand-offs between the reversible blocks / the trainer and the fused layers (no kernels here: importable without the CUDA
+library): the reversible residual offered to a sub-network's last GEMM epilogue, the gradient accumulation offered to its
+LayerNorm-backward kernel, and the flat gradient buffer the weight-gradient kernels accumulate into directly."""
 from __future__ import annotations
 
 from typing import Optional
@@ -67,3 +69,35 @@ class GradAccumRequest:
             return None
         req.consumed = True
         return b
+
+
+# Storages of the flat gradient buffers (distributed.GradientBuckets) whose views are the parameters' ``.grad``.
+_SINK_STORAGES = set()
+
+
+def register_grad_storage(flat: torch.Tensor) -> None:
+    _SINK_STORAGES.add(flat.untyped_storage().data_ptr())
+
+
+def grad_sink(*params) -> Optional[torch.Tensor]:
+    """The ``.grad`` buffers of ``params`` as ONE fp32 tensor (rows stacked along dim 0) when they are views of a registered flat
+    gradient buffer lying back to back in it (GradientBuckets lays a block's parameters out in declaration order), else None.
+    A hand-written backward then lets its weight-gradient kernel (split-K ``red.global.add``, column-sum atomics) accumulate
+    straight into the buffer and returns ``None`` for those inputs: no zero-filled temporary, no separate ``grad += `` pass."""
+    grads = []
+    for p in params:
+        g = getattr(p, "grad", None)
+        if (g is None or g.dtype != torch.float32 or not g.is_contiguous()
+                or g.untyped_storage().data_ptr() not in _SINK_STORAGES):
+            return None
+        grads.append(g)
+    first = grads[0]
+    if len(grads) == 1:
+        return first
+    offset = first.storage_offset()
+    for g in grads:
+        if g.storage_offset() != offset or g.shape[1:] != first.shape[1:] or g.device != first.device:
+            return None
+        offset += g.numel()
+    rows = sum(g.shape[0] for g in grads)
+    return torch.as_strided(first, (rows,) + tuple(first.shape[1:]), first.stride(), first.storage_offset())

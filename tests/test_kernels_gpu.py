@@ -110,12 +110,17 @@ def test_attention_forward_and_merge(ops, core, rnd, bucket, impl, causal, pad):
     mk = None if c["mask"] is None else c["mask"].to(torch.uint8).to(DEV)
     o, lse = ops.lsh_attn_fwd(c["qk"], c["v"], sticker.to(torch.int32).to(DEV).view(B, H, R * T), mk, _gpu_spec(ops, c), H, R, bucket)
     assert report("o_rounds", o.view(B * H, R, T, 64), want["o_rounds"], o_x) <= TOL
-    # lse is fp32: absolute 1e-4, except rows whose only target is themselves (lse = self_value ~ -5e4: one fp32 ulp = 4e-3)
-    assert ((lse.cpu().view(B * H, R, T) - lse_ref).abs() <= 1e-4 + 2e-7 * lse_ref.abs()).all()
+    # lse is fp32: absolute 1e-4 against the rounded oracle (the kernel's normaliser is the sum of the bf16 P row, which the exact
+    # oracle's differs from by up to 2^-9 relative on a peaked row: printed), except rows whose only target is themselves
+    # (lse = self_value ~ -5e4: one fp32 ulp = 4e-3)
+    got_lse = lse.cpu().view(B * H, R, T)
+    print(f"[parity] lse_rounds: max abs vs rounded oracle {(got_lse - want['lse_rounds']).abs().max():.2e}, vs exact fp32 oracle "
+          f"{(got_lse - lse_ref)[lse_ref > -1e4].abs().max():.2e}")
+    assert ((got_lse - want["lse_rounds"]).abs() <= 1e-4 + 2e-7 * lse_ref.abs()).all()
+    assert ((got_lse - lse_ref).abs() <= 4e-3 + 2e-7 * lse_ref.abs()).all()
     out, lse_tot = ops.lsh_merge_fwd(o, lse)
     assert report("merged out", to_bh(out, H), want["out"], out_x) <= TOL
-    want_tot = torch.logsumexp(lse_ref, 1)
-    assert ((lse_tot.cpu().view(B * H, T) - want_tot).abs() <= 1e-4 + 2e-7 * want_tot.abs()).all()
+    assert ((lse_tot.cpu().view(B * H, T) - want["lse"]).abs() <= 1e-4 + 2e-7 * want["lse"].abs()).all()
 
 
 @pytest.mark.parametrize("bucket", [64, 128])
@@ -255,7 +260,7 @@ def test_attention_full_size_with_heavy_padding(ops, core, rnd, causal):
     out_ref, o_ref, lse_ref = core.unsort_and_merge(so, slse, ud, R)
     want = rnd.forward(to_bh(q1, 1), to_bh(v1, 1), st, ud, bucket, R, core.LSHSpec.reformer_pytorch(64, causal), mask[b:b + 1].bool().cpu())
     assert report("full-size o_rounds slice", o1[b, h], want["o_rounds"][0], o_ref[0]) <= TOL
-    assert ((l1[b, h].cpu() - lse_ref[0]).abs() <= 1e-4 + 2e-7 * lse_ref[0].abs()).all()
+    assert ((l1[b, h].cpu() - want["lse_rounds"][0]).abs() <= 1e-4 + 2e-7 * lse_ref[0].abs()).all()
 
 
 @pytest.mark.parametrize("name,B,T,H,R,bucket,causal,pad,impl", [

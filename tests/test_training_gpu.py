@@ -70,8 +70,11 @@ def test_graph_replay_equals_eager_steps_with_dropout_and_changing_batches():
         b = _batch(2, 100 + i)
         lg, le = graph.step(b), eager.step(b)
         assert abs(lg.item() - le.item()) <= 1e-4 * abs(le.item()), (i, lg.item(), le.item())
+    # Parameters after three AdamW updates.  Split-K weight gradients are summed with atomics (bits differ run to run) and Adam's
+    # m / sqrt(v) turns a last-bit difference of a near-zero gradient into a full-size step of that element: 1e-3 of the parameter
+    # norm, against O(1) if the recompute had seen other rotations / masks than the forward.
     for (k, a), c in zip(model_g.named_parameters(), model_e.parameters()):
-        assert rel_l2(a, c) <= 1e-4, k       # split-K weight gradients are summed with atomics: bits differ run to run, values do not
+        assert rel_l2(a, c) <= 1e-3, k
     # the reference's warm-up reaches the replayed graph: a zero rate leaves the weights alone, the next rate moves them
     w = {k: v.detach().clone() for k, v in model_g.named_parameters()}
     set_lr(opt_g, 0.0)
@@ -110,7 +113,7 @@ def test_three_accumulated_micro_batches_equal_one_batch_of_three_times_the_size
     assert abs(sum(losses) / 3 - big_loss) <= 1e-4 * abs(big_loss)
     assert rel_l2(acc.grad_norm, one.grad_norm) <= 1e-3
     for (k, a), c in zip(model_a.named_parameters(), model_b.parameters()):
-        assert rel_l2(a, c) <= 2e-4, k
+        assert rel_l2(a, c) <= 3e-3, k       # one AdamW step of rate 1e-3 on gradients that agree to bf16-operand level (see above)
 
 
 _DDP_WORKER = r"""
