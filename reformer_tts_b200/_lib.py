@@ -6,10 +6,12 @@ Build it with ``python reformer_tts_b200/csrc/build.py`` (or ``__graft_entry__.b
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libreformer_b200.so"
+# RTTS_LIB: experiment / trace builds of the same sources (tools/ only; the product and the tests load the in-tree library)
+LIB_PATH = Path(os.environ.get("RTTS_LIB") or Path(__file__).resolve().parent / "libreformer_b200.so")
 
 
 class LSHSpecStruct(ctypes.Structure):

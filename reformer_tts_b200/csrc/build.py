@@ -9,7 +9,8 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
-LIB = HERE.parent / "libreformer_b200.so"
+LIB = HERE.parent / (os.environ.get("RTTS_LIB_NAME") or "libreformer_b200.so")      # RTTS_LIB_NAME + RTTS_DEFS: experiment builds beside the product library
+OBJ_DIR = HERE / ("build" if not os.environ.get("RTTS_LIB_NAME") else "build_" + os.environ["RTTS_LIB_NAME"].replace(".so", ""))
 SOURCES = ["api.cu", "lsh_bucket.cu", "lsh_hash_tc.cu", "lsh_attn_fwd.cu", "lsh_attn_bwd.cu", "gemm.cu", "rowwise.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",
@@ -40,13 +41,13 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     objs = []
     procs = []
     build_id = source_hash()
-    id_file = HERE / "build" / "build_id.txt"
+    id_file = OBJ_DIR / "build_id.txt"
     id_changed = not id_file.exists() or id_file.read_text() != build_id
     for name in SOURCES:
         src = HERE / name
         if not src.exists():
             continue
-        obj = HERE / "build" / (name + ".o")
+        obj = OBJ_DIR / (name + ".o")
         obj.parent.mkdir(exist_ok=True)
         objs.append(obj)
         if force or _stale(obj, src) or (name == "api.cu" and id_changed):

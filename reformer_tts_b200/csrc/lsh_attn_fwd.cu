@@ -110,8 +110,9 @@ struct AttnFwdSmem {
   static constexpr int kSlotBytes = 2 * kTileBytes;
   static constexpr int kOffOnes = kSlots * kSlotBytes;               // 8 rows x 128 B of bf16 1.0 (1024-B aligned): B operand of the row-sum MMA (P . 1)
   static constexpr int kOffMeta = kOffOnes + 1024;                   // per slot: float scale[128], int pos[128], int exact_tag (+pad), half pos16[128]
-  static constexpr int kMetaScale = 0, kMetaPos = kQRows * 4, kMetaTag = 2 * kQRows * 4;
-  static constexpr int kMetaGeo = kMetaTag + 16;                     // int4 {row_bh, base_main (round * T), round_start, -}: written by the loader
+  static constexpr int kMetaScale = 0, kMetaPos = kQRows * 4;
+  static constexpr int kMetaGeo = 2 * kQRows * 4;                    // one 16-byte record {row_bh, base_main (round * T), round_start, exact tag}
+  static constexpr int kMetaTag = kMetaGeo + 12;                     // (the first three words by loader thread 0, the tag by whichever thread sees a large bound)
   static constexpr int kMetaPos16 = 2 * kQRows * 4 + 32;             // fp16 position per row (+inf for a padded token): packed position mask
   static constexpr int kMetaBytes = 2 * kQRows * 4 + 32 + kQRows * 2;
   static constexpr int kOffPart = kOffMeta + kSlots * kMetaBytes;    // float[2 softmax groups][kParts][128 rows]: row maxima of the exact two-pass mode (exchange inside one tile)
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int RT = p.R * p.T;
+  const uint32_t sbase = smem_u32(smem);       // shared-window address of the dynamic segment, computed once (per-tile code adds offsets)
 #ifdef RTTS_TRACE
   const long long t_cta0 = clock64();
 #endif
@@ -418,16 +420,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
     const int m = tid - kFirstEpiWarp * 32;         // query row = TMEM lane (warp % 4 selects the lane quarter)
     const int lane = tid & 31;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const uint32_t a_stage = smem_u32(smem + L::kOffStage) + (warp & 3) * 4096;      // this warp's 32 rows x 128 B
+    const uint32_t a_stage = sbase + L::kOffStage + (warp & 3) * 4096;      // this warp's 32 rows x 128 B
     for (int k = 0; k < my_tiles; ++k) {
       const int g = k & 1;
       const uint32_t ph = (k >> 1) & 1;
-      const uint32_t a_fin = smem_u32(smem + L::kOffFin) + (g * 2 + ph) * L::kFinBytes;
+      const uint32_t a_fin = sbase + L::kOffFin + (g * 2 + ph) * L::kFinBytes;
       // Only o_full is waited for.  PV(k) is issued after p_full(k), so o_full(k) implies that the softmax group's partial sums and
       // slots are in shared memory; and p_full must NOT be waited on here: p_full(k+2) needs only PV(k) (not this role), so with a
       // slow epilogue the barrier can run two phases ahead of a waiter, whose parity test would then never pass.  o_full cannot:
       // PV(k+2) waits for this role's o_free(k).
-      mbar_wait_relaxed(o_full + g, ph, 40);
+      if (lane == 0) mbar_wait_relaxed(o_full + g, ph, 40);      // one polling lane per warp
+      __syncwarp();
       tc_fence_after_sync();
       uint32_t rs;
       tmem_ld1(t_lane + g * 256 + kColSum, &rs);                   // row sum of the (bf16) P row, from the tensor pipe
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const int row_bh = static_cast<int>(fin.x);
       uint32_t dup = 0;
       if (fin.y != 0) {                                           // only there can the own token sit in the look-back chunk a second time
-        const uint32_t a_dup = smem_u32(smem + L::kOffDup) + ((g * 2 + ph) * kQRows + m) * 4;
+        const uint32_t a_dup = sbase + L::kOffDup + ((g * 2 + ph) * kQRows + m) * 4;
         dup = lds32(a_dup);
         if (dup != 0) sts32(a_dup, 0u);                          // (this role owns the row's flag once o_full has fired)
       }
@@ -668,7 +671,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           // a query whose score bound could push a visible key below the exp2 underflow: the pair runs this tile in exact mode
           if (p.score_scale_log2 * p.score_scale_log2 / ks * 1.001f >= kExactBound) *reinterpret_cast<volatile int*>(meta + L::kMetaTag) = k + 1;
         }
-        if (lt == 0) *reinterpret_cast<int4*>(meta + L::kMetaGeo) = make_int4(row_bh, x_cur.round * p.T, x_cur.t_round == 0, 0);
+        if (lt == 0) {
+          *reinterpret_cast<int2*>(meta + L::kMetaGeo) = make_int2(row_bh, x_cur.round * p.T);
+          *reinterpret_cast<int*>(meta + L::kMetaGeo + 8) = x_cur.t_round == 0;
+        }
       }
       if (pending >= 0) {
         cp_async_wait<1>();         // everything but the group just committed has landed
@@ -714,14 +720,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
     const int diag_col = BUCKET + (m & ~31);
     // Every instruction of this per-tile prologue is executed by 16 warps (the kernel is bound by instruction issue), so the ring
     // position is carried incrementally instead of being re-derived from k (k % 6, k / 6 are multiply-high sequences).
-    const uint32_t a_meta0 = smem_u32(smem + L::kOffMeta), a_full0 = smem_u32(full);
+    const uint32_t a_meta0 = sbase + L::kOffMeta, a_sfull = sbase + L::kOffBar + 2 * kSlots * 8;
+    const float bound_c = p.score_scale_log2 * p.score_scale_log2 * 1.001f;
     int st_i = grp_id % kSlots;                     // ring slot of tile k
-    uint32_t full_par = 0;                          // (k / kSlots) & 1
     for (int k = grp_id; k < my_tiles; k += kGroups) {
       const int wg = k & 1;                         // TMEM region / barrier set of this tile
       const uint32_t ph = (k >> 1) & 1;
       const uint32_t t_row = t_lane + wg * 256;
-      const uint32_t a_part = smem_u32(smem + L::kOffPart) + grp_id * kMaxParts * kQRows * 4;      // float [kParts][128 rows]: exact-mode row maxima
+      const uint32_t a_part = sbase + L::kOffPart + grp_id * kMaxParts * kQRows * 4;      // float [kParts][128 rows]: exact-mode row maxima
       const int sp_i = st_i == 0 ? kSlots - 1 : st_i - 1;
       const uint32_t a_meta = a_meta0 + st_i * L::kMetaBytes, a_meta_p = a_meta0 + sp_i * L::kMetaBytes;
       // key column j of the tile: j < BUCKET -> look-back row kTail + j of the previous slot, else main row j - BUCKET
@@ -729,18 +735,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const uint32_t a_scale_mn = a_meta + L::kMetaScale - BUCKET * 4, a_pos_mn = a_meta + L::kMetaPos - BUCKET * 4;
       const uint32_t a_p16_lb = a_meta_p + L::kMetaPos16 + kTail * 2, a_p16_mn = a_meta + L::kMetaPos16 - BUCKET * 2;
       if (m == 0 && part == 0) RTTS_STAMP(2, k, 0);
-      // (sleeping waits: 16 polling warps would starve the loader warps they are waiting for of issue slots)
-      mbar_wait_relaxed_a(a_full0 + st_i * 8, full_par, 100);      // metadata of this tile (and of its look-back rows) is visible
-      if (m == 0 && part == 0) RTTS_STAMP(2, k, 3);
       st_i += kGroups;                              // (for the next tile)
-      if (st_i >= kSlots) { st_i -= kSlots; full_par ^= 1u; }
+      if (st_i >= kSlots) st_i -= kSlots;
+      // ONE wait per tile, by one lane: S(k) was issued after the MMA thread had seen full[slot], so its completion also certifies
+      // the loader's metadata (written long before); 16 warps x 32 lanes polling one barrier word serialise in the barrier unit.
+      // (sleeping wait: polling warps would take issue slots from the loader warps)
+      if ((tid & 31) == 0) mbar_wait_relaxed_a(a_sfull + wg * 8, ph, 40);
+      __syncwarp();
+      tc_fence_after_sync();
+      if (m == 0 && part == 0) RTTS_STAMP(2, k, 3);
       const uint4 geo = lds128(a_meta + L::kMetaGeo);
       const int row_bh = static_cast<int>(geo.x), base_main = static_cast<int>(geo.y);
       const bool round_start = geo.z != 0;
+      const bool exact = static_cast<int>(geo.w) == k + 1;
       const int q_enc = static_cast<int>(lds32(a_meta + L::kMetaPos + m * 4));
       int q_limit = p.causal ? (q_enc & ~kPadFlag) : (kPadFlag - 1);
       if (p.mask_mode == RTTS_MASK_QUERY_AND_KEY && (q_enc & kPadFlag)) q_limit = -1;   // padded query: all masked
-      const bool exact = static_cast<int>(lds32(a_meta + L::kMetaTag)) == k + 1;
       // packed position mask: the query's limit as an fp16 pair (causal: its own position; otherwise the largest finite value, which
       // only a padded key's +inf exceeds; a fully masked query: -1)
       uint32_t q_limit2;
@@ -752,9 +762,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       const bool packed = p.pos16 != 0 && !exact;
       // stabiliser: |q_i| * score_scale * log2(e) = score_scale_log2^2 / key_scale[own row] for both key-norm variants ...
       // (key_scale = score_scale_log2 / |x| up to the norm's epsilon), times (1 + 2^-10) so rounding cannot push a score above it
-      const float row_bound = p.score_scale_log2 * p.score_scale_log2 / __uint_as_float(lds32(a_meta + L::kMetaScale + m * 4)) * 1.001f;
-      mbar_wait_relaxed(s_full + wg, ph, 40);
-      tc_fence_after_sync();
+      const float row_bound = __fdividef(bound_c, __uint_as_float(lds32(a_meta + L::kMetaScale + m * 4)));
       if (m == 0 && part == 0) RTTS_STAMP(2, k, 1);
 
       float row_max = row_bound;
@@ -793,6 +801,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
           const bool self_chunk = col == diag_col || (round_start && col < BUCKET);
           const uint32_t t_p = t_row + p_col<BUCKET>(col >> 5);
           tmem_ld_wait();
+          if (m == 0 && part == 0) RTTS_STAMP(2, k, 4);
           if (exact) {
             soft_chunk<true, true, true>(r0, a_pos, a_scale, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
             tmem_st8(t_p, pk);
@@ -837,6 +846,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
             tmem_st8(t_p, pk);
             soft_chunk<false, false, false>(r1, a_pos + 64, a_scale + 64, neg_m, q_limit, q_enc, mv, sv, sum4, pk);
           }
+          if (m == 0 && part == 0) RTTS_STAMP(2, k, 5);
           tmem_st8(t_p + 8, pk);        // P over S columns this thread has already consumed
         } else {
 #pragma unroll 1
@@ -896,19 +906,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lsh_attn_fwd_kernel(const Attn
       // visible key cannot underflow: s - bound >= -2*bound > -126): its P row stays zero and the epilogue substitutes the exact
       // result (rp R8 "except when no other targets are available": softmax uniform over the self columns, all of which hold the
       // query's own token, so out = v[own position], lse = self_value + log(#self columns)); `dup` tells it about a second self column.
-      if (round_start && win0 == 0 && dup != 0) sts32(smem_u32(smem + L::kOffDup) + ((wg * 2 + ph) * kQRows + m) * 4, dup);
+      if (round_start && win0 == 0 && dup != 0) sts32(sbase + L::kOffDup + ((wg * 2 + ph) * kQRows + m) * 4, dup);
       if (part == 0) {
         // (buffers are per (tile parity, phase): tile k+4 writes the same ones, and its S is issued only after epilogue(k+2) - hence
         // epilogue(k) - has signalled o_free)
-        const uint32_t a_fin = smem_u32(smem + L::kOffFin) + (wg * 2 + ph) * L::kFinBytes;
+        const uint32_t a_fin = sbase + L::kOffFin + (wg * 2 + ph) * L::kFinBytes;
         sts32(a_fin + L::kFinMax + m * 4, __float_as_uint(row_max));
         sts32(a_fin + L::kFinSlot + m * 4, static_cast<uint32_t>(base_main + (q_enc & ~kPadFlag)));      // unsorted slot = round * T + position
         if (m == 0) sts128(a_fin + L::kFinRow, make_uint4(static_cast<uint32_t>(row_bh), round_start ? 1u : 0u, 0u, 0u));
       }
+      if (m == 0 && part == 0) RTTS_STAMP(2, k, 6);
       tmem_st_wait();
+      if (m == 0 && part == 0) RTTS_STAMP(2, k, 7);
       tc_fence_before_sync();       // this thread's TMEM reads of S / writes of P precede the MMAs that consume / overwrite the region
       __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(p_full + wg);
+      if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_sfull + (2 + wg) * 8) : "memory");      // p_full[wg]
       if (m == 0 && part == 0) RTTS_STAMP(2, k, 2);
     }
   }

@@ -86,7 +86,7 @@ class TrainStep:
 
     def __init__(self, model: nn.Module, loss_fn: nn.Module, optimizer: torch.optim.Optimizer, example_batch: Dict[str, torch.Tensor],
                  use_cuda_graph: bool = True, averager=None, warmup_steps: int = 3, seed: int = 1234, grad_clip: Optional[float] = None,
-                 accumulate_grad_batches: int = 1, private_rng: Optional[bool] = None):
+                 accumulate_grad_batches: int = 1, private_rng: Optional[bool] = None, keep_grads: bool = False):
         self.model, self.loss_fn, self.optimizer, self.averager = model, loss_fn, optimizer, averager
         self.grad_clip, self.accumulate = grad_clip, int(accumulate_grad_batches)
         assert self.accumulate >= 1
@@ -98,6 +98,8 @@ class TrainStep:
         self.static_loss = self.static_loss_micro = None
         self.graph_error = None
         self.grad_norm: Optional[torch.Tensor] = None                  # global gradient norm of the latest boundary step (before clipping)
+        self.keep_grads = keep_grads                                   # tests: keep a copy of the (averaged, clipped) flat gradient of the latest boundary step
+        self.last_grads: Optional[torch.Tensor] = None
         self.optimizer_steps = 0
         self._micro_index = 0
         self._generators = []
@@ -151,6 +153,10 @@ class TrainStep:
             if self.grad_clip is not None:      # global 2-norm of the AVERAGED gradient: after the all-reduce
                 self.grad_norm = torch.linalg.vector_norm(self.buckets.flat)
                 self.buckets.flat.mul_(clip_coefficient(self.grad_norm, self.grad_clip))
+            if self.keep_grads:
+                if self.last_grads is None:
+                    self.last_grads = torch.empty_like(self.buckets.flat)
+                self.last_grads.copy_(self.buckets.flat)
             self.optimizer.step()
             self.buckets.zero()
         return loss

@@ -407,7 +407,7 @@ def test_weight_gradients_accumulated_straight_into_the_flat_buffer_equal_autogr
     torch.manual_seed(4)
     enc = ReformerEnc(128, **kw["enc_reformer_kwargs"]).to(DEV).train()
     dec = ReformerDec(128, **kw["dec_reformer_kwargs"]).to(DEV).train()
-    x, mem = torch.randn(2, 256, 128, device=DEV), torch.randn(2, 128, 128, device=DEV)
+    x, mem = torch.randn(2, 256, 128, device=DEV, requires_grad=True), torch.randn(2, 128, 128, device=DEV)
     dy = torch.randn(2, 256, 128, device=DEV)
 
     def run():

@@ -24,11 +24,11 @@ lib.rtts_debug_set_fwd_trace(None)
 per_cta = trace.cpu()[4 * 32 * 8:].view(148, 32)
 t = trace.cpu()[:4 * 32 * 8].view(4, 32, 8)
 t0 = int(t[t > 0].min())
-names = {0: ["kv_full ok", "S issued", "p_full ok", "PV issued", "loop top", "o_free ok", "PV mmas out"], 1: ["start", "stk loaded", "kv_free ok", "arrived"], 2: ["start", "s_full ok", "P done", "full ok", "w0 chunks", "fast done", "ld cycles", "w12 chunks"], 3: ["o_full ok", "stored"]}
+names = {0: ["kv_full ok", "S issued", "p_full ok", "PV issued", "loop top", "o_free ok", "PV mmas out"], 1: ["start", "stk loaded", "kv_free ok", "arrived"], 2: ["start", "s_full ok", "P done", "full ok", "S loaded", "chunks done", "fin stored", "P stored"], 3: ["o_full ok", "stored"]}
 for n in range(0, 16):
     print(f"--- tile {n}")
     for role, rn in ((1, "loader"), (0, "mma"), (2, "softmax"), (3, "epilogue")):
-        print(f"  {rn:8s}", "  ".join(f"{nm}={(int(t[role, n, k]) - t0) if nm not in ("ld cycles", "w0 chunks", "w12 chunks") else int(t[role, n, k])}" for k, nm in enumerate(names[role])))
+        print(f"  {rn:8s}", "  ".join(f"{nm}={(int(t[role, n, k]) - t0) if nm not in ("-",) else int(t[role, n, k])}" for k, nm in enumerate(names[role])))
 
 print("per-CTA cycles until role done: softmax(w0) softmax(w8) epilogue(w16) loader(w20) mma(w24)")
 for cta in list(range(0, 148, 12)) + [147]:
