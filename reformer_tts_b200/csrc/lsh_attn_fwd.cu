@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "host_util.h"
+#include "lsh_attn_params.h"
 #include "rtts_b200.h"
 
 namespace rtts {
@@ -30,25 +31,6 @@ constexpr int kDh = 64;
 constexpr int kQRows = 128;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr int kPadFlag = 0x40000000;
-
-struct AttnFwdParams {
-  const __nv_bfloat16* qk;
-  const __nv_bfloat16* v;
-  int64_t ld;
-  const int32_t* sticker;
-  const float* sumsq;   // [B,H,T] |qk row|^2
-  const uint8_t* mask;
-  __nv_bfloat16* o_rounds;
-  float* lse_rounds;
-  long long* trace;     // debug: per-role clock64 stamps of CTA 0 (nullable)
-  int T, H, R;
-  int tiles_per_row;  // R*T / 128
-  float score_scale_log2;  // score_scale * log2(e)
-  float mask_value_log2, self_value_log2;
-  int key_norm, mask_mode, causal;
-  int pos16;          // T <= 2048: positions are exact in fp16, the position mask is evaluated two keys per instruction
-};
 
 // Persistent, warp-specialised pipeline; CTA c owns tiles [c*N/grid, (c+1)*N/grid) of the (row, tile-in-row) order.
 //   warp 24     : TMEM allocation; one elected lane issues every tcgen05.mma  (S(k) as soon as block k lands, then PV(k-1) when P(k-1) is ready)
@@ -994,6 +976,7 @@ __global__ void __launch_bounds__(256) lsh_merge_fwd_kernel(const __nv_bfloat16*
 }
 
 static long long* g_fwd_trace = nullptr;   // debug only (rtts_debug_set_fwd_trace)
+static int g_fwd_tile_kernel = 0;          // debug only (rtts_debug_set_fwd_kernel): 1 = bucket 64 on the tile kernel of this file
 
 template <int BUCKET>
 int launch_attn_fwd(const AttnFwdParams& p, int ctas, cudaStream_t stream) {
@@ -1044,6 +1027,7 @@ extern "C" int rtts_lsh_attn_fwd(const void* qk, const void* v, int64_t ld, cons
   const int64_t ctas = static_cast<int64_t>(B) * H * p.tiles_per_row;
   RTTS_REQUIRE(ctas > 0 && ctas < (1ll << 31), "rtts_lsh_attn_fwd: bad grid");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bucket == 64 && !g_fwd_tile_kernel) return launch_attn_fwd64(p, B, s);      // block-streaming kernel (lsh_attn_fwd64.cu)
   return bucket == 64 ? launch_attn_fwd<64>(p, static_cast<int>(ctas), s) : launch_attn_fwd<128>(p, static_cast<int>(ctas), s);
 }
 
@@ -1069,3 +1053,5 @@ extern "C" int rtts_lsh_merge_fwd(const void* o_rounds, const float* lse_rounds,
 
 // Debug hook (not part of the product ABI): device buffer of 4*32*8 int64 receiving clock64 stamps of CTA 0.
 extern "C" void rtts_debug_set_fwd_trace(void* device_buffer) { g_fwd_trace = static_cast<long long*>(device_buffer); }
+// Debug hook (not part of the product ABI): 1 = run bucket 64 on the 128-query tile kernel (A/B measurements), 0 = default.
+extern "C" void rtts_debug_set_fwd_kernel(int tile_kernel) { g_fwd_tile_kernel = tile_kernel; }
