@@ -18,29 +18,64 @@ from typing import Optional
 
 import torch
 from torch import nn
+import weakref
 
 from . import ops
 from .ops import LSHSpec
 
 
 class _WeightCache:
-    """bf16 copies of fp32 master weights, rebuilt only when a weight's version counter moves.  ``enabled = False`` forces the
-    cast on every call (needed while a CUDA graph is captured: the cast must be part of the graph, weights change on replay)."""
+    """bf16 copies of fp32 master weights in a persistent buffer, rebuilt only when a weight's version counter moves.
+    ``enabled = False`` forces the cast on every call.  ``refresh_all()`` re-casts every known weight of the process with ONE
+    multi-tensor copy (the per-weight cat + cast + copy was ~130 small launches per training step); a training step calls it
+    right after bumping ``epoch`` (inside the captured graph too: a replay updates the weights without running Python)."""
     enabled = True
-    epoch = 0       # bumped at the start of every training step: forces one re-cast per step even when version counters cannot be
-                    # observed (a CUDA-graph replay updates the weights without running Python)
+    epoch = 0       # bumped at the start of every training step: forces one re-cast per step even when version counters cannot be observed
+    _registry = weakref.WeakSet()
 
     def __init__(self):
         self._key = None
         self._val = None
+        self._parts = None
+        self._weights = None
+        _WeightCache._registry.add(self)
+
+    def _make_key(self, weights):
+        return (_WeightCache.epoch,) + tuple((w.data_ptr(), w._version) for w in weights)
+
+    def _ensure_buffer(self, weights):
+        rows = sum(w.shape[0] for w in weights)
+        if (self._val is None or self._val.shape[0] != rows or self._val.shape[1:] != weights[0].shape[1:] or self._val.device != weights[0].device
+                or self._weights is None or len(self._weights) != len(weights) or any(a is not b for a, b in zip(self._weights, weights))):
+            self._val = torch.empty((rows,) + tuple(weights[0].shape[1:]), dtype=torch.bfloat16, device=weights[0].device)
+            self._parts, r = [], 0
+            for w in weights:
+                self._parts.append(self._val[r:r + w.shape[0]])
+                r += w.shape[0]
+            self._weights = tuple(weights)
 
     def get(self, *weights: torch.Tensor) -> torch.Tensor:
-        key = (_WeightCache.epoch,) + tuple((w.data_ptr(), w._version) for w in weights)
+        key = self._make_key(weights)
         if key != self._key or not _WeightCache.enabled:
             with torch.no_grad():
-                self._val = torch.cat([w.detach() for w in weights], dim=0).to(torch.bfloat16).contiguous()
+                self._ensure_buffer(weights)
+                torch._foreach_copy_(self._parts, [w.detach() for w in weights])
             self._key = key
         return self._val
+
+    @classmethod
+    def refresh_all(cls):
+        """Re-cast every weight that has been requested before (one multi-tensor kernel per dtype / device group)."""
+        dst, src = [], []
+        for c in list(cls._registry):
+            if c._weights is None or c._val is None:
+                continue
+            dst += c._parts
+            src += [w.detach() for w in c._weights]
+            c._key = c._make_key(c._weights)
+        if dst:
+            with torch.no_grad():
+                torch._foreach_copy_(dst, src)
 
 
 class _LSHAttentionFn(torch.autograd.Function):

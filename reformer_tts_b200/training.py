@@ -142,7 +142,8 @@ class TrainStep:
         if not self.buckets.attached():
             raise RuntimeError("parameter gradients were detached from the flat buffer (do not call zero_grad(set_to_none=True))")
         if self._weights_changed:
-            _WeightCache.epoch += 1       # bf16 weight copies are rebuilt once per optimiser step (inside the captured graph too)
+            _WeightCache.epoch += 1       # bf16 weight copies are rebuilt once per optimiser step (inside the captured graph too),
+            _WeightCache.refresh_all()    # all of them by one multi-tensor cast
         if self.averager is not None:
             self.averager.sync_enabled = boundary
         loss = loss_of_batch(self.model, self.loss_fn, batch)

@@ -5,7 +5,7 @@ from reformer_tts_b200 import ops, _lib
 lib = _lib.load()
 lib.rtts_debug_set_fwd_kernel.argtypes = [ctypes.c_int]
 dev = "cuda"
-for (B, T, H, R, causal, pad) in [(20, 1024, 8, 8, 1, 0), (20, 1024, 8, 8, 1, 100), (20, 256, 8, 8, 0, 40), (4, 4096, 8, 4, 1, 0)]:
+for (B, T, H, R, causal, pad) in [(20, 1024, 8, 8, 1, 0), (20, 256, 8, 8, 0, 40), (16, 1024, 8, 4, 1, 0), (8, 2048, 8, 4, 1, 0), (4, 4096, 8, 4, 1, 0), (1, 16384, 8, 4, 1, 0), (16, 1024, 8, 4, 0, 0)]:
     torch.manual_seed(0)
     qkv = torch.randn(B, T, 2 * H * 64, device=dev).bfloat16()
     qk, v = qkv[..., :H * 64], qkv[..., H * 64:]

@@ -54,3 +54,24 @@ tot_k = sum(e.self_device_time_total for e in ks)
 print(f"\nkernels only: {tot_k / 1e3:.2f} ms in {sum(e.count for e in ks)} launches")
 for e in sorted(ks, key=lambda e: -e.self_device_time_total)[:45]:
     print(f"  {e.self_device_time_total / 1e3:8.3f} ms {100 * e.self_device_time_total / tot_k:5.1f}%  n={e.count:4d}  {e.key[:110]}")
+
+# where the non-library kernels come from: kernels grouped by (kernel name, innermost frame inside this repository)
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof2:
+    bench.train_step(model, loss_fn, opt, data)
+    torch.cuda.synchronize()
+from collections import defaultdict  # noqa: E402
+agg = defaultdict(lambda: [0, 0.0])
+evs = prof2.events()
+for e in evs:
+    if e.device_type == DeviceType.CUDA or not e.kernels:
+        continue
+    frame = next((f for f in (e.stack or []) if "/repo/" in f and "profile_step" not in f), "(autograd / optimizer)")
+    for k in e.kernels:
+        if "rtts" in k.name or "spin_kernel" in k.name:
+            continue
+        key = (k.name[:60], frame.split("/repo/")[-1][:80])
+        agg[key][0] += 1
+        agg[key][1] += k.duration
+print("\nnon-library kernels by call site:")
+for (kn, fr), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+    print(f"  {t / 1e3:7.3f} ms n={n:4d}  {kn:60s} {fr}")
