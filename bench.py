@@ -307,7 +307,10 @@ def run_ours(args, kwargs, world, rank, local_rank):
         key_fwd, key_bwd = f"lsh_attn_fwd[T={t}]", f"lsh_attn_bwd[T={t}]"
         fwd_ms, bwd_ms = kernel_ms.get(key_fwd, {}).get("avg_ms"), kernel_ms.get(key_bwd, {}).get("avg_ms")
         peak = peaks["bf16_tflops_sustained"]
-        roofline = {"bound": "tensor", "kernel": f"lsh_attn_fwd_kernel<{bucket}> (decoder shape B={b} T={t} H=8 R={r})", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
+        # the forward kernel of the decoder's self-attention: bucket 64 up to T = 2048 runs the block-streaming kernel (lsh_attn_fwd64.cu)
+        kname, ksrc = (("lsh_attn_fwd64_kernel", ["lsh_attn_fwd64.cu", "lsh_attn_params.h", "common.cuh"]) if bucket == 64 and t <= 2048
+                       else (f"lsh_attn_fwd_kernel<{bucket}>", ["lsh_attn_fwd.cu", "lsh_attn_params.h", "common.cuh"]))
+        roofline = {"bound": "tensor", "kernel": f"{kname} (decoder shape B={b} T={t} H=8 R={r})", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
                     "traffic": None, "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)"}
         if fwd_ms:
             roofline["achieved"] = flops_fwd / (fwd_ms * 1e-3) / 1e12
@@ -317,8 +320,7 @@ def run_ours(args, kwargs, world, rank, local_rank):
             roofline["algorithmic_flop_per_launch"] = flops_fwd
             # DRAM bytes of one launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of
             # this kernel at this shape; null when the kernel's sources have changed since that capture.  Algorithmic minimum beside it.
-            roofline["traffic"], roofline["traffic_source"] = ncu_traffic(f"lsh_attn_fwd_kernel<{bucket}>", f"B={b},T={t},H=8,R={r}",
-                                                                         ["lsh_attn_fwd.cu", "common.cuh"])
+            roofline["traffic"], roofline["traffic_source"] = ncu_traffic(kname, f"B={b},T={t},H=8,R={r}", ksrc)
             roofline["algorithmic_min_bytes"] = 2 * b * t * d * 2 + r * b * t * d * 2 + r * b * 8 * t * 4
         if bwd_ms:
             roofline["bwd_kernel"] = {"kernel": f"lsh_attn_bwd_kernel<{bucket}> (decoder shape)", "avg_launch_ms": bwd_ms,

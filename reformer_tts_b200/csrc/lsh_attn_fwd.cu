@@ -1030,7 +1030,8 @@ extern "C" int rtts_lsh_attn_fwd(const void* qk, const void* v, int64_t ld, cons
   // bucket 64: the block-streaming kernel (lsh_attn_fwd64.cu) wherever its packed fp16 position compare applies (T <= 2048: equal
   // to the tile kernel of this file within 1 % at the training shapes, with 2/3 of its tensor work); beyond, its integer-compare
   // path is 5-8 % behind the tile kernel (tools/ab_fwd.py, profiles/README.md), which keeps those lengths
-  if (bucket == 64 && p.pos16 && !g_fwd_tile_kernel) return launch_attn_fwd64(p, B, s);
+  if (bucket == 64 && p.pos16 && g_fwd_tile_kernel == 0) return launch_attn_fwd64p(p, B, s);
+  if (bucket == 64 && p.pos16 && g_fwd_tile_kernel == 2) return launch_attn_fwd64(p, B, s);
   return bucket == 64 ? launch_attn_fwd<64>(p, static_cast<int>(ctas), s) : launch_attn_fwd<128>(p, static_cast<int>(ctas), s);
 }
 

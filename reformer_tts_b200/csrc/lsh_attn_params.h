@@ -27,7 +27,8 @@ struct AttnFwdParams {
   int pos16;          // T <= 2048: positions are exact in fp16, the position mask is evaluated two keys per instruction
 };
 
-// lsh_attn_fwd64.cu
+// lsh_attn_fwd64.cu (block-streaming kernel) / lsh_attn_fwd64p.cu (paired-chunk kernel: the default for bucket 64, T <= 2048)
 int launch_attn_fwd64(const AttnFwdParams& p, int B, cudaStream_t stream);
+int launch_attn_fwd64p(const AttnFwdParams& p, int B, cudaStream_t stream);
 
 }  // namespace rtts
