@@ -41,11 +41,12 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kExactBound = 60.f;
 
 constexpr int kSoftWarps = 8;           // two groups of four (warp & 3 = TMEM lane quarter = SM sub-partition)
-constexpr int kLoaderWarps = 4;
+constexpr int kKLoaders = 4, kVLoaders = 2;      // K loader i takes the entries e = i mod 4, V loader i the entries e = i mod 2
+constexpr int kLoaderWarps = kKLoaders + kVLoaders;
 constexpr int kFirstLoaderWarp = kSoftWarps;
 constexpr int kSWarp = kFirstLoaderWarp + kLoaderWarps;
 constexpr int kPVWarp = kSWarp + 1;
-constexpr int kThreads = (kPVWarp + 1) * 32;      // 448 threads: up to 144 registers each
+constexpr int kThreads = (kPVWarp + 1) * 32;      // 512 threads: up to 128 registers each
 
 constexpr int kSlots = 8;               // ring of gathered chunks (K and V rows), an entry is released by the PV that last reads it
 constexpr int kMetaSlots = 32;          // ring of per-row metadata: an entry is rewritten 32 entries later, which needs the PV of an
@@ -69,13 +70,19 @@ struct Smem {
   static constexpr int kOffStage = kOffMeta + kMetaSlots * kMetaBytes;   // output staging: 32 rows x 128 B (swizzled) per softmax warp
   static constexpr int kStageBytes = 32 * 128;
   static constexpr int kOffBar = kOffStage + kSoftWarps * kStageBytes;
-  static constexpr int kNumBars = 2 * kSlots + 8;
+  static constexpr int kNumBars = 4 * kSlots + 8;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kTotal = kOffTmem + 16;
   static_assert(kOffOnes % 1024 == 0 && kOffMeta % 16 == 0 && kOffStage % 16 == 0 && kOffBar % 8 == 0, "alignment");
   static_assert(kTotal <= 232448, "shared memory budget of one CTA (227 KB)");
 };
 constexpr int kFlagRoundStart = 2, kFlagExact = 4;
+
+#ifdef RTTS_TRACE      // timeline build (tools/trace_fwd64p.py): RTTS_DEFS=-DRTTS_TRACE python reformer_tts_b200/csrc/build.py -f
+#define P_STAMP(role, n, k) do { if (p.trace != nullptr && blockIdx.x == 0 && (n) < 64) p.trace[((role) * 64 + (n)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define P_STAMP(role, n, k) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint2 lds64(uint32_t saddr) {
   uint2 v;
@@ -108,6 +115,18 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) 
 __device__ __forceinline__ void warp_wait(uint32_t bar_addr, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait_a(bar_addr, parity);
   __syncwarp();
+}
+// base + a * b with a 32 x 32 -> 64-bit multiply-add (one IMAD.WIDE): row addresses of the gather and of the scatter-store
+__device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
+  uint64_t d;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void cp_async16_g(uint32_t smem_dst, uint64_t gaddr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gaddr) : "memory");
+}
+__device__ __forceinline__ void stg128(uint64_t gaddr, const uint4& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(gaddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
   asm("{\n"
@@ -142,10 +161,15 @@ __device__ __forceinline__ void soft16_packed(uint32_t* r, uint32_t a_scale, uin
       ffma2(x[q * 4 + 2], x[q * 4 + 3], x[q * 4 + 2], x[q * 4 + 3], __uint_as_float(s[q].z), __uint_as_float(s[q].w), neg_m, neg_m);
     }
   }
+#ifndef RTTS_X_NOEXP      // (ablation builds: tools/ablate_fwd64p.sh)
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = exp2f(x[i]);
+#endif
 #pragma unroll
   for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
+#ifdef RTTS_X_NOMASK
+  return;
+#endif
   const uint4 k0 = lds128(a_p16), k1 = lds128(a_p16 + 16);
   const uint32_t kp[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
   const __half2 qp = *reinterpret_cast<const __half2*>(&q_pos2);
@@ -256,9 +280,11 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
   const uint32_t sbase = smem_u32(smem);
   // barriers (shared-window addresses); ring entry e uses index e % kSlots with phase parity (e / kSlots) & 1, tile t of group
   // g = t & 1 uses the group's barrier with parity (t >> 1) & 1
-  const uint32_t a_kfull = sbase + L::kOffBar;                 // [kSlots]  entry landed (its loader warp)
-  const uint32_t a_pv = a_kfull + kSlots * 8;                  // [kSlots]  the last PV reading the entry has completed (tcgen05.commit)
-  const uint32_t a_sfull = a_pv + kSlots * 8;                  // [2]       tcgen05.commit
+  const uint32_t a_kfull = sbase + L::kOffBar;                 // [kSlots]  K rows + metadata of the entry landed (its K loader warp)
+  const uint32_t a_vfull = a_kfull + kSlots * 8;               // [kSlots]  V rows of the entry landed (its V loader warp)
+  const uint32_t a_kfree = a_vfull + kSlots * 8;               // [kSlots]  the last S reading the entry's K rows has completed (tcgen05.commit)
+  const uint32_t a_vfree = a_kfree + kSlots * 8;               // [kSlots]  the last PV reading the entry's V rows has completed (tcgen05.commit)
+  const uint32_t a_sfull = a_vfree + kSlots * 8;               // [2]       tcgen05.commit
   const uint32_t a_pfull = a_sfull + 2 * 8;                    // [2]       the 4 warps of the group
   const uint32_t a_ofull = a_pfull + 2 * 8;                    // [2]       tcgen05.commit
   const uint32_t a_ofree = a_ofull + 2 * 8;                    // [2]       the 4 warps of the group have read O and the row sums
@@ -275,9 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
   if (tid == 0) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
     int b = 0;
-    for (int s = 0; s < kSlots; ++s) mbar_init(bars + b++, 1);          // kfull
-    for (int s = 0; s < kSlots; ++s) mbar_init(bars + b++, 1);          // pv
-    for (int s = 0; s < 2; ++s) mbar_init(bars + b++, 1);               // s_full
+    for (int s = 0; s < 2 * kSlots; ++s) mbar_init(bars + b++, 1);      // kfull, vfull
+    for (int s = 0; s < kSlots; ++s) mbar_init(bars + b++, 2);          // kfree: both S threads
+    for (int s = 0; s < kSlots; ++s) mbar_init(bars + b++, 1);          // vfree
+    for (int s = 0; s < 2; ++s) mbar_init(bars + b++, 2);               // s_full: both S threads
     for (int s = 0; s < 2; ++s) mbar_init(bars + b++, 4);               // p_full
     for (int s = 0; s < 2; ++s) mbar_init(bars + b++, 1);               // o_full
     for (int s = 0; s < 2; ++s) mbar_init(bars + b++, 4);               // o_free
@@ -292,48 +319,80 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
   if (*tmem_slot != 0) __trap();          // all 512 columns are ours: addresses below are compile-time constants
 
   if (warp == kSWarp) {
-    // ================================================= S = [X_e ; X_e+1] [X_e-1 ; X_e ; X_e+1]^T ===================
+    // ================================================= S, look-back block: [X_e ; X_e+1] X_e-1^T ==================
+    // The score MMA of a tile is issued in two parts by two threads.  The main block (columns 64..191) is chained by the PV
+    // thread right behind PV(t-2) - the tensor pipe executes one thread's MMAs in issue order, so it needs no barrier and is
+    // complete long before the group has finished its epilogue.  The look-back block (columns 0..63) overwrites the row-sum
+    // columns of tile t-2, so it waits until the group has read them (o_free) - four MMAs on the path instead of the whole S.
     if (elect_one()) {
       constexpr uint32_t idesc_lb = umma_idesc_bf16(128, kC, false, false);
-      constexpr uint32_t idesc_main = umma_idesc_bf16(128, 2 * kC, false, false);
       constexpr uint32_t hi = umma_desc_hi_sw128(1024);
       const uint32_t k_lo0 = umma_desc_lo(sbase + L::kOffK, 16);
+      uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
       TileIter ti(tg0, p.tiles_per_row);
       int landed = -1;                     // entries 0..landed have been waited for
       for (int t = 0; t < my_tiles; ++t) {
         const int g = t & 1, e = ti.e;
+        P_STAMP(0, t, 0);
         for (int x = landed + 1; x <= e + 1; ++x) mbar_wait_a(a_kfull + (x & (kSlots - 1)) * 8, (x / kSlots) & 1);
         landed = e + 1;
-        // S(t) overwrites the S / P columns PV(t-2) read and the row-sum columns the epilogue of tile t-2 reads
+        P_STAMP(0, t, 1);
         if (t >= 2) mbar_wait_a(a_ofree + g * 8, ((t >> 1) & 1) ^ 1);
         tc_fence_after_sync();
+        P_STAMP(0, t, 2);
         const uint32_t t_reg = g * 256;
         const uint32_t q_lo = k_lo0 + (e & (kSlots - 1)) * (L::kChunkBytes >> 4);            // rows of (e, e+1): slot 7 continues into the mirror of slot 0
         const uint32_t lb_lo = k_lo0 + ((e - 1) & (kSlots - 1)) * (L::kChunkBytes >> 4);
 #pragma unroll
-        for (int kk = 0; kk < kDh / 16; ++kk) {
-          umma_ss_lo(t_reg, q_lo + kk * 2, lb_lo + kk * 2, hi, idesc_lb, kk > 0);
-          umma_ss_lo(t_reg + kC, q_lo + kk * 2, q_lo + kk * 2, hi, idesc_main, kk > 0);
-        }
-        umma_commit(reinterpret_cast<uint64_t*>(smem + L::kOffBar) + 2 * kSlots + g);
+        for (int kk = 0; kk < kDh / 16; ++kk) umma_ss_lo(t_reg, q_lo + kk * 2, lb_lo + kk * 2, hi, idesc_lb, kk > 0);
+        umma_commit(bars + 4 * kSlots + g);               // s_full (second arrival: the main block is committed by the PV thread)
+        // K rows: entries e-1 and e are not read again; e+1 holds the look-back keys of the next tile unless this tile closes the
+        // row or the run (both S threads arrive: each commit covers its own thread's MMAs)
+        umma_commit(bars + 2 * kSlots + ((e - 1) & (kSlots - 1)));
+        umma_commit(bars + 2 * kSlots + (e & (kSlots - 1)));
+        if (ti.last_in_row() || t + 1 == my_tiles) umma_commit(bars + 2 * kSlots + ((e + 1) & (kSlots - 1)));
+        P_STAMP(0, t, 3);
         ti.next();
       }
     }
   } else if (warp == kPVWarp) {
-    // ================================================= O = P V, rowsum = P 1 =======================================
+    // ================================================= O = P V, rowsum = P 1;  S main block of tile t+2 ==============
     if (elect_one()) {
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, kDh, false, true);
       constexpr uint32_t idesc_sum = umma_idesc_bf16(128, 16, false, false);
+      constexpr uint32_t idesc_main = umma_idesc_bf16(128, 2 * kC, false, false);
       constexpr uint32_t hi = umma_desc_hi_sw128(1024);
       constexpr uint32_t hi_ones = umma_desc_hi_sw128(0);         // the 16 rows of B alias one 1 KB atom of ones
       const uint32_t v_lo0 = umma_desc_lo(sbase + L::kOffV, 0);   // MN-major operand (V rows)
+      const uint32_t k_lo0 = umma_desc_lo(sbase + L::kOffK, 16);
       const uint32_t ones_lo = umma_desc_lo(sbase + L::kOffOnes, 16);
       uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
-      TileIter ti(tg0, p.tiles_per_row);
+      TileIter ti(tg0, p.tiles_per_row), ts(tg0, p.tiles_per_row);      // ts: the tile whose main S block is issued next
+      int k_landed = -1, v_landed = -1;
+      auto issue_s_main = [&](int t2) {      // main block of tile t2: [X_e ; X_e+1] [X_e ; X_e+1]^T -> columns 64..191 of its region
+        const int e = ts.e;
+        for (int x = k_landed + 1; x <= e + 1; ++x) mbar_wait_a(a_kfull + (x & (kSlots - 1)) * 8, (x / kSlots) & 1);
+        k_landed = e + 1;
+        tc_fence_after_sync();
+        const uint32_t q_lo = k_lo0 + (e & (kSlots - 1)) * (L::kChunkBytes >> 4);
+#pragma unroll
+        for (int kk = 0; kk < kDh / 16; ++kk) umma_ss_lo((t2 & 1) * 256 + kC, q_lo + kk * 2, q_lo + kk * 2, hi, idesc_main, kk > 0);
+        umma_commit(bars + 4 * kSlots + (t2 & 1));        // s_full (first arrival)
+        umma_commit(bars + 2 * kSlots + ((e - 1) & (kSlots - 1)));
+        umma_commit(bars + 2 * kSlots + (e & (kSlots - 1)));
+        if (ts.last_in_row() || t2 + 1 == my_tiles) umma_commit(bars + 2 * kSlots + ((e + 1) & (kSlots - 1)));
+        ts.next();
+      };
+      issue_s_main(0);
+      if (my_tiles > 1) issue_s_main(1);
       for (int t = 0; t < my_tiles; ++t) {
         const int g = t & 1, e = ti.e;
+        P_STAMP(0, t, 4);
+        for (int x = v_landed + 1; x <= e + 1; ++x) mbar_wait_a(a_vfull + (x & (kSlots - 1)) * 8, (x / kSlots) & 1);
+        v_landed = e + 1;
         mbar_wait_a(a_pfull + g * 8, (t >> 1) & 1);      // (the group's epilogue of tile t-2 precedes this in its program order: O is drained)
         tc_fence_after_sync();
+        P_STAMP(0, t, 5);
         const uint32_t t_reg = g * 256;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -346,38 +405,54 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
         }
 #pragma unroll
         for (int j = 0; j < 12; ++j) umma_ts_lo(t_reg + kColSum, t_reg + 32 * (j >> 1) + 8 * (j & 1), ones_lo, hi_ones, idesc_sum, j > 0);
-        umma_commit(bars + 2 * kSlots + 4 + g);           // o_full
-        // entries e-1 and e are not read again (S(t) completed before the softmax of this tile started); e+1 is the look-back
-        // chunk of the next tile unless this tile closes the row or the run
-        umma_commit(bars + kSlots + ((e - 1) & (kSlots - 1)));
-        umma_commit(bars + kSlots + (e & (kSlots - 1)));
-        if (ti.last_in_row() || t + 1 == my_tiles) umma_commit(bars + kSlots + ((e + 1) & (kSlots - 1)));
+        umma_commit(bars + 4 * kSlots + 4 + g);           // o_full
+        // the V rows of entries e-1 and e are not read again; e+1 is the look-back chunk of the next tile unless this tile closes
+        // the row or the run
+        umma_commit(bars + 3 * kSlots + ((e - 1) & (kSlots - 1)));
+        umma_commit(bars + 3 * kSlots + (e & (kSlots - 1)));
+        if (ti.last_in_row() || t + 1 == my_tiles) umma_commit(bars + 3 * kSlots + ((e + 1) & (kSlots - 1)));
+        P_STAMP(0, t, 6);
+        // the S / P columns 64..191 of the region are free once PV(t) has executed - which the pipe does before anything this thread
+        // issues afterwards
+        if (t + 2 < my_tiles) issue_s_main(t + 2);
         ti.next();
       }
     }
   } else if (warp >= kFirstLoaderWarp) {
     // ================================================= loaders =====================================================
-    // Warp w gathers the entries e = w (mod 4) on its own (no cross-warp step on the per-entry path): lane = (row within a group of
-    // 4, 16-byte piece), 16 passes of K and V rows; lane l also owns the metadata of rows l and l + 32.  Software-pipelined: the
-    // stickers and |x|^2 / mask values of the warp's NEXT entry are requested before the current one is copied.
+    // Two K loaders and two V loaders (loader warp 2i: K rows + metadata, 2i+1: V rows; each takes the entries e = i mod 2).  The K
+    // rows of an entry are released by the S that last reads them - before the softmax of that tile has even started - and the V
+    // rows by the PV, so the K side runs several tiles ahead and an S never waits for a slot that a PV still holds (with one ring
+    // for both, S(t+3) could not be issued before PV(t) had completed plus a full gather latency: the S issuer sat on the loads).
+    // lane = (row within a group of 4, 16-byte piece), 8 passes of two 128-byte rows; lane l also owns the metadata of rows l and
+    // l + 32.  Software-pipelined: the stickers (and |x|^2 / mask values) of the warp's NEXT entry are requested before the current
+    // one is copied, and an entry is announced when the next one's copies are queued (or as soon as the warp would block).
     const int lw = warp - kFirstLoaderWarp;
+    const bool is_v = lw >= kKLoaders;
+    const int l_first = is_v ? lw - kKLoaders : lw, l_stride = is_v ? kVLoaders : kKLoaders;
     const int grp = lane >> 3, c = lane & 7;
-    const uint32_t ld32 = static_cast<uint32_t>(p.ld);
+    const uint32_t ld_bytes = static_cast<uint32_t>(p.ld) * 2u;      // row pitch: T * ld < 2^31 elements (checked by the host)
+    const int src_e = grp;                                            // lane holding the position of row 8 * i2 + grp is (8 * i2 + grp) & 31
     const float ssl2 = p.score_scale_log2;
+    const uint32_t a_full = is_v ? a_vfull : a_kfull, a_free = is_v ? a_vfree : a_kfree;
     EntryIter it(2 * tg0, 2 * tg1, cpr, cpround, p.R, p.H);
     auto fetch = [&]() {                              // this warp's next entry
       Entry x = it.next();
-      it.next(); it.next(); it.next();
+      for (int i = 1; i < l_stride; ++i) it.next();
       return x;
     };
-    // raw stickers (round * T + position) of rows lane, lane + 32 and their |x|^2 / mask values
-    auto prefetch = [&](const Entry& x, int& s0, int& s1, float& q0, float& q1, uint32_t& v0, uint32_t& v1) {
-      q0 = q1 = 1.f;
-      v0 = v1 = 1u;
+    // raw stickers (round * T + position) of rows lane, lane + 32: requested TWO entries ahead; (K side) their |x|^2 / mask values:
+    // requested one entry ahead, when the stickers they depend on have arrived - no load is waited for on the per-entry path
+    auto load_stickers = [&](const Entry& x, int& s0, int& s1) {
       if (!x.ok) return;
       const int32_t* stk = p.sticker + static_cast<int64_t>(x.row) * RT + x.j * kC;
       s0 = __ldg(stk + lane);
       s1 = __ldg(stk + 32 + lane);
+    };
+    auto load_meta = [&](const Entry& x, int s0, int s1, float& q0, float& q1, uint32_t& v0, uint32_t& v1) {
+      q0 = q1 = 1.f;
+      v0 = v1 = 1u;
+      if (!x.ok || is_v) return;
       const int base = x.round * p.T;
       const float* sq = p.sumsq + static_cast<int64_t>(x.row) * p.T - base;
       q0 = __ldg(sq + s0);
@@ -388,27 +463,31 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
         v1 = __ldg(mk + s1);
       }
     };
-    for (int i = 0; i < lw; ++i) it.next();
-    Entry e0 = fetch(), e1;
-    int s0 = 0, s1 = 0, n0 = 0, n1 = 0;
+    for (int i = 0; i < l_first; ++i) it.next();
+    Entry e0 = fetch(), e1 = fetch(), e2;
+    int s0 = 0, s1 = 0, n0 = 0, n1 = 0, m0 = 0, m1 = 0;
     float q0, q1, nq0, nq1;
     uint32_t v0, v1, nv0, nv1;
-    prefetch(e0, s0, s1, q0, q1, v0, v1);
+    load_stickers(e0, s0, s1);
+    load_stickers(e1, n0, n1);
+    load_meta(e0, s0, s1, q0, q1, v0, v1);
     int pending = -1;
     auto announce = [&](int slot) {
       fence_proxy_async_smem();            // cp.async / st.shared data -> visible to the tensor-core (async) proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive_a(a_kfull + slot * 8);
+      if (lane == 0) mbar_arrive_a(a_full + slot * 8);
     };
-    for (int e = lw; e0.ok; e += kLoaderWarps) {
+    for (int e = l_first; e0.ok; e += l_stride) {
       const int slot = e & (kSlots - 1), ms = e & (kMetaSlots - 1);
-      e1 = fetch();
-      prefetch(e1, n0, n1, nq0, nq1, nv0, nv1);
+      if (lane == 0) P_STAMP(1, e, is_v ? 4 : 0);
+      e2 = fetch();
+      load_stickers(e2, m0, m1);
+      load_meta(e1, n0, n1, nq0, nq1, nv0, nv1);
       const int base_round = e0.round * p.T;
-      // data slot: the last PV reading the entry that lived there has completed
+      // the last MMA reading the entry that lived in the slot has completed
       if (e >= kSlots) {
         int ready = 1;
-        if (lane == 0) ready = mbar_try_wait_a(a_pv + slot * 8, ((e / kSlots) - 1) & 1);
+        if (lane == 0) ready = mbar_try_wait_a(a_free + slot * 8, ((e / kSlots) - 1) & 1);
         ready = __shfl_sync(0xffffffffu, ready, 0);
         if (!ready) {
           if (pending >= 0) {              // would block: do not sit on an entry that has already landed
@@ -416,33 +495,39 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
             announce(pending);
             pending = -1;
           }
-          warp_wait(a_pv + slot * 8, ((e / kSlots) - 1) & 1);
+          warp_wait(a_free + slot * 8, ((e / kSlots) - 1) & 1);
         }
       }
+      if (lane == 0) P_STAMP(1, e, is_v ? 5 : 1);
       const int p0 = s0 - base_round, p1 = s1 - base_round;
       // rows 4i + grp: the swizzle term (row & 7) alternates between grp and grp + 4 with the parity of i
-      const uint32_t sKe = sbase + L::kOffK + slot * L::kChunkBytes + sw128_offset(grp, c), sKo = sbase + L::kOffK + slot * L::kChunkBytes + sw128_offset(grp + 4, c);
-      constexpr uint32_t kVoff = L::kOffV - L::kOffK;      // slot s of the V ring sits kVoff behind slot s of the K ring
-      const __nv_bfloat16* qk_b = p.qk + static_cast<int64_t>(e0.b) * p.T * p.ld + e0.h * kDh + c * 8;
-      const __nv_bfloat16* v_b = p.v + static_cast<int64_t>(e0.b) * p.T * p.ld + e0.h * kDh + c * 8;
-      const bool mirror = slot == 0 && e > 0;      // slot kSlots mirrors slot 0 (K rows): the 128 rows of (slot 7, slot 0)
-#pragma unroll 1
+      const uint32_t ring = sbase + (is_v ? L::kOffV : L::kOffK) + slot * L::kChunkBytes;
+      const uint32_t d_e = ring + sw128_offset(grp, c), d_o = ring + sw128_offset(grp + 4, c);
+      // row addresses = base of the (batch, head, 16-byte piece) + position * row pitch: one IMAD.WIDE each (the generic form - 64-bit
+      // pointer arithmetic on element offsets, lane selects, a rolled loop - was 590 of the loader's 920 instructions per entry)
+      const uint64_t src_b = static_cast<uint64_t>(__cvta_generic_to_global((is_v ? p.v : p.qk) + static_cast<int64_t>(e0.b) * p.T * p.ld + e0.h * kDh + c * 8));
+      const bool mirror = !is_v && slot == 0 && e > 0;      // slot kSlots mirrors slot 0 (K rows): the 128 rows of (slot 7, slot 0)
+#pragma unroll
       for (int i2 = 0; i2 < kC / 8; ++i2) {
         const int psel = i2 < 4 ? p0 : p1;
-        const int pre = __shfl_sync(0xffffffffu, psel, (8 * i2 + grp) & 31), pro = __shfl_sync(0xffffffffu, psel, (8 * i2 + 4 + grp) & 31);
-        const uint32_t offe = static_cast<uint32_t>(pre) * ld32, offo = static_cast<uint32_t>(pro) * ld32;       // element offsets inside the batch entry: T * ld < 2^31 (checked by the host)
-        const uint32_t de = sKe + i2 * 1024, dd = sKo + i2 * 1024;
-        cp_async16(de, qk_b + offe);
-        cp_async16(de + kVoff, v_b + offe);
-        cp_async16(dd, qk_b + offo);
-        cp_async16(dd + kVoff, v_b + offo);
+        const uint32_t pre = static_cast<uint32_t>(__shfl_sync(0xffffffffu, psel, src_e + 8 * (i2 & 3)));
+        const uint32_t pro = static_cast<uint32_t>(__shfl_sync(0xffffffffu, psel, src_e + 8 * (i2 & 3) + 4));
+        const uint64_t ge = mad_wide(pre, ld_bytes, src_b), go = mad_wide(pro, ld_bytes, src_b);
+#ifdef RTTS_X_NOCOPY
+        if (pre == 0xffffffffu)
+#endif
+        {
+          cp_async16_g(d_e + i2 * 1024, ge);
+          cp_async16_g(d_o + i2 * 1024, go);
+        }
         if (mirror) {
-          cp_async16(de + kSlots * L::kChunkBytes, qk_b + offe);
-          cp_async16(dd + kSlots * L::kChunkBytes, qk_b + offo);
+          cp_async16_g(d_e + i2 * 1024 + kSlots * L::kChunkBytes, ge);
+          cp_async16_g(d_o + i2 * 1024 + kSlots * L::kChunkBytes, go);
         }
       }
       cp_async_commit();
-      {
+      if (lane == 0) P_STAMP(1, e, is_v ? 6 : 2);
+      if (!is_v) {
         const uint32_t a_meta = sbase + L::kOffMeta + ms * L::kMetaBytes;
         bool big = false;
 #pragma unroll
@@ -485,8 +570,9 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
         announce(pending);
       }
       pending = slot;
-      e0 = e1;
-      s0 = n0; s1 = n1; q0 = nq0; q1 = nq1; v0 = nv0; v1 = nv1;
+      if (lane == 0) P_STAMP(1, e, is_v ? 7 : 3);
+      e0 = e1; e1 = e2;
+      s0 = n0; s1 = n1; n0 = m0; n1 = m1; q0 = nq0; q1 = nq1; v0 = nv0; v1 = nv1;
     }
     if (pending >= 0) {
       cp_async_wait<0>();
@@ -512,8 +598,10 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
       const uint32_t a_meta_q = sbase + L::kOffMeta + (eq & (kMetaSlots - 1)) * L::kMetaBytes;
       const uint32_t a_meta_lb = sbase + L::kOffMeta + ((eq - 1) & (kMetaSlots - 1)) * L::kMetaBytes;
       // S(t) was issued after its thread had seen the entries land, so its completion also certifies the loaders' metadata
+      if (q == 0 && lane == 0) P_STAMP(2, t, 0);
       warp_wait(a_sfull + g * 8, ph);
       tc_fence_after_sync();
+      if (q == 0 && lane == 0) P_STAMP(2, t, 1);
       const uint4 info = lds128(a_meta_q + L::kMInfo);       // {row_bh, round * T, flags, -}
       const uint2 qm = lds64(a_meta_q + L::kMQ + rr * 8);
       float row_max = -__uint_as_float(qm.x);
@@ -588,10 +676,12 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
       tc_fence_before_sync();       // this thread's TMEM reads of S / writes of P precede the MMAs that consume / overwrite the region
       __syncwarp();
       if (lane == 0) mbar_arrive_a(a_pfull + g * 8);
+      if (lane == 0 && (q == 0 || q == 3)) P_STAMP(2, t, 2 + (q == 3));
 
       // ---------------------------------------------- epilogue of the same rows ----------------------------------
       warp_wait(a_ofull + g * 8, ph);
       tc_fence_after_sync();
+      if (q == 0 && lane == 0) P_STAMP(2, t, 4);
       uint32_t rs, o0[32], o1[32];
       tmem_ld1(t_lane + kColSum, &rs);
       tmem_ld32(t_lane + kColO, o0);
@@ -601,6 +691,7 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_a(a_ofree + g * 8);      // the region may be overwritten by S(t+2)
+      if (q == 0 && lane == 0) P_STAMP(2, t, 5);
       float sum = __uint_as_float(rs);
       // all terms exactly zero: the row sees only itself (rp R8): softmax uniform over the self columns, which all hold the
       // query's own token, so out = v[own position], lse = self_value + log(#self columns)
@@ -643,16 +734,23 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
       p.lse_rounds[row_base + out_slot] = (row_max + log2f(sum)) * kLn2;
       // scatter-store, one full 128-byte row per 8 lanes (four rows per instruction)
       {
-        const char* obase = reinterpret_cast<const char*>(p.o_rounds) + row_base * (kDh * 2) + l7 * 16;
-#pragma unroll 2
+        const uint64_t obase = static_cast<uint64_t>(__cvta_generic_to_global(p.o_rounds)) + static_cast<uint64_t>(row_base) * (kDh * 2) + l7 * 16;
+        const uint32_t r4 = lane >> 3;
+        // rows 4 * itr + r4: the swizzle term (row & 7) alternates between r4 and r4 + 4 with the parity of itr
+        const uint32_t a_e = a_stage + r4 * 128 + ((l7 ^ r4) << 4), a_o = a_stage + (r4 + 4) * 128 + ((l7 ^ (r4 + 4)) << 4);
+#pragma unroll
         for (int itr = 0; itr < 8; ++itr) {
-          const int row = itr * 4 + (lane >> 3);
-          const uint4 u = lds128(a_stage + row * 128 + ((l7 ^ (row & 7)) << 4));
-          const uint32_t os = __shfl_sync(0xffffffffu, out_slot, row);
-          *reinterpret_cast<uint4*>(const_cast<char*>(obase) + static_cast<uint64_t>(os) * (kDh * 2)) = u;
+          const uint4 u = lds128(((itr & 1) ? a_o : a_e) + (itr >> 1) * 1024);
+          const uint32_t os = __shfl_sync(0xffffffffu, out_slot, itr * 4 + r4);
+#ifndef RTTS_X_NOSTORE
+          stg128(mad_wide(os, kDh * 2, obase), u);
+#else
+          if (os == 0xffffffffu) stg128(mad_wide(os, kDh * 2, obase), u);
+#endif
         }
       }
       __syncwarp();                 // the staging tile is free again
+      if (q == 0 && lane == 0) P_STAMP(2, t, 6);
     }
   }
   tc_fence_before_sync();
