@@ -27,11 +27,12 @@ t = trace.cpu().view(4, 64, 8)
 t0 = int(t[t > 0].min())
 names = {1: ["K start", "K slot free", "K copies issued", "K meta done", "V start", "V slot free", "V copies issued", "V done"],
          0: ["S: top", "S: landed", "S: region free", "S: committed", "PV: top", "PV: p_full", "PV: committed"],
+         3: ["meta read", "ld0", "blk0 done", "ld1", "blk1 done", "st_wait done"],
          2: ["top", "s_full", "w0 p-arrived", "w3 p-arrived", "o_full", "o_free arrived", "stored"]}
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 for i in range(2 * n + 2):
     print(f"entry {i:2d} loader ", "  ".join(f"{nm}={int(t[1, i, k]) - t0 if int(t[1, i, k]) else '-'}" for k, nm in enumerate(names[1])))
 for i in range(n):
     print(f"--- tile {i}")
-    for role, rn in ((0, "mma"), (2, "softmax")):
+    for role, rn in ((0, "mma"), (2, "softmax"), (3, "w0 detail")):
         print(f"  {rn:8s}", "  ".join(f"{nm}={int(t[role, i, k]) - t0 if int(t[role, i, k]) else '-'}" for k, nm in enumerate(names[role])))
