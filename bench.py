@@ -307,8 +307,8 @@ def run_ours(args, kwargs, world, rank, local_rank):
         key_fwd, key_bwd = f"lsh_attn_fwd[T={t}]", f"lsh_attn_bwd[T={t}]"
         fwd_ms, bwd_ms = kernel_ms.get(key_fwd, {}).get("avg_ms"), kernel_ms.get(key_bwd, {}).get("avg_ms")
         peak = peaks["bf16_tflops_sustained"]
-        # the forward kernel of the decoder's self-attention: bucket 64 up to T = 2048 runs the block-streaming kernel (lsh_attn_fwd64.cu)
-        kname, ksrc = (("lsh_attn_fwd64_kernel", ["lsh_attn_fwd64.cu", "lsh_attn_params.h", "common.cuh"]) if bucket == 64 and t <= 2048
+        # the forward kernel of the decoder's self-attention: bucket 64 up to T = 2048 runs the paired-chunk kernel (lsh_attn_fwd64p.cu)
+        kname, ksrc = (("lsh_attn_fwd64p_kernel", ["lsh_attn_fwd64p.cu", "lsh_attn_params.h", "common.cuh"]) if bucket == 64 and t <= 2048
                        else (f"lsh_attn_fwd_kernel<{bucket}>", ["lsh_attn_fwd.cu", "lsh_attn_params.h", "common.cuh"]))
         roofline = {"bound": "tensor", "kernel": f"{kname} (decoder shape B={b} T={t} H=8 R={r})", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None,
                     "traffic": None, "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)"}

@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
     // for both, S(t+3) could not be issued before PV(t) had completed plus a full gather latency: the S issuer sat on the loads).
     // lane = (row within a group of 4, 16-byte piece), 8 passes of two 128-byte rows; lane l also owns the metadata of rows l and
     // l + 32.  Software-pipelined: the stickers (and |x|^2 / mask values) of the warp's NEXT entry are requested before the current
-    // one is copied, and an entry is announced when the next one's copies are queued (or as soon as the warp would block).
+    // one is copied; the entry is announced as soon as its rows have landed.
     const int lw = warp - kFirstLoaderWarp;
     const bool is_v = lw >= kKLoaders;
     const int l_first = is_v ? lw - kKLoaders : lw, l_stride = is_v ? kVLoaders : kKLoaders;
@@ -497,7 +497,6 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
     load_stickers(e0, s0, s1);
     load_stickers(e1, n0, n1);
     load_meta(e0, s0, s1, q0, q1, v0, v1);
-    int pending = -1;
     auto announce = [&](int slot) {
       fence_proxy_async_smem();            // cp.async / st.shared data -> visible to the tensor-core (async) proxy
       __syncwarp();
@@ -516,11 +515,6 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
         if (lane == 0) ready = mbar_try_wait_a(a_free + slot * 8, ((e / kSlots) - 1) & 1);
         ready = __shfl_sync(0xffffffffu, ready, 0);
         if (!ready) {
-          if (pending >= 0) {              // would block: do not sit on an entry that has already landed
-            cp_async_wait<0>();
-            announce(pending);
-            pending = -1;
-          }
           warp_wait(a_free + slot * 8, ((e / kSlots) - 1) & 1);
         }
       }
@@ -591,18 +585,13 @@ __global__ void __launch_bounds__(kThreads, 1) lsh_attn_fwd64p_kernel(const Attn
           sts128(a_meta + L::kMInfo, make_uint4(static_cast<uint32_t>(e0.row), static_cast<uint32_t>(base_round), static_cast<uint32_t>(flags), 0u));
         }
       }
-      if (pending >= 0) {
-        cp_async_wait<1>();         // everything but the group just committed has landed
-        announce(pending);
-      }
-      pending = slot;
+      // announce as soon as the rows have landed: a loader handles one entry per one or two tiles, so waiting ~700 cycles here costs
+      // nothing, while an announcement deferred to the warp's next entry reached the PV thread a whole tile later
+      cp_async_wait<0>();
+      announce(slot);
       if (lane == 0) P_STAMP(1, e, is_v ? 7 : 3);
       e0 = e1; e1 = e2;
       s0 = n0; s1 = n1; n0 = m0; n1 = m1; q0 = nq0; q1 = nq1; v0 = nv0; v1 = nv1;
-    }
-    if (pending >= 0) {
-      cp_async_wait<0>();
-      announce(pending);
     }
   } else {
     // ================================================= softmax + epilogue ==========================================
