@@ -233,6 +233,45 @@ def test_attention_sizes_of_baseline_configs(ops, core):
     assert torch.isfinite(out.float()).all() and (out.float() - 1).abs().max().item() <= 2 ** -7    # rows of P sum to 1
 
 
+@pytest.mark.parametrize("B,T,H,R,causal,pad", [(3, 1024, 8, 8, True, 0), (5, 256, 8, 8, False, 40), (2, 128, 2, 1, True, 0), (1, 2048, 4, 3, True, 300),
+                                               (37, 128, 4, 2, False, 17)])
+def test_attention_bucket64_kernels_agree(ops, core, B, T, H, R, causal, pad):
+    """The three bucket-64 forward kernels (paired-chunk = the default, 128-query tiles, block-streaming) are independent
+    implementations of the same arithmetic: per-round outputs and log-sum-exps must agree to bf16 / fp32 rounding.  Shapes cover
+    runs of a CTA that start inside a (batch, head) row, rows of a single tile (T = 128, R = 1), more CTAs than tiles and fewer."""
+    import ctypes
+    from reformer_tts_b200 import _lib
+    lib = _lib.load()
+    lib.rtts_debug_set_fwd_kernel.argtypes = [ctypes.c_int]
+    torch.manual_seed(11)
+    qkv = torch.randn(B, T, 2 * H * 64, device=DEV).bfloat16()
+    qk, v = qkv[..., :H * 64], qkv[..., H * 64:]
+    nb = T // 64
+    rot = torch.randn(1, 64, R, nb // 2, device=DEV)
+    mask = None
+    if pad:
+        mask = torch.ones(B, T, dtype=torch.uint8, device=DEV)
+        mask[:, T - pad:] = 0
+    spec = ops.LSHSpec.reformer_pytorch(64, causal)
+    buckets, sumsq = ops.lsh_hash(qk, rot, H, R, nb, return_sumsq=True)
+    sticker, _ = ops.lsh_sort(buckets, T, R, nb)
+    res = []
+    try:
+        for which in (0, 1, 2):
+            lib.rtts_debug_set_fwd_kernel(which)
+            o, lse = ops.lsh_attn_fwd(qk, v, sticker, mask, spec, H, R, 64, sumsq=sumsq)
+            torch.cuda.synchronize()
+            res.append((o.float(), lse.clone()))
+    finally:
+        lib.rtts_debug_set_fwd_kernel(0)
+    for which, name in ((1, "tile"), (2, "block")):
+        # (the kernels form the stabiliser with differently rounded arithmetic, so a P value near a bf16 rounding boundary can fall
+        # on either side: agreement is to bf16 OUTPUT rounding, 2^-9 / sqrt(3) = 1.1e-3 if every element differed by half an ulp;
+        # each kernel alone is held to TOL against the rounded oracle by the tests above)
+        assert rel_l2(res[0][0], res[which][0]) <= 2e-3, name
+        assert (res[0][1] - res[which][1]).abs().max().item() <= 4e-3, name      # fp32 spacing at 5e4 is 4e-3
+
+
 @pytest.mark.parametrize("causal", [False, True])
 def test_attention_full_size_with_heavy_padding(ops, core, rnd, causal):
     """BASELINE.json config 2 decoder shape (B=20, T=1024, 8 heads, 8 rounds, bucket 64) with 224 padded positions per sequence
