@@ -160,6 +160,10 @@ int rtts_gemm_bf16_dropout(const void* A, int64_t lda, int a_mn_major, const voi
 
 /* ---- small fused element-wise helpers used by the host mirror -------------------------------- */
 
+/* Column sums of a bf16 matrix (row pitch ld elements): colsum fp32 [cols] += sum_rows x[r, :].  Bias gradients of gradient matrices
+ * that are already bf16 (the autograd sum over the batch of nn.Linear / nn.MultiheadAttention biases, ref:reformer_tts/model/reformer.py:161-186). */
+int rtts_colsum_bf16(const void* x, int64_t ld, float* colsum, int rows, int cols, void* stream);
+
 /* fp32 -> bf16 cast with optional column-sum accumulation (bias gradients): colsum fp32 [cols] += sum_rows. */
 int rtts_cast_bf16_colsum(const float* x, void* y, float* colsum, int rows, int cols, void* stream);
 /* Same with inverted dropout applied first: y = bf16(keep * scale * x), colsum += column sums of the masked values

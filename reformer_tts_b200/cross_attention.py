@@ -82,9 +82,9 @@ class _CrossAttentionFn(torch.autograd.Function):
         dkv = torch.stack((dk4.transpose(1, 2), dv4.transpose(1, 2)), dim=2).reshape(rows_kv, 2 * d)
         # input projections: weights [3D, D] = [Wq; Wk; Wv]
         g_win, s_win = target((3 * d, d), p_win)
-        g_bin = torch.empty(3 * d, dtype=torch.float32, device=dev)
-        torch.sum(dq, dim=0, dtype=torch.float32, out=g_bin[:d])
-        torch.sum(dkv, dim=0, dtype=torch.float32, out=g_bin[d:])
+        g_bin = torch.zeros(3 * d, dtype=torch.float32, device=dev)
+        ops.colsum_bf16(dq, g_bin[:d])
+        ops.colsum_bf16(dkv, g_bin[d:])
         ops.gemm(dq, xn, a_mn_major=True, b_mn_major=True, out=g_win[:d], accumulate=True, split_k=_split_k(rows_q, tiles))
         ops.gemm(dkv, memb, a_mn_major=True, b_mn_major=True, out=g_win[d:], accumulate=True, split_k=_split_k(rows_kv, 2 * tiles))
         dxn = ops.gemm(dq, wq_bf16, b_mn_major=True)                                        # fp32 [B*T, D]

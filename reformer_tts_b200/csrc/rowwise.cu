@@ -195,6 +195,49 @@ __global__ void __launch_bounds__(kCastThreads) cast_bf16_colsum_kernel(const fl
   }
 }
 
+// colsum[c] += sum_rows x[r,c] for a bf16 matrix (bias gradients of gradient matrices that are already bf16): the same strip
+// scheme as above - `tpr` threads (8 bf16 each) cover one row of the strip, eight 16-byte loads in flight per thread, shared-memory
+// reduction over the row lanes, two 16-byte vector reductions per thread and CTA.
+__global__ void __launch_bounds__(kCastThreads) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, float* __restrict__ colsum, int rows,
+                                                                    int cols, int rows_per_cta, int tpr) {
+  __shared__ float red[kCastThreads][9];
+  const int lane_row = threadIdx.x / tpr, lanes = kCastThreads / tpr;
+  const int c = (blockIdx.x * tpr + threadIdx.x % tpr) * 8;
+  const bool live = c < cols;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto add = [&](const uint4& u) {
+    acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+    acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+  };
+  if (live) {
+    int r = r0 + lane_row;
+    for (; r + 7 * lanes < r1; r += 8 * lanes) {
+      uint4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r + i * lanes) * ld + c));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) add(v[i]);
+    }
+    for (; r < r1; r += lanes) add(__ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ld + c)));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+  __syncthreads();
+  if (lane_row == 0 && live) {
+    for (int l = 1; l < lanes; ++l)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += red[l * tpr + threadIdx.x][i];
+    if ((reinterpret_cast<uintptr_t>(colsum + c) & 15) == 0) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + c), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]), "f"(acc[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + c + 4), "f"(acc[4]), "f"(acc[5]), "f"(acc[6]), "f"(acc[7]) : "memory");
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(colsum + c + i, acc[i]);
+    }
+  }
+}
+
 // delta[(b*H+h)*T + t] = <dout[b,t,h,:], out[b,t,h,:]>, bf16 inputs, 8 lanes per 64-wide head slice.
 __global__ void __launch_bounds__(256) lsh_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                                                         int64_t ld, float* __restrict__ delta, int T, int H, int64_t rows) {
@@ -284,6 +327,25 @@ extern "C" int rtts_layernorm_bwd_acc(const float* dy, const float* x, const flo
     default: return fail(kErrUnsupported, "rtts_layernorm_bwd: dim=%d unsupported (128, 256, 512, 1024)", dim);
   }
   return check_launch("rtts_layernorm_bwd");
+}
+
+extern "C" int rtts_colsum_bf16(const void* x, int64_t ld, float* colsum, int rows, int cols, void* stream) {
+  RTTS_REQUIRE(x && colsum, "rtts_colsum_bf16: null pointer");
+  RTTS_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && ld >= cols, "rtts_colsum_bf16: cols=%d and ld must be multiples of 8", cols);
+  RTTS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "rtts_colsum_bf16: x must be 16-byte aligned");
+  const int vec = cols / 8;                                   // 16-byte pieces per row
+  int tpr = 1;
+  while (tpr < vec && tpr < 128) tpr *= 2;                    // threads per row of a strip (power of two <= 128: at most 1024 columns per CTA)
+  const int strips = (vec + tpr - 1) / tpr;
+  int ctas_y = (4 * kNumSMs + strips - 1) / strips;           // ~4 CTAs per SM
+  const int lanes = kCastThreads / tpr;
+  const int max_y = (rows + 8 * lanes - 1) / (8 * lanes);
+  if (ctas_y > max_y) ctas_y = max_y;
+  if (ctas_y < 1) ctas_y = 1;
+  const int rows_per_cta = (rows + ctas_y - 1) / ctas_y;
+  colsum_bf16_kernel<<<dim3(strips, ctas_y), kCastThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, colsum, rows, cols,
+                                                                                                   rows_per_cta, tpr);
+  return check_launch("rtts_colsum_bf16");
 }
 
 extern "C" int rtts_cast_bf16_colsum(const float* x, void* y, float* colsum, int rows, int cols, void* stream) {

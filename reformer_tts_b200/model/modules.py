@@ -41,6 +41,36 @@ def _conv5(cin, cout):
     return nn.Conv1d(cin, cout, kernel_size=5, padding=2)
 
 
+def _conv_stack_tokens_last(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """``seq(x.transpose(1, 2)).transpose(1, 2)`` for a stack of Conv1d / BatchNorm1d / elementwise layers, x = [B, T, C].
+
+    On the GPU the token-major activation IS the channels-last image [B, C, 1, T] (strides T*C, 1, -, C), so the stack runs on 4-D
+    channels-last views: the vendor convolutions take it as is (their implicit-GEMM kernels are NHWC; with the reference's [B, C, T]
+    layout every convolution was wrapped in an NCHW->NHWC / NHWC->NCHW transpose pair - 56 launches, ~0.6 ms of a 22.7 ms step) and
+    both transposes around the stack are views.  Same modules, same parameters, same state-dict keys, same arithmetic (BatchNorm1d's
+    running-statistics bookkeeping included); the CPU path (oracle) keeps the reference's layout."""
+    if not x.is_cuda:
+        return seq(x.transpose(1, 2)).transpose(1, 2)
+    import torch.nn.functional as F
+    h = x.transpose(1, 2).unsqueeze(2)                      # [B, C, 1, T]: a view, contiguous in the channels-last sense
+    for m in seq:
+        if isinstance(m, nn.Conv1d):
+            w = m.weight.unsqueeze(2).contiguous(memory_format=torch.channels_last)
+            h = F.conv2d(h, w, m.bias, stride=(1, m.stride[0]), padding=(0, m.padding[0]), dilation=(1, m.dilation[0]), groups=m.groups)
+        elif isinstance(m, nn.BatchNorm1d):
+            factor = 0.0 if m.momentum is None else m.momentum
+            if m.training and m.track_running_stats and m.num_batches_tracked is not None:
+                m.num_batches_tracked.add_(1)
+                if m.momentum is None:
+                    factor = 1.0 / float(m.num_batches_tracked)
+            use_batch_stats = m.training or (m.running_mean is None and m.running_var is None)
+            h = F.batch_norm(h, m.running_mean if not m.training or m.track_running_stats else None,
+                             m.running_var if not m.training or m.track_running_stats else None, m.weight, m.bias, use_batch_stats, factor, m.eps)
+        else:
+            h = m(h)
+    return h.squeeze(2).transpose(1, 2)
+
+
 class EncoderPreNet(nn.Module):
     """Embedding -> 3 x (dropout, conv5, batch-norm, ReLU) -> dropout -> Linear  (ref:...modules.py:8-61)."""
 
@@ -56,8 +86,7 @@ class EncoderPreNet(nn.Module):
         self.convolutions = nn.Sequential(OrderedDict(layers))
 
     def forward(self, tokens):
-        x = self.convolutions(self.embed(tokens).transpose(1, 2))
-        return self.projection(x.transpose(1, 2))
+        return self.projection(_conv_stack_tokens_last(self.convolutions, self.embed(tokens)))
 
 
 class DecoderPreNet(nn.Module):
@@ -90,7 +119,7 @@ class PostConvNet(nn.Module):
         self.layers = nn.Sequential(OrderedDict(layers))
 
     def forward(self, mel):
-        return self.layers(mel.transpose(1, 2)).transpose(1, 2)
+        return _conv_stack_tokens_last(self.layers, mel)
 
 
 class ScaledPositionalEncoding(nn.Module):

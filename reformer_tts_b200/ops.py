@@ -335,6 +335,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     return out
 
 
+def colsum_bf16(x: torch.Tensor, colsum: torch.Tensor) -> torch.Tensor:
+    """colsum (fp32 [cols]) += column sums of the bf16 matrix x [rows, cols] (rows may be strided): bias gradients."""
+    _check(x, torch.bfloat16, "x")
+    _check(colsum, torch.float32, "colsum")
+    assert x.dim() == 2 and x.stride(1) == 1 and colsum.is_contiguous() and colsum.numel() == x.shape[1]
+    _launch("colsum_bf16", "rtts_colsum_bf16", _ptr(x), x.stride(0), _ptr(colsum), x.shape[0], x.shape[1], _stream())
+    return colsum
+
+
 def cast_bf16_colsum(x: torch.Tensor, colsum: Optional[torch.Tensor] = None, keep_mask: Optional[torch.Tensor] = None,
                      keep_scale: float = 1.0) -> torch.Tensor:
     """fp32 [rows, cols] -> bf16 copy; colsum (fp32 [cols]) += column sums.  With ``keep_mask`` (uint8, x's shape) the inverted

@@ -460,3 +460,15 @@ def test_cast_colsum_and_delta(ops):
     o = torch.randn(3, 256, 512, device=DEV).bfloat16()
     want = (a.float() * o.float()).view(3, 256, 8, 64).sum(-1).permute(0, 2, 1)
     assert rel_l2(ops.lsh_delta(a, o, 8), want) <= 1e-5
+
+
+@pytest.mark.parametrize("rows,cols,ld", [(20480, 512, 512), (5120, 1024, 1024), (777, 64, 96), (3, 8, 8)])
+def test_colsum_bf16(ops, rows, cols, ld):
+    """Bias gradients of bf16 gradient matrices: fp32 column sums accumulated into the target (strided rows allowed)."""
+    torch.manual_seed(2)
+    buf = torch.randn(rows, ld, device=DEV).bfloat16()
+    x = buf[:, :cols]
+    acc = torch.full((cols,), 0.5, device=DEV)
+    ops.colsum_bf16(x, acc)
+    want = x.double().sum(0) + 0.5
+    assert (acc.double() - want).abs().max().item() <= 1e-5 * max(1.0, x.double().abs().sum(0).max().item())

@@ -437,3 +437,46 @@ def test_weight_gradients_accumulated_straight_into_the_flat_buffer_equal_autogr
     for m in (enc, dec):
         for k, p in m.named_parameters():
             assert rel_l2(p.grad, 2 * plain[id(p)]) <= 1e-5, k
+
+
+@pytest.mark.parametrize("net_name", ["post", "enc_pre"])
+def test_conv_stacks_on_token_major_views_equal_the_reference_layout(net_name):
+    """Pre / post nets (outside the hot path): on the GPU the Conv1d / BatchNorm1d stacks run on channels-last views of the token-major
+    activation instead of the reference's [B, C, T] tensors.  Same modules and parameters: outputs, input / parameter gradients and
+    the batch-norm running statistics must equal the reference-layout run of the same stack (exact fp32 convolutions for the check)."""
+    from reformer_tts_b200.model import modules as M
+    torch.manual_seed(5)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        if net_name == "post":
+            net = M.PostConvNet(80, 128, 0.0, 3).to(DEV)
+            x = torch.randn(3, 200, 80, device=DEV, requires_grad=True)
+            run_new = lambda n, t: n(t)
+            run_ref = lambda n, t: n.layers(t.transpose(1, 2)).transpose(1, 2)
+        else:
+            net = M.EncoderPreNet(40, 128, dropout=0.0).to(DEV)
+            x = torch.randn(3, 64, 128, device=DEV, requires_grad=True)      # (the embedding output)
+            run_new = lambda n, t: M._conv_stack_tokens_last(n.convolutions, t)
+            run_ref = lambda n, t: n.convolutions(t.transpose(1, 2)).transpose(1, 2)
+        ref_net = copy.deepcopy(net)
+        x_ref = x.detach().clone().requires_grad_(True)
+        net.train(); ref_net.train()
+        y, y_ref = run_new(net, x), run_ref(ref_net, x_ref)
+        g = torch.randn_like(y)
+        y.backward(g); y_ref.backward(g)
+        assert rel_l2(y, y_ref) <= 1e-5 and rel_l2(x.grad, x_ref.grad) <= 1e-5
+        # (the bias of a convolution that feeds a batch-norm has a mathematically zero gradient - rounding noise on both sides -, so the
+        # distance is measured against the largest gradient of the net, not against the tensor itself)
+        scale = max(b.grad.norm().item() for b in ref_net.parameters() if b.grad is not None)
+        for (name, a), (_, b) in zip(net.named_parameters(), ref_net.named_parameters()):
+            if b.grad is None:      # (the pre-net's embedding / projection are not part of the stack)
+                assert a.grad is None, name
+                continue
+            assert (a.grad - b.grad).norm().item() <= 1e-4 * max(b.grad.norm().item(), 1e-3 * scale), name
+        for (name, a), (_, b) in zip(net.named_buffers(), ref_net.named_buffers()):
+            assert torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-6), name      # running_mean / running_var / num_batches_tracked
+        net.eval(); ref_net.eval()
+        assert rel_l2(run_new(net, x.detach()), run_ref(ref_net, x.detach())) <= 1e-5
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
