@@ -486,6 +486,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lsh_attn_bwd_kernel(const Attn
 // dq_b is written for every slot when bucket == 128, and only for slots in even chunks when bucket == 64
 // (the chunk index comes from `undo`).
 // ---------------------------------------------------------------------------------------------------------------------
+// RC > 0: the number of rounds is a compile-time constant, so the R `undo` words and all 3 R 16-byte slices of a row are requested
+// before anything is added (as in lsh_merge_fwd_kernel: with a rolled loop every round waited for its own `undo` word and then
+// for the conditional dq_b load - one dependent chain of three loads per round, 3.9 TB/s).  RC == 0: any R, rolled.
+template <int RC>
 __global__ void __launch_bounds__(256) lsh_grad_reduce_kernel(const __nv_bfloat16* __restrict__ dqk_main, const __nv_bfloat16* __restrict__ dq_b,
                                                               const __nv_bfloat16* __restrict__ dvr, const int32_t* __restrict__ undo,
                                                               __nv_bfloat16* __restrict__ dqk, __nv_bfloat16* __restrict__ dv, int64_t ld, int T, int H, int R,
@@ -500,13 +504,36 @@ __global__ void __launch_bounds__(256) lsh_grad_reduce_kernel(const __nv_bfloat1
     acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
     acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
   };
-  for (int r = 0; r < R; ++r) {
-    const int64_t idx = (bh * R + r) * T + t;
-    add8(aq, __ldg(reinterpret_cast<const uint4*>(dqk_main + idx * kBDh) + c));
-    add8(av, __ldg(reinterpret_cast<const uint4*>(dvr + idx * kBDh) + c));
-    bool has_b = true;
-    if (bucket == 64) has_b = ((__ldg(undo + idx) >> 6) & 1) == 0;
-    if (has_b) add8(aq, __ldg(reinterpret_cast<const uint4*>(dq_b + idx * kBDh) + c));
+  if (RC > 0) {
+    constexpr int N = RC > 0 ? RC : 1;
+    const int64_t idx0 = bh * RC * T + t;
+    bool has_b[N];
+    uint4 um[N], uv[N], ub[N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) has_b[r] = bucket != 64 || ((__ldg(undo + idx0 + static_cast<int64_t>(r) * T) >> 6) & 1) == 0;
+#pragma unroll
+    for (int r = 0; r < N; ++r) um[r] = __ldg(reinterpret_cast<const uint4*>(dqk_main + (idx0 + static_cast<int64_t>(r) * T) * kBDh) + c);
+#pragma unroll
+    for (int r = 0; r < N; ++r) uv[r] = __ldg(reinterpret_cast<const uint4*>(dvr + (idx0 + static_cast<int64_t>(r) * T) * kBDh) + c);
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+      ub[r] = has_b[r] ? __ldg(reinterpret_cast<const uint4*>(dq_b + (idx0 + static_cast<int64_t>(r) * T) * kBDh) + c) : make_uint4(0u, 0u, 0u, 0u);
+    // (same order of additions as the rolled form: main, v, b per round)
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      add8(aq, um[r]);
+      add8(av, uv[r]);
+      if (has_b[r]) add8(aq, ub[r]);
+    }
+  } else {
+    for (int r = 0; r < R; ++r) {
+      const int64_t idx = (bh * R + r) * T + t;
+      add8(aq, __ldg(reinterpret_cast<const uint4*>(dqk_main + idx * kBDh) + c));
+      add8(av, __ldg(reinterpret_cast<const uint4*>(dvr + idx * kBDh) + c));
+      bool has_b = true;
+      if (bucket == 64) has_b = ((__ldg(undo + idx) >> 6) & 1) == 0;
+      if (has_b) add8(aq, __ldg(reinterpret_cast<const uint4*>(dq_b + idx * kBDh) + c));
+    }
   }
   const int64_t b = bh / H;
   const int h = static_cast<int>(bh - b * H);
@@ -571,8 +598,17 @@ extern "C" int rtts_lsh_grad_reduce(const void* dqk_main, const void* dq_b, cons
   RTTS_REQUIRE(bucket == 128 || (bucket == 64 && undo), "rtts_lsh_grad_reduce: bucket 64 needs undo");
   const int64_t rows = static_cast<int64_t>(B) * H * T;
   const int64_t blocks = (rows * 8 + 255) / 256;
-  lsh_grad_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dqk_main), static_cast<const __nv_bfloat16*>(dq_b), static_cast<const __nv_bfloat16*>(dv_rounds), undo, static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), ld, T, H, R, bucket, rows);
+  const auto launch = [&](auto kernel) {
+    kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dqk_main), static_cast<const __nv_bfloat16*>(dq_b), static_cast<const __nv_bfloat16*>(dv_rounds), undo,
+        static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), ld, T, H, R, bucket, rows);
+  };
+  switch (R) {      // the reference configs use 8 (RP / HF default) and 4 (long-sequence sweep) hash rounds
+    case 8: launch(lsh_grad_reduce_kernel<8>); break;
+    case 4: launch(lsh_grad_reduce_kernel<4>); break;
+    case 2: launch(lsh_grad_reduce_kernel<2>); break;
+    default: launch(lsh_grad_reduce_kernel<0>); break;
+  }
   return check_launch("rtts_lsh_grad_reduce");
 }
 
