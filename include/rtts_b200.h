@@ -158,6 +158,23 @@ int rtts_gemm_bf16_dropout(const void* A, int64_t lda, int a_mn_major, const voi
                            const uint8_t* keep_mask, int64_t ldkeep, float keep_scale, int M, int N, int K, int epilogue,
                            int split_k, void* stream);
 
+/* ---- dense decoder -> encoder attention core (nn.MultiheadAttention's softmax(QK^T / sqrt(dh)) V) ----------
+ * Replaces the attention core of ref:reformer_tts/model/reformer.py:161-186 (torch.nn.MultiheadAttention.forward with
+ * key_padding_mask and attention dropout).  q [B,T,H*dh], k / v [B,S,..] (head h at column h*dh, row pitch ldkv), all bf16,
+ * token-major; keep uint8 [B,S] (1 = valid key, NULL = all valid); T a multiple of 128, S a multiple of 32 up to 256, dh = 64.
+ * Dropout (p_drop > 0) drops normalised probabilities by a counter-based hash of (*seed, element): the same mask is
+ * regenerated by every call given the same device seed word.  out bf16 [B,T,H*dh]; lse fp32 [B,H,T] (log2 domain: max * scale *
+ * log2(e) + log2(row sum)), consumed by rtts_xattn_bwd. */
+int rtts_xattn_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const uint8_t* keep, float scale, float p_drop,
+                   const uint64_t* seed, void* out, int64_t ldo, float* lse, int B, int T, int S, int H, int dh, void* stream);
+
+/* Backward of rtts_xattn_fwd (scores recomputed in-kernel from q, k and lse).  dout bf16 [B,T,H*dh]; delta fp32 [B,H,T] =
+ * <dout, out> per (b,h,t) (rtts_lsh_delta).  dq bf16 [B,T,H*dh] is written; dk / dv fp32 [B,S,..] (head h at column h*dh, row
+ * pitch lddkv) are ACCUMULATED into (zero them first): every 128-query tile adds its partial sums with vector reductions. */
+int rtts_xattn_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const uint8_t* keep, float scale, float p_drop,
+                   const uint64_t* seed, const void* dout, int64_t lddo, const float* lse, const float* delta, void* dq, int64_t lddq,
+                   float* dk, float* dv, int64_t lddkv, int B, int T, int S, int H, int dh, void* stream);
+
 /* ---- small fused element-wise helpers used by the host mirror -------------------------------- */
 
 /* Column sums of a bf16 matrix (row pitch ld elements): colsum fp32 [cols] += sum_rows x[r, :].  Bias gradients of gradient matrices

@@ -40,6 +40,8 @@ SIGNATURES = {
     "rtts_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "rtts_layernorm_bwd_acc": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "rtts_gemm_bf16": [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P],
+    "rtts_xattn_fwd": [_P, _L, _P, _P, _L, _P, _F, _F, _P, _P, _L, _P, _I, _I, _I, _I, _I, _P],
+    "rtts_xattn_bwd": [_P, _L, _P, _P, _L, _P, _F, _F, _P, _P, _L, _P, _P, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _P],
     "rtts_colsum_bf16": [_P, _L, _P, _I, _I, _P],
     "rtts_cast_bf16_colsum": [_P, _P, _P, _I, _I, _P],
     "rtts_cast_bf16_colsum_dropout": [_P, _P, _F, _P, _P, _I, _I, _P],

@@ -11,7 +11,7 @@ HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 LIB = HERE.parent / (os.environ.get("RTTS_LIB_NAME") or "libreformer_b200.so")      # RTTS_LIB_NAME + RTTS_DEFS: experiment builds beside the product library
 OBJ_DIR = HERE / ("build" if not os.environ.get("RTTS_LIB_NAME") else "build_" + os.environ["RTTS_LIB_NAME"].replace(".so", ""))
-SOURCES = ["api.cu", "lsh_bucket.cu", "lsh_hash_tc.cu", "lsh_attn_fwd.cu", "lsh_attn_fwd64.cu", "lsh_attn_fwd64p.cu", "lsh_attn_bwd.cu", "gemm.cu", "rowwise.cu"]
+SOURCES = ["api.cu", "lsh_bucket.cu", "lsh_hash_tc.cu", "lsh_attn_fwd.cu", "lsh_attn_fwd64.cu", "lsh_attn_fwd64p.cu", "lsh_attn_bwd.cu", "gemm.cu", "rowwise.cu", "xattn.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",
          "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"), "-I", str(HERE)]

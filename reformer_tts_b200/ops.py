@@ -335,6 +335,47 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     return out
 
 
+def xattn_supported(t: int, s: int, dh: int) -> bool:
+    """Shapes the dense cross-attention kernels take (rtts_xattn_fwd / _bwd)."""
+    return dh == 64 and t % 128 == 0 and s % 32 == 0 and 32 <= s <= 256
+
+
+def _xattn_args(q, k, v, keep, n_heads):
+    _check(q, torch.bfloat16, "q"); _check(k, torch.bfloat16, "k"); _check(v, torch.bfloat16, "v")
+    b, t, d = q.shape
+    s = k.shape[1]
+    assert q.stride(2) == 1 and q.stride(0) == t * q.stride(1) and k.stride(2) == 1 and v.stride() == k.stride() and k.stride(0) == s * k.stride(1)
+    if keep is not None:
+        _check(keep, torch.uint8, "keep")
+        assert keep.is_contiguous() and keep.shape == (b, s)
+    return b, t, s, d // n_heads
+
+
+def xattn_fwd(q, k, v, keep, n_heads: int, scale: float, p_drop: float = 0.0, seed: Optional[torch.Tensor] = None):
+    """softmax(q k^T scale) v per head with key padding (keep uint8 [B,S], 1 = valid) and probability dropout keyed by the device
+    word ``seed`` (int64 [1]).  q [B,T,D], k / v [B,S,D] views (bf16, unit inner stride) -> out bf16 [B,T,D], lse fp32 [B,H,T]."""
+    b, t, s, dh = _xattn_args(q, k, v, keep, n_heads)
+    out = torch.empty((b, t, q.shape[2]), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((b, n_heads, t), dtype=torch.float32, device=q.device)
+    _launch("xattn_fwd", "rtts_xattn_fwd", _ptr(q), q.stride(1), _ptr(k), _ptr(v), k.stride(1), _ptr(keep), float(scale), float(p_drop), _ptr(seed),
+            _ptr(out), out.stride(1), _ptr(lse), b, t, s, n_heads, dh, _stream())
+    return out, lse
+
+
+def xattn_bwd(q, k, v, keep, n_heads: int, scale: float, p_drop: float, seed, dout, lse, delta):
+    """Backward of xattn_fwd -> dq bf16 [B,T,D], dkv fp32 [B,S,2D] (dk | dv)."""
+    b, t, s, dh = _xattn_args(q, k, v, keep, n_heads)
+    _check(dout, torch.bfloat16, "dout")
+    d = q.shape[2]
+    assert dout.shape == q.shape and dout.stride(2) == 1 and dout.stride(0) == t * dout.stride(1)
+    dq = torch.empty((b, t, d), dtype=torch.bfloat16, device=q.device)
+    dkv = torch.zeros((b, s, 2 * d), dtype=torch.float32, device=q.device)
+    _launch("xattn_bwd", "rtts_xattn_bwd", _ptr(q), q.stride(1), _ptr(k), _ptr(v), k.stride(1), _ptr(keep), float(scale), float(p_drop), _ptr(seed),
+            _ptr(dout), dout.stride(1), _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(1), _ptr(dkv), _ptr(dkv[..., d:]), dkv.stride(1), b, t, s, n_heads, dh,
+            _stream())
+    return dq, dkv
+
+
 def colsum_bf16(x: torch.Tensor, colsum: torch.Tensor) -> torch.Tensor:
     """colsum (fp32 [cols]) += column sums of the bf16 matrix x [rows, cols] (rows may be strided): bias gradients."""
     _check(x, torch.bfloat16, "x")

@@ -472,3 +472,79 @@ def test_colsum_bf16(ops, rows, cols, ld):
     ops.colsum_bf16(x, acc)
     want = x.double().sum(0) + 0.5
     assert (acc.double() - want).abs().max().item() <= 1e-5 * max(1.0, x.double().abs().sum(0).max().item())
+
+
+def _xattn_drop_mask(seed: int, B, H, T, S, p_drop):
+    """The kernels' counter-based dropout mask (csrc/xattn.cu drop_hash), restated with 64-bit integer tensors: keep [B,H,T,S] bool."""
+    M = 0xFFFFFFFF
+    row = torch.arange(B * H * T, dtype=torch.int64).view(B, H, T, 1)
+    pair = torch.arange(S // 2, dtype=torch.int64).view(1, 1, 1, S // 2)
+    x = ((row * (S // 2) + pair) & M) * 0x9E3779B1 + (seed & M) & M
+    x = x & M
+    x ^= x >> 15
+    x = (x * 0x85EBCA77) & M
+    x ^= x >> 13
+    x = (x * 0xC2B2AE3D + ((seed >> 32) & M)) & M
+    x ^= x >> 16
+    thr = int(p_drop * 65536.0)
+    keep = torch.stack(((x & 0xFFFF) >= thr, (x >> 16) >= thr), dim=-1).view(B, H, T, S)
+    return keep
+
+
+@pytest.mark.parametrize("B,T,S,H,pad,p_drop", [(2, 256, 256, 2, True, 0.0), (3, 128, 128, 8, False, 0.15), (2, 1024, 256, 8, True, 0.15), (1, 128, 64, 1, True, 0.0)])
+def test_xattn_forward_backward(ops, B, T, S, H, pad, p_drop):
+    """Dense decoder -> encoder attention core (nn.MultiheadAttention's softmax(QK^T / sqrt(dh)) V with key padding mask and
+    probability dropout, ref:reformer_tts/model/reformer.py:161-186) against the same arithmetic in fp32 with the kernels' operand
+    roundings (bf16 q / k / v / dout, P and dS rounded to bf16 where the kernels store them) and the regenerated dropout mask."""
+    torch.manual_seed(9)
+    D = H * 64
+    q = torch.randn(B, T, D, device=DEV).bfloat16()
+    kv = torch.randn(B, S, 2 * D, device=DEV).bfloat16()
+    dout = torch.randn(B, T, D, device=DEV).bfloat16()
+    keep = None
+    if pad:
+        keep = torch.ones(B, S, dtype=torch.uint8, device=DEV)
+        for b in range(B):
+            keep[b, S - 7 - 13 * b:] = 0
+    seed = torch.tensor([0x1234567_89ABCDE], dtype=torch.int64, device=DEV)
+    scale = 0.125
+    k, v = kv[..., :D], kv[..., D:]
+    out, lse = ops.xattn_fwd(q, k, v, keep, H, scale, p_drop, seed)
+    delta = ops.lsh_delta(dout, out, H)
+    dq, dkv = ops.xattn_bwd(q, k, v, keep, H, scale, p_drop, seed, dout, lse, delta)
+    torch.cuda.synchronize()
+
+    # exact reference (CPU, fp64, autograd) ...
+    qf = q.double().cpu().view(B, T, H, 64).transpose(1, 2).requires_grad_(True)
+    kf = k.double().cpu().reshape(B, S, H, 64).transpose(1, 2).requires_grad_(True)
+    vf = v.double().cpu().reshape(B, S, H, 64).transpose(1, 2).requires_grad_(True)
+    s = qf @ kf.transpose(-1, -2) * scale
+    if keep is not None:
+        s = s.masked_fill(~keep.bool().cpu()[:, None, None, :], float("-inf"))
+    prob = torch.softmax(s, dim=-1)
+    dmask = torch.ones_like(prob)
+    if p_drop > 0:
+        dmask = _xattn_drop_mask(int(seed.item()), B, H, T, S, p_drop).double() / (1.0 - p_drop)
+    ref = (prob * dmask) @ vf
+    go = dout.double().cpu().view(B, T, H, 64).transpose(1, 2)
+    ref.backward(go)
+    # ... and the same arithmetic with a bf16 rounding exactly where the kernels store a bf16 operand: the un-normalised
+    # exponentials (forward), D o P and dS (backward), the outputs
+    with torch.no_grad():
+        r16 = lambda x: x.float().bfloat16().double()
+        sd = s.detach()
+        e = torch.exp(sd - sd.amax(-1, keepdim=True))
+        keep01 = (dmask > 0).double()
+        out_r = r16((r16(e) * keep01) @ vf / e.sum(-1, keepdim=True) / (1.0 - p_drop))
+        dp = go @ vf.transpose(-1, -2)
+        dl = (go * bf16r(out.float()).double().cpu().view(B, T, H, 64).transpose(1, 2)).sum(-1, keepdim=True)       # delta from the stored output
+        pr = prob.detach()
+        ds_r = r16(pr * (dmask * dp - dl) * scale)
+        dq_r, dk_r, dv_r = r16(ds_r @ kf), ds_r.transpose(-1, -2) @ qf, r16(pr * dmask).transpose(-1, -2) @ go
+    lse_ref = torch.logsumexp(s.detach(), dim=-1) / 0.6931471805599453      # log2 domain
+    bh = lambda x: x.double().cpu().view(B, -1, H, 64).transpose(1, 2)
+    assert report("xattn out", bh(out), out_r, ref.detach()) <= TOL
+    assert (lse.double().cpu() - lse_ref).abs().max().item() <= 1e-3
+    assert report("xattn dq", bh(dq), dq_r, qf.grad) <= TOL
+    assert report("xattn dk", bh(dkv[..., :D]), dk_r, kf.grad) <= TOL
+    assert report("xattn dv", bh(dkv[..., D:]), dv_r, vf.grad) <= TOL
