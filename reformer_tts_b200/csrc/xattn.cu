@@ -79,11 +79,13 @@ struct FwdSmem {
   static constexpr int kOffK = kQ * 128;                    // 32 KB
   static constexpr int kOffV = kOffK + kMaxS * 128;         // 32 KB
   static constexpr int kOffBias = kOffV + kMaxS * 128;      // float[256]: 0 / -inf per key
-  static constexpr int kOffBar = kOffBias + kMaxS * 4;
+  static constexpr int kOffXch = kOffBias + kMaxS * 4;      // float[2][128], then uint8[16]: chunk of 16 keys holds a padded key
+  static constexpr int kOffBar = kOffXch + 2 * kQ * 4 + 16;
   static constexpr int kTotal = kOffBar + 32;
 };
 
-__global__ void __launch_bounds__(kQ, 2) xattn_fwd_kernel(const Params p) {
+constexpr int kFwdThreads = 256;        // thread = (query row, half of the keys, half of the output row)
+__global__ void __launch_bounds__(kFwdThreads, 2) xattn_fwd_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -91,8 +93,9 @@ __global__ void __launch_bounds__(kQ, 2) xattn_fwd_kernel(const Params p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::kOffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FwdSmem::kOffBar + 16);
   float* bias = reinterpret_cast<float*>(smem + FwdSmem::kOffBias);
+  float* xch = reinterpret_cast<float*>(smem + FwdSmem::kOffXch);      // [2 halves][128 rows]: row maxima, then row sums
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int t0 = blockIdx.x * kQ, h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.x, b = blockIdx.y, t0 = blockIdx.z * kQ;
   const int S = p.S;
 
   if (tid == 0) {
@@ -101,12 +104,19 @@ __global__ void __launch_bounds__(kQ, 2) xattn_fwd_kernel(const Params p) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 256);
-  load_rows(sbase + FwdSmem::kOffQ, p.q + (static_cast<int64_t>(b) * p.T + t0) * p.ldq + h * kDh, p.ldq, kQ, tid, kQ);
-  load_rows(sbase + FwdSmem::kOffK, p.k + static_cast<int64_t>(b) * S * p.ldkv + h * kDh, p.ldkv, S, tid, kQ);
-  load_rows(sbase + FwdSmem::kOffV, p.v + static_cast<int64_t>(b) * S * p.ldkv + h * kDh, p.ldkv, S, tid, kQ);
+  load_rows(sbase + FwdSmem::kOffQ, p.q + (static_cast<int64_t>(b) * p.T + t0) * p.ldq + h * kDh, p.ldq, kQ, tid, kFwdThreads);
+  load_rows(sbase + FwdSmem::kOffK, p.k + static_cast<int64_t>(b) * S * p.ldkv + h * kDh, p.ldkv, S, tid, kFwdThreads);
+  load_rows(sbase + FwdSmem::kOffV, p.v + static_cast<int64_t>(b) * S * p.ldkv + h * kDh, p.ldkv, S, tid, kFwdThreads);
   cp_async_commit();
-  for (int j = tid; j < S; j += kQ) bias[j] = (p.keep == nullptr || p.keep[static_cast<int64_t>(b) * S + j]) ? 0.f : -INFINITY;
+  for (int j = tid; j < S; j += kFwdThreads) bias[j] = (p.keep == nullptr || p.keep[static_cast<int64_t>(b) * S + j]) ? 0.f : -INFINITY;
   cp_async_wait<0>();
+  __syncthreads();
+  // chunks of 16 keys without a padded key skip the bias (one shared-memory load + add per score otherwise)
+  if (tid < S / 16) {
+    float acc = 0.f;
+    for (int i = 0; i < 16; ++i) acc += bias[tid * 16 + i];
+    reinterpret_cast<uint8_t*>(smem + FwdSmem::kOffXch)[2 * kQ * 4 + tid] = acc < 0.f;
+  }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -125,17 +135,28 @@ __global__ void __launch_bounds__(kQ, 2) xattn_fwd_kernel(const Params p) {
   bar_wait(bars, 0);
   tc_fence_after_sync();
 
-  // thread = query row = TMEM lane
-  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const uint32_t row = static_cast<uint32_t>((b * p.H + h) * p.T + t0 + tid);
+  const int rowi = tid & (kQ - 1), half = tid >> 7;
+  const uint8_t* padded = reinterpret_cast<const uint8_t*>(smem + FwdSmem::kOffXch) + 2 * kQ * 4;
+  const int hs = S >> 1, k0 = half * hs;       // this thread's keys [k0, k0 + hs)
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  const uint32_t row = static_cast<uint32_t>((b * p.H + h) * p.T + t0 + rowi);
   float mx = -INFINITY;
-  for (int c0 = 0; c0 < S; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(t_row + c0, r);
+  for (int c0 = k0; c0 < k0 + hs; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(t_row + c0, r);
     tmem_ld_wait();
+    if (padded[c0 >> 4]) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]) + bias[c0 + i]);
+      for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[i]) + bias[c0 + i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+    }
   }
+  xch[half * kQ + rowi] = mx;
+  __syncthreads();
+  mx = fmaxf(mx, xch[(half ^ 1) * kQ + rowi]);
+  __syncthreads();                          // (the slots are reused for the sums)
   const float neg = -mx * p.c;
   uint32_t seed_lo = 0, seed_hi = 0;
   const bool drop = p.seed != nullptr;
@@ -144,15 +165,20 @@ __global__ void __launch_bounds__(kQ, 2) xattn_fwd_kernel(const Params p) {
     seed_lo = static_cast<uint32_t>(sd);
     seed_hi = static_cast<uint32_t>(sd >> 32);
   }
+  // P blocks are written back over the S columns of the SAME half that have been consumed: keys [k0, k0 + hs) -> columns k0 + (key - k0) / 2
   float sum = 0.f;
-  for (int c0 = 0; c0 < S; c0 += 32) {
-    uint32_t r[32], pk[16];
-    tmem_ld32(t_row + c0, r);
+  for (int c0 = k0; c0 < k0 + hs; c0 += 16) {
+    uint32_t r[16], pk[8];
+    tmem_ld16(t_row + c0, r);
     tmem_ld_wait();
+    if (padded[c0 >> 4]) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float e0 = exp2f(fmaf(__uint_as_float(r[i]) + bias[c0 + i], p.c, neg));
-      float e1 = exp2f(fmaf(__uint_as_float(r[i + 1]) + bias[c0 + i + 1], p.c, neg));
+      for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + bias[c0 + i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      float e0 = exp2f(fmaf(__uint_as_float(r[i]), p.c, neg));
+      float e1 = exp2f(fmaf(__uint_as_float(r[i + 1]), p.c, neg));
       sum += e0 + e1;                      // the normaliser is taken BEFORE the dropout (nn.MultiheadAttention drops normalised probabilities)
       if (drop) {
         const uint32_t hsh = drop_hash(seed_lo, seed_hi, row, static_cast<uint32_t>(c0 + i) >> 1, static_cast<uint32_t>(S) >> 1);
@@ -161,27 +187,33 @@ __global__ void __launch_bounds__(kQ, 2) xattn_fwd_kernel(const Params p) {
       }
       pk[i >> 1] = pack_bf16(e0, e1);
     }
-    tmem_st16(t_row + (c0 >> 1), pk);      // P block of 32 keys -> 16 columns, behind the S columns already consumed
+    tmem_st8(t_row + k0 + ((c0 - k0) >> 1), pk);
   }
+  xch[half * kQ + rowi] = sum;
   tmem_st_wait();
   tc_fence_before_sync();
   __syncthreads();
+  // O: 64 columns that hold neither half's P: behind P of half 0 when the halves are 128 keys wide, else behind all of S
+  const uint32_t col_o = hs >= 128 ? static_cast<uint32_t>(hs >> 1) : static_cast<uint32_t>(S);
   if (warp == 0 && elect_one()) {
     tc_fence_after_sync();
     constexpr uint32_t idesc_o = umma_idesc_bf16(kQ, kDh, false, true);
     const uint32_t v_lo = umma_desc_lo(sbase + FwdSmem::kOffV, 0);
-    for (int j = 0; j < S / 16; ++j) umma_ts_lo(tmem + 128, tmem + 8 * j, v_lo + j * (2048 >> 4), hi, idesc_o, j > 0);
+    for (int j = 0; j < S / 16; ++j) {
+      const int key = 16 * j, hh = key >= hs;
+      umma_ts_lo(tmem + col_o, tmem + hh * hs + ((key - hh * hs) >> 1), v_lo + j * (2048 >> 4), hi, idesc_o, j > 0);
+    }
     umma_commit(bars + 1);
   }
   __syncwarp();
+  sum += xch[(half ^ 1) * kQ + rowi];
   bar_wait(bars + 1, 0);
   tc_fence_after_sync();
   const float inv = p.keep_scale / sum;
-  __nv_bfloat16* orow = p.out + (static_cast<int64_t>(b) * p.T + t0 + tid) * p.ldo + h * kDh;
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
+  __nv_bfloat16* orow = p.out + (static_cast<int64_t>(b) * p.T + t0 + rowi) * p.ldo + h * kDh + half * 32;
+  {
     uint32_t r[32];
-    tmem_ld32(t_row + 128 + hh * 32, r);
+    tmem_ld32(t_row + col_o + half * 32, r);
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -190,17 +222,17 @@ __global__ void __launch_bounds__(kQ, 2) xattn_fwd_kernel(const Params p) {
       u.y = pack_bf16(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv);
       u.z = pack_bf16(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv);
       u.w = pack_bf16(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv);
-      reinterpret_cast<uint4*>(orow)[hh * 4 + i] = u;
+      reinterpret_cast<uint4*>(orow)[i] = u;
     }
   }
-  p.lse[row] = fmaf(mx, p.c, log2f(sum));
+  if (half == 0) p.lse[row] = fmaf(mx, p.c, log2f(sum));
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 // ------------------------------------------------------------------------------------------------------------ backward
-constexpr int kBwdThreads = 256;        // thread = (query row, half of the keys)
+constexpr int kBwdThreads = 512;        // thread = (query row, quarter of the keys)
 struct BwdSmem {
   static constexpr int kOffQ = 0;                           // 16 KB   Q tile      [128 queries x 64]
   static constexpr int kOffDO = kOffQ + kQ * 128;           // 16 KB   dO tile
@@ -210,8 +242,8 @@ struct BwdSmem {
   static constexpr int kOffDS = kOffV + kMaxS * 128;        // 64 KB   dS          4 atoms of 64 keys
   static constexpr int kOffDP = kOffDS + 4 * kAtom;         // 64 KB   D o P
   static constexpr int kOffBias = kOffDP + 4 * kAtom;       // float[256]
-  static constexpr int kOffBar = kOffBias + kMaxS * 4;
-  static constexpr int kTotal = kOffBar + 32;
+  static constexpr int kOffBar = kOffBias + kMaxS * 4;      // 2 barriers, the TMEM slot, uint8[16] chunk flags
+  static constexpr int kTotal = kOffBar + 48;
   static_assert(kTotal <= 232448, "shared memory budget of one CTA (227 KB)");
 };
 
@@ -225,7 +257,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) xattn_bwd_kernel(const Params 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffBar + 16);
   float* bias = reinterpret_cast<float*>(smem + L::kOffBias);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int t0 = blockIdx.x * kQ, h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.x, b = blockIdx.y, t0 = blockIdx.z * kQ;
   const int S = p.S;
 
   if (tid == 0) {
@@ -241,6 +273,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) xattn_bwd_kernel(const Params 
   cp_async_commit();
   for (int j = tid; j < S; j += kBwdThreads) bias[j] = (p.keep == nullptr || p.keep[static_cast<int64_t>(b) * S + j]) ? 0.f : -INFINITY;
   cp_async_wait<0>();
+  __syncthreads();
+  if (tid < S / 16) {
+    float acc = 0.f;
+    for (int i = 0; i < 16; ++i) acc += bias[tid * 16 + i];
+    smem[L::kOffBar + 24 + tid] = acc < 0.f;      // chunk of 16 keys holds a padded key
+  }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -260,7 +298,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) xattn_bwd_kernel(const Params 
     umma_commit(bars);
   }
   __syncwarp();
-  const int rowi = tid & (kQ - 1), half = tid >> 7;
+  const int rowi = tid & (kQ - 1), quarter = tid >> 7;
   const uint32_t row = static_cast<uint32_t>((b * p.H + h) * p.T + t0 + rowi);
   const float lse = p.lse[row], dl = p.delta[row];
   uint32_t seed_lo = 0, seed_hi = 0;
@@ -273,17 +311,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) xattn_bwd_kernel(const Params 
   bar_wait(bars, 0);
   tc_fence_after_sync();
   const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const int hs = S >> 1;               // keys per thread
-  for (int c0 = half * hs; c0 < (half + 1) * hs; c0 += 32) {
-    uint32_t r[32], d[32];
-    tmem_ld32(t_row + c0, r);
-    tmem_ld32(t_row + 256 + c0, d);
+  const int qs = S >> 2;               // keys per thread (a multiple of 16)
+  for (int c0 = quarter * qs; c0 < (quarter + 1) * qs; c0 += 16) {
+    uint32_t r[16], d[16];
+    tmem_ld16(t_row + c0, r);
+    tmem_ld16(t_row + 256 + c0, d);
     tmem_ld_wait();
-    uint32_t ds[16], pd[16];
+    uint32_t ds[8], pd[8];
+    if (smem[L::kOffBar + 24 + (c0 >> 4)]) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const float p0 = exp2f(fmaf(__uint_as_float(r[i]) + bias[c0 + i], p.c, -lse));
-      const float p1 = exp2f(fmaf(__uint_as_float(r[i + 1]) + bias[c0 + i + 1], p.c, -lse));
+      for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + bias[c0 + i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float p0 = exp2f(fmaf(__uint_as_float(r[i]), p.c, -lse));
+      const float p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), p.c, -lse));
       float m0 = 1.f, m1 = 1.f;        // D = keep / (1 - p)
       if (drop) {
         const uint32_t hsh = drop_hash(seed_lo, seed_hi, row, static_cast<uint32_t>(c0 + i) >> 1, static_cast<uint32_t>(S) >> 1);
@@ -295,11 +337,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) xattn_bwd_kernel(const Params 
       ds[i >> 1] = pack_bf16(g0, g1);
       pd[i >> 1] = pack_bf16(p0 * m0, p1 * m1);
     }
-    // 32 keys = four 16-byte pieces of row `rowi` in the atom of these keys
+    // 16 keys = two 16-byte pieces of row `rowi` in the atom of these keys
     const uint32_t a_ds = sbase + L::kOffDS + (c0 >> 6) * L::kAtom, a_dp = sbase + L::kOffDP + (c0 >> 6) * L::kAtom;
     const int piece0 = (c0 & 63) >> 3;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
       sts128(a_ds + sw128_offset(rowi, piece0 + i), make_uint4(ds[4 * i], ds[4 * i + 1], ds[4 * i + 2], ds[4 * i + 3]));
       sts128(a_dp + sw128_offset(rowi, piece0 + i), make_uint4(pd[4 * i], pd[4 * i + 1], pd[4 * i + 2], pd[4 * i + 3]));
     }
@@ -329,40 +371,46 @@ __global__ void __launch_bounds__(kBwdThreads, 1) xattn_bwd_kernel(const Params 
   __syncwarp();
   bar_wait(bars + 1, 0);
   tc_fence_after_sync();
-  if (half == 0) {
-    // dQ row -> bf16
-    __nv_bfloat16* qrow = p.dq + (static_cast<int64_t>(b) * p.T + t0 + rowi) * p.lddq + h * kDh;
+  if (quarter < 2) {
+    // dQ row -> bf16 (a half row per thread)
+    __nv_bfloat16* qrow = p.dq + (static_cast<int64_t>(b) * p.T + t0 + rowi) * p.lddq + h * kDh + quarter * 32;
+    uint32_t r[32];
+    tmem_ld32(t_row + quarter * 32, r);
+    tmem_ld_wait();
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      uint32_t r[32];
-      tmem_ld32(t_row + hh * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1]));
-        u.y = pack_bf16(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
-        u.z = pack_bf16(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]));
-        u.w = pack_bf16(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
-        reinterpret_cast<uint4*>(qrow)[hh * 4 + i] = u;
-      }
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      u.x = pack_bf16(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1]));
+      u.y = pack_bf16(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
+      u.z = pack_bf16(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]));
+      u.w = pack_bf16(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
+      reinterpret_cast<uint4*>(qrow)[i] = u;
     }
   }
-  // dK (half 0) / dV (half 1): lane = key of the block; the tile's partial sums are added to the fp32 gradient
-  for (int m = 0; m < nblk; ++m) {
+  // quarter a of the threads takes accumulator a (dK block 0 | dK block 1 | dV block 0 | dV block 1): lane = key of the block; the tile's
+  // partial sums are added to the fp32 gradient (CTAs that run together belong to different (batch, head) pairs: the query tile is the
+  // slowest grid dimension, so the eight partial sums of an element do not queue up on one L2 address)
+  {
+    const int m = quarter & 1, is_v = quarter >> 1;
     const int key = m * 128 + rowi;
-    float* g = (half == 0 ? p.dk : p.dv) + (static_cast<int64_t>(b) * S + key) * p.lddkv + h * kDh;
+    if (m < nblk) {
+      float* g = (is_v ? p.dv : p.dk) + (static_cast<int64_t>(b) * S + key) * p.lddkv + h * kDh;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      uint32_t r[32];
-      tmem_ld32(t_row + (half == 0 ? 64 : 192) + 64 * m + hh * 32, r);
-      tmem_ld_wait();
-      if (key < S) {
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld32(t_row + (is_v ? 192 : 64) + 64 * m + hh * 32, r);
+        tmem_ld_wait();
+#ifdef XA_NORED
+        if (key < -1) {
+#else
+        if (key < S) {
+#endif
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + hh * 32 + 4 * i), "f"(__uint_as_float(r[4 * i])), "f"(__uint_as_float(r[4 * i + 1])),
-                       "f"(__uint_as_float(r[4 * i + 2])), "f"(__uint_as_float(r[4 * i + 3]))
-                       : "memory");
+          for (int i = 0; i < 8; ++i)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + hh * 32 + 4 * i), "f"(__uint_as_float(r[4 * i])), "f"(__uint_as_float(r[4 * i + 1])),
+                         "f"(__uint_as_float(r[4 * i + 2])), "f"(__uint_as_float(r[4 * i + 3]))
+                         : "memory");
+        }
       }
     }
   }
@@ -409,7 +457,8 @@ extern "C" int rtts_xattn_fwd(const void* q, int64_t ldq, const void* k, const v
     if (e != cudaSuccess) return fail(kErrCuda, "rtts_xattn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  xa::xattn_fwd_kernel<<<dim3(T / xa::kQ, H, B), xa::kQ, xa::FwdSmem::kTotal, static_cast<cudaStream_t>(stream)>>>(p);
+  // (the query tile is the slowest grid dimension: CTAs that run together then belong to different (batch, head) pairs)
+  xa::xattn_fwd_kernel<<<dim3(H, B, T / xa::kQ), xa::kFwdThreads, xa::FwdSmem::kTotal, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("rtts_xattn_fwd");
 }
 
@@ -444,6 +493,6 @@ extern "C" int rtts_xattn_bwd(const void* q, int64_t ldq, const void* k, const v
     if (e != cudaSuccess) return fail(kErrCuda, "rtts_xattn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  xa::xattn_bwd_kernel<<<dim3(T / xa::kQ, H, B), xa::kBwdThreads, xa::BwdSmem::kTotal, static_cast<cudaStream_t>(stream)>>>(p);
+  xa::xattn_bwd_kernel<<<dim3(H, B, T / xa::kQ), xa::kBwdThreads, xa::BwdSmem::kTotal, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("rtts_xattn_bwd");
 }

@@ -12,8 +12,10 @@ def t(f,n=20):
     for _ in range(n): f()
     b.record(); torch.cuda.synchronize(); return a.elapsed_time(b)*1e3/n
 out,lse=ops.xattn_fwd(q,k,v,keep,H,0.125,0.15,seed); delta=ops.lsh_delta(do,out,H)
-print('xattn_fwd us', t(lambda: ops.xattn_fwd(q,k,v,keep,H,0.125,0.15,seed)))
-print('xattn_bwd us', t(lambda: ops.xattn_bwd(q,k,v,keep,H,0.125,0.15,seed,do,lse,delta)))
+print('xattn_fwd us', t(lambda: ops.xattn_fwd(q,k,v,keep,H,0.125,0.15,seed)), ' no dropout', t(lambda: ops.xattn_fwd(q,k,v,keep,H,0.125,0.0,None)), ' no mask', t(lambda: ops.xattn_fwd(q,k,v,None,H,0.125,0.0,None)))
+print('xattn_bwd us', t(lambda: ops.xattn_bwd(q,k,v,keep,H,0.125,0.15,seed,do,lse,delta)), ' no dropout', t(lambda: ops.xattn_bwd(q,k,v,keep,H,0.125,0.0,None,do,lse,delta)))
+import sys as _s
+if len(_s.argv) > 1: raise SystemExit
 import torch.nn.functional as F
 ql=q.view(B,T,H,64).transpose(1,2).detach().requires_grad_(True); kl=k.reshape(B,S,H,64).transpose(1,2).detach().requires_grad_(True); vl=v.reshape(B,S,H,64).transpose(1,2).detach().requires_grad_(True)
 km=keep.bool()[:,None,None,:]
