@@ -150,7 +150,8 @@ err = max(gerr, max((a - c).abs().max().item() for a, c in zip(model_g.parameter
 flat = torch.cat([p.detach().reshape(-1) for p in model_g.parameters()])
 other = flat.clone(); dist.all_reduce(other, op=dist.ReduceOp.MAX)
 same = float((flat - other).abs().max())      # replicas stay identical: every rank applied the same averaged gradient
-print("DDP_RESULT", rank, err, same, float(g.grad_norm), float(e.grad_norm), flush=True)
+# (one file per rank: two ranks printing at the same moment interleave their lines on the shared stdout)
+open(os.path.join(sys.argv[2], f"result_{rank}.txt"), "w").write(" ".join(str(x) for x in ("DDP_RESULT", rank, err, same, float(g.grad_norm), float(e.grad_norm))))
 torch.cuda.synchronize(); dist.barrier(); os._exit(0)
 """
 
@@ -162,10 +163,10 @@ def test_data_parallel_graph_replay_equals_eager_overlapped_path_on_two_gpus(tmp
     script = tmp_path / "ddp_worker.py"
     script.write_text(_DDP_WORKER)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29611", str(script), ROOT], capture_output=True, text=True, timeout=900)
+                          "--master-port", "29611", str(script), ROOT, str(tmp_path)], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    results = [l.split() for l in out.stdout.splitlines() if l.startswith("DDP_RESULT")]
-    assert len(results) == 2
+    results = [(tmp_path / f"result_{r}.txt").read_text().split() for r in range(2)]
+    assert all(r[0] == "DDP_RESULT" for r in results)
     for _, rank, err, same, gn_g, gn_e in results:
         assert float(err) <= 1e-4 and float(same) == 0.0, results      # err = max(gradient rel-L2 of step 1, max |parameter difference| / 30)
         assert abs(float(gn_g) - float(gn_e)) <= 1e-3 * float(gn_e)
