@@ -29,6 +29,7 @@ constexpr int kMaxS = 256;              // keys (all of them resident)
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct Params {
+  long long* trace;                             // debug: clock64 stamps of CTA (0,0,0) (nullable)
   const __nv_bfloat16* q;  int64_t ldq;          // [B, T, H*64]
   const __nv_bfloat16* k;  const __nv_bfloat16* v;  int64_t ldkv;      // [B, S, ...]: head h at column h*64 of each
   const uint8_t* keep;                           // [B, S] 1 = valid key (nullable)
@@ -56,6 +57,12 @@ __device__ __forceinline__ uint32_t drop_hash(uint32_t seed_lo, uint32_t seed_hi
   x ^= x >> 16;
   return x;
 }
+
+#ifdef RTTS_TRACE
+#define XA_STAMP(k) do { if (p.trace != nullptr && blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == 0) p.trace[k] = clock64(); } while (0)
+#else
+#define XA_STAMP(k) do { } while (0)
+#endif
 
 __device__ __forceinline__ void load_rows(uint32_t s_tile, const __nv_bfloat16* g, int64_t ld, int rows, int tid, int nthreads) {
   // rows x 128 B -> SWIZZLE_128B tile (16-byte cp.async pieces)
@@ -98,6 +105,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) xattn_fwd_kernel(const Params 
   const int h = blockIdx.x, b = blockIdx.y, t0 = blockIdx.z * kQ;
   const int S = p.S;
 
+  XA_STAMP(0);
   if (tid == 0) {
     mbar_init(bars, 1);
     mbar_init(bars + 1, 1);
@@ -108,6 +116,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) xattn_fwd_kernel(const Params 
   load_rows(sbase + FwdSmem::kOffK, p.k + static_cast<int64_t>(b) * S * p.ldkv + h * kDh, p.ldkv, S, tid, kFwdThreads);
   load_rows(sbase + FwdSmem::kOffV, p.v + static_cast<int64_t>(b) * S * p.ldkv + h * kDh, p.ldkv, S, tid, kFwdThreads);
   cp_async_commit();
+  XA_STAMP(1);
   for (int j = tid; j < S; j += kFwdThreads) bias[j] = (p.keep == nullptr || p.keep[static_cast<int64_t>(b) * S + j]) ? 0.f : -INFINITY;
   cp_async_wait<0>();
   __syncthreads();
@@ -122,6 +131,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) xattn_fwd_kernel(const Params 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  XA_STAMP(2);
   constexpr uint32_t hi = umma_desc_hi_sw128(1024);
 
   if (warp == 0 && elect_one()) {
@@ -134,6 +144,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) xattn_fwd_kernel(const Params 
   __syncwarp();
   bar_wait(bars, 0);
   tc_fence_after_sync();
+  XA_STAMP(3);
 
   const int rowi = tid & (kQ - 1), half = tid >> 7;
   const uint8_t* padded = reinterpret_cast<const uint8_t*>(smem + FwdSmem::kOffXch) + 2 * kQ * 4;
@@ -153,6 +164,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) xattn_fwd_kernel(const Params 
       for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
     }
   }
+  XA_STAMP(4);
   xch[half * kQ + rowi] = mx;
   __syncthreads();
   mx = fmaxf(mx, xch[(half ^ 1) * kQ + rowi]);
@@ -189,6 +201,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) xattn_fwd_kernel(const Params 
     }
     tmem_st8(t_row + k0 + ((c0 - k0) >> 1), pk);
   }
+  XA_STAMP(5);
   xch[half * kQ + rowi] = sum;
   tmem_st_wait();
   tc_fence_before_sync();
@@ -209,6 +222,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) xattn_fwd_kernel(const Params 
   sum += xch[(half ^ 1) * kQ + rowi];
   bar_wait(bars + 1, 0);
   tc_fence_after_sync();
+  XA_STAMP(6);
   const float inv = p.keep_scale / sum;
   __nv_bfloat16* orow = p.out + (static_cast<int64_t>(b) * p.T + t0 + rowi) * p.ldo + h * kDh + half * 32;
   {
@@ -228,6 +242,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) xattn_fwd_kernel(const Params 
   if (half == 0) p.lse[row] = fmaf(mx, p.c, log2f(sum));
   tc_fence_before_sync();
   __syncthreads();
+  XA_STAMP(7);
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
@@ -424,6 +439,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) xattn_bwd_kernel(const Params 
 
 using namespace rtts;
 
+static long long* g_xa_trace = nullptr;
+extern "C" void rtts_debug_set_xattn_trace(void* device_buffer) { g_xa_trace = static_cast<long long*>(device_buffer); }
+
 static int xattn_check(const char* fn, int B, int T, int S, int H, int dh) {
   if (dh != xa::kDh) return fail(kErrBadArg, "%s: head size %d unsupported (64 only)", fn, dh);
   if (B <= 0 || H <= 0 || T <= 0 || T % xa::kQ != 0) return fail(kErrBadArg, "%s: T=%d must be a positive multiple of 128", fn, T);
@@ -451,6 +469,7 @@ extern "C" int rtts_xattn_fwd(const void* q, int64_t ldq, const void* k, const v
   p.scale = scale;
   p.c = scale * xa::kLog2e;
   p.B = B; p.T = T; p.S = S; p.H = H;
+  p.trace = g_xa_trace;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(xa::xattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xa::FwdSmem::kTotal);
