@@ -48,11 +48,24 @@ class GradientBuckets:
                 if own:
                     self._block_bucket[id(block)] = len(groups)
                     groups.append(own)
-        rest = [p for p in params if id(p) not in seen]
-        self.rest_bucket: Optional[int] = None
-        if rest:
-            self.rest_bucket = len(groups)
-            groups.append(rest)
+        # Everything outside the reversible stacks, one bucket per sub-module (module path, two components deep: `postnet.layers`, `dec.prenet`,
+        # `enc.prenet`, `dec.mel_linear`, ...) in parameter order: the modules behind the decoder finish their backward first and the
+        # ones in front of the encoder last, so one bucket for all of them could only be reduced after the whole backward - 45 % of the
+        # gradient bytes with nothing left to overlap them with.  `rest_buckets` lists them; a bucket is reduced as soon as every one of
+        # its parameters has accumulated its gradient (GradientAverager, post-accumulate hooks).
+        names = {id(p): n for n, p in model.named_parameters()}
+        self.rest_buckets: List[int] = []
+        last_key = None
+        for p in params:
+            if id(p) in seen:
+                continue
+            key = ".".join(names.get(id(p), "").split(".")[:-1][:2])      # the owning module's path, two components deep
+            if key != last_key or not self.rest_buckets:
+                self.rest_buckets.append(len(groups))
+                groups.append([])
+                last_key = key
+            groups[-1].append(p)
+        self.rest_bucket: Optional[int] = self.rest_buckets[-1] if self.rest_buckets else None
         self.groups = groups
         bounds, total = [], 0
         for g in groups:
@@ -103,6 +116,14 @@ class GradientAverager:
         self._avg_in_collective = self.world > 1 and dist.get_backend() == "nccl"
         for seq in [m for m in model.modules() if isinstance(m, ReversibleSequence)]:
             seq.on_block_done = self._on_block_done
+        # the buckets outside the reversible stacks: reduced when the last of their parameters has accumulated its gradient
+        self._pending = {}
+        self._hooks = []
+        if self.world > 1:
+            for index in self.buckets.rest_buckets:
+                group = self.buckets.groups[index]
+                for p in group:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, index=index, n=len(group): self._on_param_done(index, n)))
 
     # -- internals -------------------------------------------------------------------------------------------------
     def _reduce(self, index: int, async_op: bool):
@@ -113,6 +134,14 @@ class GradientAverager:
         work = dist.all_reduce(self.buckets.bucket(index), op=op, async_op=async_op)
         if async_op:
             self._works.append(work)
+
+    def _on_param_done(self, index: int, n_params: int):
+        if not (self.overlap and self.sync_enabled and self.world > 1):
+            return
+        left = self._pending.get(index, n_params) - 1
+        self._pending[index] = left
+        if left == 0:
+            self._reduce(index, async_op=True)
 
     def _on_block_done(self, index, block):
         if not (self.overlap and self.sync_enabled and self.world > 1):
@@ -131,6 +160,7 @@ class GradientAverager:
     # -- API -------------------------------------------------------------------------------------------------------
     def finish(self):
         """Call after ``loss.backward()``: reduces what is left and orders the compute stream after every collective."""
+        self._pending.clear()
         if self.world == 1 or not self.sync_enabled:
             self._done.clear()
             return

@@ -298,7 +298,7 @@ net = Net()
 data = torch.randn(6, 5, 8)
 lo, hi = shard_batch(6, dist.get_rank(), 2)
 avg = GradientAverager(net, overlap=(sys.argv[4] == "1"))
-assert avg.buckets.attached() and len(avg.buckets.groups) == 4       # three reversible blocks + everything else
+assert avg.buckets.attached() and len(avg.buckets.groups) == 4       # three reversible blocks + one bucket per module outside the stack (inp)
 # micro-batch 1 of 2: local accumulation only (no collective), micro-batch 2: reduce
 avg.sync_enabled = False
 (0.5 * net(data[lo:hi]) / (hi - lo)).backward()
@@ -426,7 +426,8 @@ def test_gradient_buckets_layout():
     model = _ToyTTS()
     model.stop.weight.requires_grad_(False)
     b = GradientBuckets(model)
-    assert len(b.groups) == 3 and b.rest_bucket == 2                     # two reversible blocks, then everything else
+    # two reversible blocks, then one bucket per module outside the stack in parameter order: inp, mel, stop (bias only)
+    assert len(b.groups) == 5 and b.rest_buckets == [2, 3, 4] and [len(g) for g in b.groups[2:]] == [2, 2, 1]
     assert all(start % 64 == 0 for start, _ in b.bounds) and b.flat.numel() % 64 == 0
     n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
     assert sum(p.numel() for g in b.groups for p in g) == n_train and model.stop.weight.grad is None
