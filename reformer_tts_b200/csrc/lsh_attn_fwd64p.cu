@@ -4,19 +4,21 @@
 // and to the chunk before it).  The unit of work is a TILE = two consecutive chunks (e, e+1) as queries = the 128 lanes of one
 // MMA, against the three chunks (e-1, e, e+1) that hold their keys:
 //     S = [X_e ; X_e+1] [X_e-1 ; X_e ; X_e+1]^T      tcgen05.mma M=128, N=64 (look-back block) + N=128 (main block), K=64
-//     P = exp2(S * key_scale - bound[query])         thread = query row: its 128-key window (columns 0-127 for the rows of
-//                                                    chunk e, 64-191 for chunk e+1), masks on the packed bf16 pairs,
-//                                                    written back over S in TMEM; the 64 columns outside the window are zeroed
+//     P = exp2(S * key_scale - bound[query])         thread = (query row, half of its 128-key window: columns 0-127 for the rows
+//                                                    of chunk e, 64-191 for chunk e+1), masks on the packed bf16 pairs, written
+//                                                    back over S in TMEM; the 64 columns outside the window are zeroed
 //     O = P V,  rowsum = P 1                         tcgen05.mma, A = P from TMEM
-//     out = O / rowsum -> bf16                       the SAME thread (FA-4 layout: no hand-over between roles)
-// A third of the score MMA is spent on (query, key) blocks outside the windows; the tensor pipe has that room (it is ~50 %
-// busy at the kernel's MUFU bound), and in exchange a query row lives on ONE TMEM lane for both of its key chunks: no
-// exchange between lanes, no separate epilogue role, no row-sum or maximum passed through shared memory.
+//     out = O / rowsum -> bf16                       the SAME threads (FA-4 layout: no hand-over between roles)
+// A third of the score MMA is spent on (query, key) blocks outside the windows; the tensor pipe has that room (it is ~30 %
+// busy), and in exchange a query row lives on ONE TMEM lane for both of its key chunks: no exchange between lanes, no
+// separate epilogue role, no row sum or maximum passed through shared memory.
 //
-// Roles (14 warps): warps 0-7 = two groups of four softmax + epilogue warps (group g takes the tiles t = g mod 2: while one
-// group waits for its PV the other computes, and every SM sub-partition runs one warp of each group over the same loop),
-// warps 8-11 loaders (warp w gathers the ring entries e = w mod 4: sticker -> position -> 16-byte cp.async of the qk and v
-// rows into SWIZZLE_128B chunks + per-row metadata), warp 12 issues S, warp 13 issues PV + row sums.
+// Roles (24 warps): warps 0-15 = two groups of eight softmax + epilogue warps (group g owns TMEM region g and takes the tiles
+// t = g mod 2: while one group waits for its PV the other computes; two warps - window halves - per lane quarter and group, so
+// every SM sub-partition runs four of them over the same loop), warps 16-19 K loaders (warp w gathers the K rows + per-row
+// metadata of the ring entries e = w mod 4: sticker -> position -> 16-byte cp.async into SWIZZLE_128B chunks), warps 20-21 V
+// loaders (entries e = w mod 2), warp 22: one thread issuing the look-back block of S, warp 23: one thread issuing PV + row
+// sums of tile t and, chained behind them, the main block of S of tile t+2.
 // Ring entries: every owned chunk, preceded by its cyclic predecessor (keys only) at the start of the run and of every
 // (batch, head) row (the row's LAST chunk: rp's roll).  Entry e lives in data slot e % 8 and metadata slot e % 32.
 // TMEM: region g = columns [256 g, 256 g + 256): S in [0,192), P block of keys 32q..32q+31 in place at [32q, 32q+16),
