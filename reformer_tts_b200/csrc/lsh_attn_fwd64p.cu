@@ -51,9 +51,12 @@ constexpr int kPVWarp = kSWarp + 1;
 constexpr int kThreads = (kPVWarp + 1) * 32;      // 768 threads: up to 80 registers each
 
 constexpr int kSlots = 8;               // ring of gathered chunks (K and V rows), an entry is released by the PV that last reads it
-constexpr int kMetaSlots = 32;          // ring of per-row metadata: an entry is rewritten 32 entries later, which needs the PV of an
-                                        // entry >= 24 later, i.e. of a tile whose predecessors' epilogues (same group: program order;
-                                        // other group: its p_full precedes that PV) are long done - no barrier of its own
+constexpr int kMetaSlots = 32;          // ring of per-row metadata, no barrier of its own: entry x + 32 is written by a K loader after the K slot
+                                        // of entry x + 24 was released, i.e. after both blocks of S(T') of a tile T' >= tile(x) + 8 were issued.
+                                        // Its look-back block waited for o_free(T' - 2) (that group has finished every tile <= T' - 4 in
+                                        // program order), its main block was chained behind PV(T' - 2), issued after PV(T' - 3), which
+                                        // needed p_full(T' - 3) (the other group has finished every tile <= T' - 5): the readers of entry
+                                        // x's metadata - tiles tile(x) and tile(x) + 1, dup scan of the epilogue included - are done
 constexpr uint32_t kColO = 192, kColSum = 16;
 
 struct Smem {
