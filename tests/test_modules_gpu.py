@@ -394,6 +394,45 @@ def test_reversible_recompute_reproduces_rotations_and_dropout():
         assert rel_l2(g_rev[k], g_plain[k]) <= 2e-3, k
 
 
+def test_decoder_recompute_reproduces_the_cross_attention_dropout_mask():
+    """The attention-probability dropout of the cross-attention core is generated inside rtts_xattn_fwd / _bwd from a seed word drawn from
+    the CUDA generator (where nn.MultiheadAttention would draw its mask).  Deterministic's RNG replay must hand the recompute - and the
+    backward kernel - the same word: the reversible gradient of a decoder stack with cross-attention dropout 0.3 and post_attn_dropout
+    0.2 must equal plain autograd through the same sub-networks executed once with the same RNG stream."""
+    from reformer_tts_b200.model import ReformerDec
+    from reformer_tts_b200.model.reversible import ReversibleHalfResidual
+    torch.manual_seed(4)
+    kw = _small_kwargs()["dec_reformer_kwargs"]
+    kw["attn_kwargs"]["dropout"] = 0.3
+    kw["self_attn_kwargs"]["post_attn_dropout"] = 0.2
+    dec = ReformerDec(128, **kw).to(DEV).train()
+    x = torch.randn(2, 256, 128, device=DEV)
+    mem = torch.randn(2, 128, 128, device=DEV)
+    kpm = torch.zeros(2, 128, dtype=torch.bool, device=DEV)
+    kpm[1, 90:] = True
+    dy = torch.randn(2, 256, 128, device=DEV)
+    torch.manual_seed(12)
+    xa, ma = x.clone().requires_grad_(True), mem.clone().requires_grad_(True)
+    dec(xa, ma, key_padding_mask=kpm)[0].backward(dy)
+    g_rev = _grads(dec)
+    dec.zero_grad()
+    # the same computation without reversibility: HalfResidual y1 = x1 + f(x2), then the halves swap; plain autograd, same RNG stream
+    torch.manual_seed(12)
+    xb, mb = x.clone().requires_grad_(True), mem.clone().requires_grad_(True)
+    h1 = h2 = xb
+    for i, blk in enumerate(dec.layers.blocks):
+        if isinstance(blk, ReversibleHalfResidual):
+            extra = dict(key=mb, value=mb, key_padding_mask=kpm) if i % 6 == 2 else {}
+            h1 = h1 + blk.f.net(h2, **extra)
+        else:
+            h1, h2 = h2, h1
+    (h1 + h2).backward(dy)
+    g_plain = _grads(dec)
+    assert rel_l2(xa.grad, xb.grad) <= 2e-3 and rel_l2(ma.grad, mb.grad) <= 2e-3
+    for k in g_plain:
+        assert rel_l2(g_rev[k], g_plain[k]) <= 2e-3, k
+
+
 def test_no_cpu_path():
     from reformer_tts_b200.lsh_attention import LSHSelfAttention
     from reformer_tts_b200.model import FeedForward
