@@ -83,7 +83,7 @@ __device__ __forceinline__ void load_rows(uint32_t s_tile, const __nv_bfloat16* 
 
 __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 16); ++spin) {
+  for (uint32_t spin = 0; spin < (1u << 18); ++spin) {      // 2^18 x 20 us > 5 s: a protocol bug traps instead of hanging the GPU
     if (mbar_try_wait_suspend(bar, parity, 20000u)) return;
   }
   __trap();
