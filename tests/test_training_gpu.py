@@ -69,13 +69,18 @@ def test_graph_replay_equals_eager_steps_with_dropout_and_changing_batches():
     for i in range(3):
         b = _batch(2, 100 + i)
         lg, le = graph.step(b), eager.step(b)
-        assert abs(lg.item() - le.item()) <= 1e-4 * abs(le.item()), (i, lg.item(), le.item())
+        # step 0 starts from identical parameters: the losses agree to rounding.  After an AdamW update the two models differ by up to
+        # lr x 2 on single elements (see below: a last-bit difference of a near-zero gradient - order-dependent fp32 reductions of the
+        # split-K weight gradients and of the cross-attention dK / dV partial sums - becomes a full-size step), so later losses and
+        # gradient norms agree to 2e-3 / 5e-3, not 1e-4 / 1e-3 (a run that happened to draw such an element failed 1 time in ~6 at 1e-4)
+        tol_loss, tol_norm = (1e-4, 1e-3) if i == 0 else (2e-3, 5e-3)
+        assert abs(lg.item() - le.item()) <= tol_loss * abs(le.item()), (i, lg.item(), le.item())
         # the whole gradient (every parameter, after averaging and clipping): only the order of the split-K atomics differs.  With
         # other rotations / dropout masks in the recompute than in the forward this would be O(1).
         # (measured 0.9e-4 .. 1.4e-4 from run to run: red.global.add of the split-K weight gradients is order-dependent)
         if i == 0:
             assert rel_l2(graph.last_grads, eager.last_grads) <= 3e-4
-        assert rel_l2(graph.grad_norm, eager.grad_norm) <= 1e-3
+        assert rel_l2(graph.grad_norm, eager.grad_norm) <= tol_norm
     # Parameters after three AdamW updates: Adam's m / sqrt(v) turns a last-bit difference of a near-zero gradient into a full-size
     # step of that element - in the worst case of opposite sign - so parameters agree to within the largest possible update
     # (3 steps x lr x 2 = 6e-3 per element; measured 3.1e-3 on one element of a pre-net convolution), not to 1e-4.
@@ -143,10 +148,10 @@ g.reseed(40 + rank); e.reseed(40 + rank)
 for i in range(3):
     b = _batch(2, 10 * i + rank)            # every rank its own shard
     lg, le = g.step(b), e.step(b)
-    assert abs(lg.item() - le.item()) <= 1e-4 * abs(le.item()), (i, lg.item(), le.item())
+    assert abs(lg.item() - le.item()) <= (1e-4 if i == 0 else 2e-3) * abs(le.item()), (i, lg.item(), le.item())      # (see the single-GPU test: parameters differ after an AdamW update)
     if i == 0:
         gerr = ((g.last_grads - e.last_grads).norm() / e.last_grads.norm()).item()
-err = max(gerr, max((a - c).abs().max().item() for a, c in zip(model_g.parameters(), model_e.parameters())) / 30)
+err = max(gerr, max((a - c).abs().max().item() for a, c in zip(model_g.parameters(), model_e.parameters())) / 60)
 flat = torch.cat([p.detach().reshape(-1) for p in model_g.parameters()])
 other = flat.clone(); dist.all_reduce(other, op=dist.ReduceOp.MAX)
 same = float((flat - other).abs().max())      # replicas stay identical: every rank applied the same averaged gradient
@@ -168,5 +173,5 @@ def test_data_parallel_graph_replay_equals_eager_overlapped_path_on_two_gpus(tmp
     results = [(tmp_path / f"result_{r}.txt").read_text().split() for r in range(2)]
     assert all(r[0] == "DDP_RESULT" for r in results)
     for _, rank, err, same, gn_g, gn_e in results:
-        assert float(err) <= 1e-4 and float(same) == 0.0, results      # err = max(gradient rel-L2 of step 1, max |parameter difference| / 30)
-        assert abs(float(gn_g) - float(gn_e)) <= 1e-3 * float(gn_e)
+        assert float(err) <= 1e-4 and float(same) == 0.0, results      # err = max(gradient rel-L2 of step 1, max |parameter difference| / 60: 3 AdamW steps x lr x 2 = 6e-3 per element at most)
+        assert abs(float(gn_g) - float(gn_e)) <= 5e-3 * float(gn_e)      # (gradient norm of the third step: the replicas' parameters differ by then)
