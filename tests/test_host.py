@@ -52,6 +52,36 @@ def test_hash_tc_shape_rules_through_the_c_abi():
     assert rc != 0 and b"null pointer" in lib.rtts_last_error()
 
 
+def test_xattn_and_colsum_argument_rules_through_the_c_abi():
+    """Argument validation of the dense cross-attention core and of the bf16 column sum happens before any CUDA call: null pointers,
+    sequence lengths the kernels do not take (T not a multiple of 128; S not a multiple of 32 / 64 or beyond 256), head sizes other
+    than 64 and dropout without a seed word are reported, not launched.  ``ops.xattn_supported`` states the same rules for the host."""
+    import ctypes
+    from reformer_tts_b200 import _lib, ops
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(4096)
+    p = ctypes.cast(buf, ctypes.c_void_p)      # 16-byte aligned host memory: never dereferenced, the calls below fail in validation
+    p = ctypes.c_void_p((p.value + 15) & ~15)
+
+    def fwd(T=1024, S=256, dh=64, p_drop=0.0, seed=None, q=p):
+        return lib.rtts_xattn_fwd(q, 512, p, p, 1024, None, 0.125, p_drop, seed, p, 512, p, 2, T, S, 8, dh, None)
+
+    def bwd(T=1024, S=256, dh=64):
+        return lib.rtts_xattn_bwd(p, 512, p, p, 1024, None, 0.125, 0.0, None, p, 512, p, p, p, 512, p, p, 1024, 2, T, S, 8, dh, None)
+
+    assert fwd(q=None) != 0 and b"null pointer" in lib.rtts_last_error()
+    assert fwd(T=1000) != 0 and b"multiple of 128" in lib.rtts_last_error()
+    assert fwd(S=320) != 0 and fwd(S=48) != 0 and b"S=" in lib.rtts_last_error()
+    assert fwd(dh=32) != 0 and b"head size" in lib.rtts_last_error()
+    assert fwd(p_drop=0.15) != 0 and b"seed" in lib.rtts_last_error()
+    assert bwd(S=96) != 0 and b"multiple of 64" in lib.rtts_last_error()
+    assert bwd(T=64) != 0 and bwd(dh=128) != 0
+    assert ops.xattn_supported(1024, 256, 64) and ops.xattn_supported(128, 64, 64)
+    assert not ops.xattn_supported(1000, 256, 64) and not ops.xattn_supported(1024, 288, 64) and not ops.xattn_supported(1024, 256, 32)
+    assert lib.rtts_colsum_bf16(None, 8, p, 4, 8, None) != 0 and b"null pointer" in lib.rtts_last_error()
+    assert lib.rtts_colsum_bf16(p, 8, p, 4, 12, None) != 0 and b"multiples of 8" in lib.rtts_last_error()
+
+
 def test_product_modules_refuse_cpu_tensors():
     from reformer_tts_b200.lsh_attention import LSHSelfAttention
     with pytest.raises(RuntimeError, match="no CPU path"):
