@@ -239,8 +239,8 @@ def test_rp_layer_post_attn_dropout_in_the_gemm_epilogue():
         assert rel_l2(g_fused[k], g_ref[k]) <= 1e-5, k
 
 
-@pytest.mark.parametrize("pad", [False, True])
-def test_cross_attention_block_equals_multihead_attention(pad):
+@pytest.mark.parametrize("pad,S", [(False, 128), (True, 128), (True, 96)])
+def test_cross_attention_block_equals_multihead_attention(pad, S):
     """WithNorm(LayerNorm, MultiheadAttentionWrapper) (ref:reformer_tts/model/reformer.py:161-186 as built at :122-125) on the
     kernel path against LayerNorm + ``nn.MultiheadAttention`` arithmetic on the CPU in the oracle's operand-rounding mode
     (oracle/rounded.py ``CrossAttentionFn``; tests/test_oracle.py checks that function against stock nn.MultiheadAttention):
@@ -249,7 +249,8 @@ def test_cross_attention_block_equals_multihead_attention(pad):
     from oracle.rounded import set_round_operands
     from reformer_tts_b200.model.reformer import MultiheadAttentionWrapper, WithNorm
     torch.manual_seed(3)
-    dim, heads, B, T, S = 128, 2, 2, 256, 128
+    dim, heads, T = 128, 2, 256
+    B = 4 if S == 96 else 2                # S = 96: a memory length the own core does not take (vendor core, inner autograd graph); B * S % 128 == 0 for the GEMMs
     ours = WithNorm(nn.LayerNorm, dim, MultiheadAttentionWrapper(dim, num_heads=heads)).to(DEV).train()
     _round_weights_to_bf16(ours)
     with torch.no_grad():
@@ -264,8 +265,8 @@ def test_cross_attention_block_equals_multihead_attention(pad):
     kpm = None
     if pad:
         kpm = torch.zeros(B, S, dtype=torch.bool)
-        kpm[0, 100:] = True
-        kpm[1, 77:] = True
+        kpm[0, S - 28:] = True
+        kpm[B - 1, 77:] = True
     xg, mg = x.to(DEV).requires_grad_(True), mem.to(DEV).requires_grad_(True)
     assert ours.fn._kernel_path_ok(xg, mg)
     y = ours(xg, key=mg, value=mg, key_padding_mask=None if kpm is None else kpm.to(DEV))
@@ -280,8 +281,10 @@ def test_cross_attention_block_equals_multihead_attention(pad):
     yr, dxr, dmr, g_ref = run(ref)
     ye, dxe, dme, g_x = run(exact)
     # LayerNorm, projections, dgrad / wgrad and the dense softmax(QK^T)V core (rtts_xattn_fwd / _bwd) are all this library's kernels
-    # at these shapes; oracle/rounded.py CrossAttentionFn rounds where they store bf16 operands.
-    tol = TOL
+    # at the shapes the core takes; oracle/rounded.py CrossAttentionFn rounds where they store bf16 operands.  S = 96 runs the core on
+    # the vendor flash kernel, whose internal roundings are only approximately mirrored: 1.5e-3 there (measured 0.6-1.2e-3).
+    from reformer_tts_b200 import ops as _ops
+    tol = TOL if _ops.xattn_supported(T, S, dim // heads) and S % 64 == 0 else 1.5 * TOL
     assert report("cross y", y, yr, ye) <= tol
     assert report("cross dx", xg.grad, dxr, dxe) <= tol and report("cross dmem", mg.grad, dmr, dme) <= tol
     g_ours = _grads(ours)
